@@ -1,0 +1,361 @@
+// index.cu -- index lifetime: HBM-resident layout, row ingestion, validation.
+//
+// Replaces the load path of castorini/dhr retrieval/gip_retrieval.py:289-315 (pickle.load ->
+// shard slice -> .cuda()).  The caller hands rows in the reference's layout -- values
+// [n, S*G + C] (fp16 as stored by encode.py:156,165 / densify_corpus.py:68-72, or the fp32 copy
+// the CPU path makes at gip_retrieval.py:313) and slice indices [n, S] -- and the index keeps
+// three row-major device arrays:
+//    lexv [N][D_pad] fp16    lexical values, D_pad = S_pad*G
+//    lexi [N][S_pad] codes   uint8 or uint16; all-zero slices are stored as CODE_EMPTY
+//    dns  [N][C_pad] fp16    dense [CLS] block
+#include <mutex>
+#include <string.h>
+#include <string>
+
+#include "internal.h"
+
+namespace dhr {
+
+static thread_local std::string g_last_cuda_error;
+
+void set_cuda_error(cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s: %s (%s) at %s:%d", cudaGetErrorName(e), cudaGetErrorString(e), what, file, line);
+    g_last_cuda_error = buf;
+    cudaGetLastError();   // clear the sticky-less error state
+}
+
+bool is_device_pointer(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+int ensure_device_buffer(void** p, size_t* cur, size_t need) {
+    if (*cur >= need && *p) return DHR_OK;
+    if (*p) { cudaFree(*p); *p = nullptr; *cur = 0; }
+    if (need == 0) return DHR_OK;
+    DHR_CUDA(cudaMalloc(p, need));
+    *cur = need;
+    return DHR_OK;
+}
+
+cudaEvent_t EventPool::get() {
+    if (used == ev.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ev.push_back(e);
+    }
+    return ev[used++];
+}
+void EventPool::destroy() {
+    for (auto e : ev) cudaEventDestroy(e);
+    ev.clear();
+    used = 0;
+}
+
+static int idx_dtype_size(int dt) {
+    switch (dt) {
+        case DHR_IDX_U8: case DHR_IDX_I8: return 1;
+        case DHR_IDX_I16: case DHR_IDX_U16: return 2;
+        case DHR_IDX_I32: return 4;
+        case DHR_IDX_I64: return 8;
+        default: return 0;
+    }
+}
+
+__device__ __forceinline__ long long load_index_value(const void* base, int dtype, size_t off) {
+    switch (dtype) {
+        case DHR_IDX_U8:  return ((const uint8_t*)base)[off];
+        case DHR_IDX_I8:  return ((const int8_t*)base)[off];
+        case DHR_IDX_I16: return ((const int16_t*)base)[off];
+        case DHR_IDX_U16: return ((const uint16_t*)base)[off];
+        case DHR_IDX_I32: return ((const int32_t*)base)[off];
+        default:          return ((const long long*)base)[off];
+    }
+}
+
+__device__ __forceinline__ __half load_value_as_half(const void* base, int dtype, size_t off, bool* lossy) {
+    if (dtype == DHR_VAL_F16) return ((const __half*)base)[off];
+    const float f = ((const float*)base)[off];
+    const __half h = __float2half_rn(f);
+    if (__half2float(h) != f && f == f) *lossy = true;
+    return h;
+}
+
+// one thread per (row, padded slice): G values + the code
+template <typename CodeT>
+__global__ void ingest_lexical_kernel(long long n, int S, int G, int S_pad, int W, int val_dtype, const void* vals,
+                                      long long vstride, int idx_dtype, const void* idx, long long istride,
+                                      __half* lexv, CodeT* lexi, long long row_base, int* flags) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * S_pad) return;
+    const long long r = i / S_pad;
+    const int s = (int)(i % S_pad);
+    __half* out = lexv + ((size_t)(row_base + r) * S_pad + s) * G;
+    CodeT* oc = lexi + (size_t)(row_base + r) * S_pad + s;
+    if (s >= S) {
+        for (int g = 0; g < G; ++g) out[g] = __float2half_rn(0.f);
+        *oc = (CodeT)CodeTraits<CodeT>::kEmpty;
+        return;
+    }
+    bool lossy = false, nonzero = false;
+    for (int g = 0; g < G; ++g) {
+        const __half h = load_value_as_half(vals, val_dtype, (size_t)r * vstride + (size_t)s * G + g, &lossy);
+        out[g] = h;
+        nonzero |= (__half_as_ushort(h) & 0x7FFFu) != 0;
+    }
+    if (lossy) atomicOr(flags + 0, 1);
+    const long long v = load_index_value(idx, idx_dtype, (size_t)r * istride + s);
+    uint32_t code = CodeTraits<CodeT>::kEmpty;
+    if (nonzero) {
+        if (v < 0 || v > (long long)CodeTraits<CodeT>::kMax) { atomicOr(flags + 1, 1); code = CodeTraits<CodeT>::kNoMatch; }
+        else code = (uint32_t)v;
+    }
+    *oc = (CodeT)code;
+}
+
+__global__ void ingest_dense_kernel(long long n, int D, int C, int C_pad, int val_dtype, const void* vals, long long vstride,
+                                    __half* dns, long long row_base, int* flags) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * C_pad) return;
+    const long long r = i / C_pad;
+    const int c = (int)(i % C_pad);
+    bool lossy = false;
+    __half h = __float2half_rn(0.f);
+    if (c < C) h = load_value_as_half(vals, val_dtype, (size_t)r * vstride + D + c, &lossy);
+    dns[(size_t)(row_base + r) * C_pad + c] = h;
+    if (lossy) atomicOr(flags + 0, 1);
+}
+
+static int ingest_device(dhr_index* h, long long n, int val_dtype, const void* d_vals, long long vstride, int idx_dtype,
+                         const void* d_idx, long long istride) {
+    const Geometry& g = h->g;
+    const int W = g.S * g.G + g.C;
+    if (g.S_pad > 0) {
+        const long long total = n * g.S_pad;
+        const unsigned blocks = (unsigned)((total + 255) / 256);
+        if (g.code_bytes == 1)
+            ingest_lexical_kernel<uint8_t><<<blocks, 256>>>(n, g.S, g.G, g.S_pad, W, val_dtype, d_vals, vstride, idx_dtype, d_idx,
+                                                            istride, h->lexv, (uint8_t*)h->lexi, h->n_rows, h->d_flags);
+        else
+            ingest_lexical_kernel<uint16_t><<<blocks, 256>>>(n, g.S, g.G, g.S_pad, W, val_dtype, d_vals, vstride, idx_dtype, d_idx,
+                                                             istride, h->lexv, (uint16_t*)h->lexi, h->n_rows, h->d_flags);
+        DHR_CUDA(cudaGetLastError());
+    }
+    if (g.C_pad > 0) {
+        const long long total = n * g.C_pad;
+        const unsigned blocks = (unsigned)((total + 255) / 256);
+        ingest_dense_kernel<<<blocks, 256>>>(n, g.S * g.G, g.C, g.C_pad, val_dtype, d_vals, vstride, h->dns, h->n_rows, h->d_flags);
+        DHR_CUDA(cudaGetLastError());
+    }
+    return DHR_OK;
+}
+
+}  // namespace dhr
+
+using namespace dhr;
+
+extern "C" {
+
+int dhr_version(void) { return DHR_B200_VERSION; }
+
+const char* dhr_strerror(int status) {
+    switch (status) {
+        case DHR_OK: return "ok";
+        case DHR_ERR_INVALID: return "invalid argument";
+        case DHR_ERR_CUDA: return "CUDA runtime error";
+        case DHR_ERR_NOMEM: return "out of memory";
+        case DHR_ERR_UNSUPPORTED: return "unsupported shape or size";
+        case DHR_ERR_LOSSY: return "fp32 corpus value is not representable in fp16";
+        case DHR_ERR_IDX_RANGE: return "corpus slice index outside the code range";
+        case DHR_ERR_STATE: return "invalid call order for this index";
+        case DHR_ERR_NO_DEVICE: return "no usable CUDA device";
+        default: return "unknown status";
+    }
+}
+
+const char* dhr_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
+
+int dhr_device_count(int* count) {
+    if (!count) return DHR_ERR_INVALID;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { set_cuda_error(e, "cudaGetDeviceCount", __FILE__, __LINE__); *count = 0; return DHR_ERR_NO_DEVICE; }
+    *count = n;
+    return DHR_OK;
+}
+
+int dhr_index_create(dhr_index** out, int device, int64_t cap_rows, int n_slices, int group, int n_dense, int idx_dtype,
+                     int64_t row_offset, unsigned flags) {
+    if (!out || cap_rows < 0 || n_slices < 0 || n_dense < 0 || group < 1 || row_offset < 0) return DHR_ERR_INVALID;
+    if (n_slices == 0 && n_dense == 0) return DHR_ERR_INVALID;
+    if (group > DHR_MAX_GROUP) return DHR_ERR_UNSUPPORTED;
+    if (cap_rows > 0x7FFFFFF0ll) return DHR_ERR_UNSUPPORTED;
+    if (n_slices > 0 && idx_dtype_size(idx_dtype) == 0) return DHR_ERR_INVALID;
+    int ndev = 0;
+    DHR_TRY(dhr_device_count(&ndev));
+    if (device < 0 || device >= ndev) return DHR_ERR_NO_DEVICE;
+    DHR_CUDA(cudaSetDevice(device));
+
+    dhr_index* h = new (std::nothrow) dhr_index();
+    if (!h) return DHR_ERR_NOMEM;
+    h->device = device;
+    h->capacity = cap_rows;
+    h->row_offset = row_offset;
+    h->idx_dtype = n_slices > 0 ? idx_dtype : DHR_IDX_NONE;
+    Geometry& g = h->g;
+    g.S = n_slices; g.G = group; g.C = n_dense;
+    g.S_pad = (int)round_up(n_slices, 16);
+    g.D_pad = g.S_pad * group;
+    g.C_pad = (int)round_up(n_dense, 8);
+    const bool narrow = (flags & DHR_INDEX_NARROW_CODES) != 0;
+    g.code_bytes = (idx_dtype_size(h->idx_dtype) == 1 || narrow || n_slices == 0) ? 1 : 2;
+    g.unit_halves = (group % 8 == 0) ? group : (group % 4 == 0) ? 2 * group : (group % 2 == 0) ? 4 * group : 8 * group;
+    g.unit_slices = g.unit_halves / group;
+    g.n_units = g.S_pad / g.unit_slices;
+    g.n_chunks = g.C_pad / 8;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e == cudaSuccess) h->num_sms = prop.multiProcessorCount;
+    int status = DHR_OK;
+    auto fail = [&](int s) { dhr_index_close(h); return s; };
+    const size_t rows = (size_t)(cap_rows > 0 ? cap_rows : 1);
+    if (g.D_pad > 0) {
+        if (cudaMalloc(&h->lexv, rows * g.D_pad * 2) != cudaSuccess) return fail(DHR_ERR_NOMEM);
+        if (cudaMalloc(&h->lexi, rows * g.S_pad * g.code_bytes) != cudaSuccess) return fail(DHR_ERR_NOMEM);
+    }
+    if (g.C_pad > 0 && cudaMalloc(&h->dns, rows * g.C_pad * 2) != cudaSuccess) return fail(DHR_ERR_NOMEM);
+    if (cudaMalloc(&h->d_flags, 4 * sizeof(int)) != cudaSuccess) return fail(DHR_ERR_NOMEM);
+    if (cudaMemset(h->d_flags, 0, 4 * sizeof(int)) != cudaSuccess) return fail(DHR_ERR_CUDA);
+    *out = h;
+    return status;
+}
+
+int dhr_index_append(dhr_index* h, int64_t n, int val_dtype, const void* vals, int64_t vstride, int idx_dtype,
+                     const void* idx, int64_t istride) {
+    if (!h || n < 0) return DHR_ERR_INVALID;
+    if (h->finalized) return DHR_ERR_STATE;
+    if (n == 0) return DHR_OK;
+    const Geometry& g = h->g;
+    const int W = g.S * g.G + g.C;
+    if (!vals || vstride < W || (val_dtype != DHR_VAL_F16 && val_dtype != DHR_VAL_F32)) return DHR_ERR_INVALID;
+    if (g.S > 0 && (!idx || istride < g.S || idx_dtype_size(idx_dtype) == 0)) return DHR_ERR_INVALID;
+    if (h->n_rows + n > h->capacity) return DHR_ERR_INVALID;
+    DHR_CUDA(cudaSetDevice(h->device));
+    const size_t vsz = val_dtype == DHR_VAL_F16 ? 2 : 4;
+    const size_t isz = g.S > 0 ? (size_t)idx_dtype_size(idx_dtype) : 0;
+    const bool v_dev = is_device_pointer(vals);
+    const bool i_dev = g.S > 0 ? is_device_pointer(idx) : true;
+    if (v_dev && i_dev) {
+        DHR_TRY(ingest_device(h, n, val_dtype, vals, vstride, idx_dtype, idx, istride));
+        DHR_CUDA(cudaDeviceSynchronize());
+        h->n_rows += n;
+        return DHR_OK;
+    }
+    // host source: stage in pieces of <= 64 MiB of values (packed, row stride = W / S)
+    const size_t row_in = (size_t)W * vsz;
+    long long piece = (long long)((64ull << 20) / (row_in ? row_in : 1));
+    if (piece < 1) piece = 1;
+    for (long long r0 = 0; r0 < n; r0 += piece) {
+        const long long m = (n - r0 < piece) ? (n - r0) : piece;
+        const void* dv = nullptr; const void* di = nullptr;
+        long long dvs = vstride, dis = istride;
+        if (v_dev) dv = (const uint8_t*)vals + (size_t)r0 * vstride * vsz;
+        else {
+            DHR_TRY(ensure_device_buffer(&h->stage_a, &h->stage_a_bytes, (size_t)piece * row_in));
+            DHR_CUDA(cudaMemcpy2D(h->stage_a, row_in, (const uint8_t*)vals + (size_t)r0 * vstride * vsz, (size_t)vstride * vsz,
+                                  row_in, (size_t)m, cudaMemcpyHostToDevice));
+            dv = h->stage_a; dvs = W;
+        }
+        if (g.S > 0) {
+            if (i_dev) di = (const uint8_t*)idx + (size_t)r0 * istride * isz;
+            else {
+                DHR_TRY(ensure_device_buffer(&h->stage_b, &h->stage_b_bytes, (size_t)piece * g.S * isz));
+                DHR_CUDA(cudaMemcpy2D(h->stage_b, (size_t)g.S * isz, (const uint8_t*)idx + (size_t)r0 * istride * isz,
+                                      (size_t)istride * isz, (size_t)g.S * isz, (size_t)m, cudaMemcpyHostToDevice));
+                di = h->stage_b; dis = g.S;
+            }
+        }
+        DHR_TRY(ingest_device(h, m, val_dtype, dv, dvs, idx_dtype, di, dis));
+        DHR_CUDA(cudaDeviceSynchronize());
+        h->n_rows += m;
+    }
+    return DHR_OK;
+}
+
+int dhr_index_finalize(dhr_index* h) {
+    if (!h) return DHR_ERR_INVALID;
+    if (h->finalized) return DHR_OK;
+    DHR_CUDA(cudaSetDevice(h->device));
+    int flags[4] = {0, 0, 0, 0};
+    DHR_CUDA(cudaMemcpy(flags, h->d_flags, sizeof(flags), cudaMemcpyDeviceToHost));
+    if (flags[0]) return DHR_ERR_LOSSY;
+    if (flags[1]) return DHR_ERR_IDX_RANGE;
+    // the ingest staging buffers are not needed any more
+    if (h->stage_a) { cudaFree(h->stage_a); h->stage_a = nullptr; h->stage_a_bytes = 0; }
+    if (h->stage_b) { cudaFree(h->stage_b); h->stage_b = nullptr; h->stage_b_bytes = 0; }
+    h->finalized = true;
+    return DHR_OK;
+}
+
+int dhr_index_open(dhr_index** out, int device, int64_t n_rows, int n_slices, int group, int n_dense, int val_dtype,
+                   const void* vals, int64_t vstride, int idx_dtype, const void* idx, int64_t istride, int64_t row_offset,
+                   unsigned flags) {
+    if (!out) return DHR_ERR_INVALID;
+    dhr_index* h = nullptr;
+    DHR_TRY(dhr_index_create(&h, device, n_rows, n_slices, group, n_dense, idx_dtype, row_offset, flags));
+    int s = dhr_index_append(h, n_rows, val_dtype, vals, vstride, idx_dtype, idx, istride);
+    if (s == DHR_OK) s = dhr_index_finalize(h);
+    if (s != DHR_OK) { dhr_index_close(h); return s; }
+    *out = h;
+    return DHR_OK;
+}
+
+int dhr_index_close(dhr_index* h) {
+    if (!h) return DHR_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    void* bufs[] = {h->lexv, h->lexi, h->dns, h->d_flags, h->stage_a, h->stage_b, h->q_lex16, h->q_lex32, h->q_dns16, h->q_dns32,
+                    h->q_code, h->topk.tau, h->topk.cnt, h->topk.overflow, h->topk.cand_score, h->topk.cand_row,
+                    h->d_out_scores, h->d_out_rows, h->d_out_counts};
+    for (void* b : bufs) if (b) cudaFree(b);
+    h->events.destroy();
+    cudaGetLastError();
+    delete h;
+    return DHR_OK;
+}
+
+int dhr_index_rows(const dhr_index* h, int64_t* n_rows) {
+    if (!h || !n_rows) return DHR_ERR_INVALID;
+    *n_rows = h->n_rows;
+    return DHR_OK;
+}
+
+int dhr_index_row_bytes(const dhr_index* h, int64_t* bytes) {
+    if (!h || !bytes) return DHR_ERR_INVALID;
+    *bytes = h->g.row_bytes();
+    return DHR_OK;
+}
+
+int dhr_index_set_option(dhr_index* h, const char* name, int64_t value) {
+    if (!h || !name) return DHR_ERR_INVALID;
+    if (!strcmp(name, "scan_variant")) { if (value < 0 || value > 1) return DHR_ERR_INVALID; h->opt_scan_variant = (int)value; return DHR_OK; }
+    if (!strcmp(name, "query_block")) {
+        if (value != 1 && value != 2 && value != 4 && value != 8) return DHR_ERR_INVALID;
+        h->opt_query_block = (int)value; return DHR_OK;
+    }
+    if (!strcmp(name, "query_groups")) { if (value < 1 || value > kMaxInflight) return DHR_ERR_INVALID; h->opt_query_groups = (int)value; return DHR_OK; }
+    if (!strcmp(name, "profile")) { h->opt_profile = value != 0; return DHR_OK; }
+    return DHR_ERR_INVALID;
+}
+
+int dhr_index_get_stats(const dhr_index* h, dhr_stats* out) {
+    if (!h || !out) return DHR_ERR_INVALID;
+    *out = h->stats;
+    return DHR_OK;
+}
+
+}  // extern "C"

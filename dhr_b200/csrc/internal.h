@@ -1,0 +1,102 @@
+// internal.h -- host-side structures shared by the translation units of libdhr_b200.so
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace dhr {
+
+constexpr int kCandCap = 16384;          // candidate slots per in-flight query (fits a 128 KiB smem sort)
+constexpr int kMaxInflight = 64;         // query slots per super-batch (query_block * query_groups)
+
+struct Geometry {
+    int S = 0, G = 1, C = 0;             // slices, values per slice, dense columns (user shape)
+    int S_pad = 0, D_pad = 0, C_pad = 0; // padded strides (elements) of the resident arrays
+    int code_bytes = 1;                  // 1 = uint8 codes, 2 = uint16 codes
+    int unit_halves = 8;                 // lcm(G, 8): fp16 values one lane handles per lexical unit
+    int unit_slices = 8;                 // unit_halves / G
+    int n_units = 0;                     // S_pad / unit_slices
+    int n_chunks = 0;                    // C_pad / 8 (16-byte dense chunks)
+    int64_t row_bytes() const { return (int64_t)D_pad * 2 + (int64_t)S_pad * code_bytes + (int64_t)C_pad * 2; }
+};
+
+// per-query selection state of one in-flight slot
+struct TopkState {
+    float*    tau = nullptr;             // [slots] strict admission threshold
+    uint32_t* cnt = nullptr;             // [slots] candidates appended (may exceed cap -> overflow)
+    uint32_t* overflow = nullptr;        // [slots] sticky overflow flag
+    float*    cand_score = nullptr;      // [slots][cap]
+    int32_t*  cand_row = nullptr;        // [slots][cap]
+};
+
+struct EventPool {
+    std::vector<cudaEvent_t> ev;
+    size_t used = 0;
+    cudaEvent_t get();
+    void reset() { used = 0; }
+    void destroy();
+};
+
+}  // namespace dhr
+
+struct dhr_index {
+    int device = 0;
+    int64_t capacity = 0, n_rows = 0, row_offset = 0;
+    dhr::Geometry g;
+    int idx_dtype = DHR_IDX_NONE;
+    bool finalized = false;
+    // resident arrays (device)
+    __half* lexv = nullptr;              // [capacity][D_pad]
+    uint8_t* lexi = nullptr;             // [capacity][S_pad] codes (uint8 or uint16)
+    __half* dns = nullptr;               // [capacity][C_pad]
+    int* d_flags = nullptr;              // [4] device-side validation flags (lossy, idx range, query needs fp32, spare)
+    // staging for host -> device appends / queries
+    void* stage_a = nullptr; size_t stage_a_bytes = 0;
+    void* stage_b = nullptr; size_t stage_b_bytes = 0;
+    // query workspace
+    void* q_lex16 = nullptr; void* q_lex32 = nullptr; void* q_dns16 = nullptr; void* q_dns32 = nullptr; void* q_code = nullptr;
+    int q_capacity = 0;
+    dhr::TopkState topk;
+    float* d_out_scores = nullptr; int64_t* d_out_rows = nullptr; int32_t* d_out_counts = nullptr; size_t out_capacity = 0;
+    // options
+    int opt_scan_variant = 0;
+    int opt_query_block = 4;
+    int opt_query_groups = 16;
+    int opt_profile = 0;
+    int num_sms = 148;
+    dhr_stats stats{};
+    dhr::EventPool events;
+};
+
+namespace dhr {
+
+// scan launch description (one chunk of rows, one super-batch of queries)
+struct ScanArgs {
+    const __half* lexv; const uint8_t* lexi; const __half* dns;
+    int S_pad, D_pad, C_pad, n_units, n_chunks;
+    long long row_begin, row_end;
+    const void* q_lex; const void* q_code; const void* q_dns;   // rows of the first query of the super-batch
+    int n_queries;                       // valid queries in the super-batch
+    int n_groups;                        // ceil(n_queries / QB)
+    int masked;
+    float* tau; uint32_t* cnt; float* cand_score; int32_t* cand_row; int cap;
+    int rows_per_cta;
+    int tile_rows;                       // TMA variant: rows per smem stage
+    int n_stages;
+};
+
+int launch_scan(const dhr_index* h, const ScanArgs& a, int query_block, bool q_f32, int variant, cudaStream_t st);
+size_t scan_tma_smem_bytes(const Geometry& g, int query_block, bool q_f32, int tile_rows, int n_stages);
+
+int launch_select(const TopkState& t, int n_slots, int k, int cap, bool final_pass, int64_t row_offset,
+                  float* out_scores, int64_t* out_rows, int32_t* out_counts, int out_base, cudaStream_t st);
+
+int launch_prep_queries(dhr_index* h, int n, int val_dtype, const void* vals, int64_t vstride, int idx_dtype,
+                        const void* idx, int64_t istride, float lamda, cudaStream_t st);
+
+int launch_rerank(const dhr_index* h, const ScanArgs& a, bool q_f32, const long long* d_cand, int n_cand, cudaStream_t st);
+
+int ensure_device_buffer(void** p, size_t* cur, size_t need);
+bool is_device_pointer(const void* p);
+
+}  // namespace dhr

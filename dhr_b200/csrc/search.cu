@@ -1,0 +1,480 @@
+// search.cu -- dhr_search / dhr_rerank orchestration: query preparation, chunked scan with a
+// tightening admission threshold, exact selection, overflow-proof fallback.
+//
+// Replaces the body of GIP_retrieval (gip_retrieval.py:88-165, exact branch and the --IP first
+// stage) and IP_retrieval (:60-85).  Selection without a score matrix:
+//   rows are scanned in chunks of increasing row ranges [b0,b1), [b1,b2), ...; the first chunk
+//   (<= cap-k rows) admits every row; after each chunk K3 keeps the best k candidates of each
+//   query and publishes tau = k-th best score; later chunks admit a row only if score > tau
+//   (strict: later rows have larger row ids, so they lose ties -- exactly the (score desc, row
+//   asc) rule).  Chunks grow geometrically so a random-order corpus admits ~k*(growth-1) rows per
+//   chunk; if a query still overflows its cap-slot buffer (adversarial order) it is re-run with
+//   uniform chunks of cap-k rows, which cannot overflow.
+#include <algorithm>
+#include <math.h>
+#include <vector>
+
+#include "internal.h"
+
+namespace dhr {
+
+// ---- query preparation ------------------------------------------------------------------------
+// one thread per (query, padded slice): values in fp16 and fp32, code; flags[2] |= 1 if any value
+// is not exactly representable in fp16 (then the scan uses the fp32-query kernels).
+template <typename CodeT>
+__global__ void prep_lexical_kernel(int n, int S, int G, int S_pad, int val_dtype, const void* vals, long long vstride,
+                                    int idx_dtype, const void* idx, long long istride, __half* q16, float* q32, CodeT* qc,
+                                    int* flags) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n * S_pad) return;
+    const int q = (int)(i / S_pad), s = (int)(i % S_pad);
+    __half* o16 = q16 + ((size_t)q * S_pad + s) * G;
+    float* o32 = q32 + ((size_t)q * S_pad + s) * G;
+    CodeT* oc = qc + (size_t)q * S_pad + s;
+    if (s >= S) {
+        for (int g = 0; g < G; ++g) { o16[g] = __float2half_rn(0.f); o32[g] = 0.f; }
+        *oc = (CodeT)CodeTraits<CodeT>::kNoMatch;
+        return;
+    }
+    bool nonzero = false, inexact = false;
+    for (int g = 0; g < G; ++g) {
+        const size_t off = (size_t)q * vstride + (size_t)s * G + g;
+        const float f = val_dtype == DHR_VAL_F16 ? __half2float(((const __half*)vals)[off]) : ((const float*)vals)[off];
+        const __half hv = __float2half_rn(f);
+        o16[g] = hv; o32[g] = f;
+        nonzero |= (f != 0.f);
+        inexact |= (__half2float(hv) != f);
+    }
+    if (inexact) atomicOr(flags + 2, 1);
+    uint32_t code = CodeTraits<CodeT>::kNoMatch;
+    if (nonzero && idx) {
+        long long v;
+        switch (idx_dtype) {
+            case DHR_IDX_U8:  v = ((const uint8_t*)idx)[(size_t)q * istride + s]; break;
+            case DHR_IDX_I8:  v = ((const int8_t*)idx)[(size_t)q * istride + s]; break;
+            case DHR_IDX_I16: v = ((const int16_t*)idx)[(size_t)q * istride + s]; break;
+            case DHR_IDX_U16: v = ((const uint16_t*)idx)[(size_t)q * istride + s]; break;
+            case DHR_IDX_I32: v = ((const int32_t*)idx)[(size_t)q * istride + s]; break;
+            default:          v = ((const long long*)idx)[(size_t)q * istride + s]; break;
+        }
+        if (v >= 0 && v <= (long long)CodeTraits<CodeT>::kMax) code = (uint32_t)v;
+    }
+    *oc = (CodeT)code;
+}
+
+__global__ void prep_dense_kernel(int n, int D, int C, int C_pad, int val_dtype, const void* vals, long long vstride,
+                                  float lamda, __half* q16, float* q32, int* flags) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n * C_pad) return;
+    const int q = (int)(i / C_pad), c = (int)(i % C_pad);
+    float f = 0.f;
+    if (c < C) {
+        const size_t off = (size_t)q * vstride + D + c;
+        f = val_dtype == DHR_VAL_F16 ? __half2float(((const __half*)vals)[off]) : ((const float*)vals)[off];
+        f = lamda * f;                                   // gip_retrieval.py:281-283, fp32 on the CPU path
+    }
+    const __half hv = __float2half_rn(f);
+    q16[(size_t)q * C_pad + c] = hv;
+    q32[(size_t)q * C_pad + c] = f;
+    if (__half2float(hv) != f) atomicOr(flags + 2, 1);
+}
+
+int launch_prep_queries(dhr_index* h, int n, int val_dtype, const void* d_vals, int64_t vstride, int idx_dtype,
+                        const void* d_idx, int64_t istride, float lamda, cudaStream_t st) {
+    const Geometry& g = h->g;
+    if (g.S_pad > 0) {
+        const long long total = (long long)n * g.S_pad;
+        const unsigned blocks = (unsigned)((total + 255) / 256);
+        if (g.code_bytes == 1)
+            prep_lexical_kernel<uint8_t><<<blocks, 256, 0, st>>>(n, g.S, g.G, g.S_pad, val_dtype, d_vals, vstride, idx_dtype, d_idx,
+                                                                 istride, (__half*)h->q_lex16, (float*)h->q_lex32,
+                                                                 (uint8_t*)h->q_code, h->d_flags);
+        else
+            prep_lexical_kernel<uint16_t><<<blocks, 256, 0, st>>>(n, g.S, g.G, g.S_pad, val_dtype, d_vals, vstride, idx_dtype, d_idx,
+                                                                  istride, (__half*)h->q_lex16, (float*)h->q_lex32,
+                                                                  (uint16_t*)h->q_code, h->d_flags);
+        DHR_CUDA(cudaGetLastError());
+        h->stats.n_prep_launches++; h->stats.n_kernel_launches++;
+    }
+    if (g.C_pad > 0) {
+        const long long total = (long long)n * g.C_pad;
+        const unsigned blocks = (unsigned)((total + 255) / 256);
+        prep_dense_kernel<<<blocks, 256, 0, st>>>(n, g.S * g.G, g.C, g.C_pad, val_dtype, d_vals, vstride, lamda,
+                                                  (__half*)h->q_dns16, (float*)h->q_dns32, h->d_flags);
+        DHR_CUDA(cudaGetLastError());
+        h->stats.n_prep_launches++; h->stats.n_kernel_launches++;
+    }
+    return DHR_OK;
+}
+
+__global__ void init_slots_kernel(TopkState t, int n_slots) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_slots) { t.tau[i] = -INFINITY; t.cnt[i] = 0u; t.overflow[i] = 0u; }
+}
+
+// ---- workspace ----------------------------------------------------------------------------------
+static int ensure_query_workspace(dhr_index* h, int n) {
+    if (n <= h->q_capacity) return DHR_OK;
+    const Geometry& g = h->g;
+    void** bufs[] = {&h->q_lex16, &h->q_lex32, &h->q_dns16, &h->q_dns32, &h->q_code};
+    for (void** b : bufs) if (*b) { cudaFree(*b); *b = nullptr; }
+    h->q_capacity = 0;
+    const size_t nn = (size_t)n + kMaxInflight;   // slack: a group may read (and discard) rows past the last query
+    if (g.D_pad > 0) {
+        DHR_CUDA(cudaMalloc(&h->q_lex16, nn * g.D_pad * 2));
+        DHR_CUDA(cudaMalloc(&h->q_lex32, nn * g.D_pad * 4));
+        DHR_CUDA(cudaMalloc(&h->q_code, nn * g.S_pad * g.code_bytes));
+    }
+    if (g.C_pad > 0) {
+        DHR_CUDA(cudaMalloc(&h->q_dns16, nn * g.C_pad * 2));
+        DHR_CUDA(cudaMalloc(&h->q_dns32, nn * g.C_pad * 4));
+    }
+    h->q_capacity = n;
+    return DHR_OK;
+}
+
+static int ensure_topk_state(dhr_index* h) {
+    TopkState& t = h->topk;
+    if (t.tau) return DHR_OK;
+    DHR_CUDA(cudaMalloc(&t.tau, kMaxInflight * sizeof(float)));
+    DHR_CUDA(cudaMalloc(&t.cnt, kMaxInflight * sizeof(uint32_t)));
+    DHR_CUDA(cudaMalloc(&t.overflow, kMaxInflight * sizeof(uint32_t)));
+    DHR_CUDA(cudaMalloc(&t.cand_score, (size_t)kMaxInflight * kCandCap * sizeof(float)));
+    DHR_CUDA(cudaMalloc(&t.cand_row, (size_t)kMaxInflight * kCandCap * sizeof(int32_t)));
+    return DHR_OK;
+}
+
+static int ensure_out_buffers(dhr_index* h, size_t n_queries, int k) {
+    const size_t need = n_queries * (size_t)k;
+    if (need <= h->out_capacity && h->d_out_scores) return DHR_OK;
+    if (h->d_out_scores) cudaFree(h->d_out_scores);
+    if (h->d_out_rows) cudaFree(h->d_out_rows);
+    if (h->d_out_counts) cudaFree(h->d_out_counts);
+    h->d_out_scores = nullptr; h->d_out_rows = nullptr; h->d_out_counts = nullptr; h->out_capacity = 0;
+    DHR_CUDA(cudaMalloc(&h->d_out_scores, need * sizeof(float)));
+    DHR_CUDA(cudaMalloc(&h->d_out_rows, need * sizeof(int64_t)));
+    DHR_CUDA(cudaMalloc(&h->d_out_counts, (n_queries + 1) * sizeof(int32_t)));
+    h->out_capacity = need;
+    return DHR_OK;
+}
+
+// chunk boundaries (row indices).  growth <= 1 selects the overflow-proof uniform schedule.
+static std::vector<long long> chunk_schedule(long long n_rows, int k, int cap, bool safe) {
+    std::vector<long long> b;
+    b.push_back(0);
+    const long long first = std::min<long long>(n_rows, (long long)cap - k);
+    if (n_rows == 0) return b;
+    b.push_back(first);
+    if (safe) {
+        while (b.back() < n_rows) b.push_back(std::min<long long>(n_rows, b.back() + (cap - k)));
+        return b;
+    }
+    double growth = 1.0 + (double)(cap - k) / (2.0 * k);
+    growth = std::min(8.0, std::max(1.25, growth));
+    while (b.back() < n_rows) {
+        long long next = (long long)ceil((double)b.back() * growth);
+        if (next <= b.back()) next = b.back() + 1;
+        b.push_back(std::min(n_rows, next));
+    }
+    return b;
+}
+
+struct QuerySet {
+    bool f32;                       // use fp32 query arrays
+    const uint8_t* lex; const uint8_t* code; const uint8_t* dns;
+    size_t lex_stride, code_stride, dns_stride;   // bytes per query
+};
+
+static QuerySet query_set(const dhr_index* h, bool f32) {
+    const Geometry& g = h->g;
+    QuerySet q;
+    q.f32 = f32;
+    q.lex = (const uint8_t*)(f32 ? h->q_lex32 : h->q_lex16);
+    q.dns = (const uint8_t*)(f32 ? h->q_dns32 : h->q_dns16);
+    q.code = (const uint8_t*)h->q_code;
+    q.lex_stride = (size_t)g.D_pad * (f32 ? 4 : 2);
+    q.dns_stride = (size_t)g.C_pad * (f32 ? 4 : 2);
+    q.code_stride = (size_t)g.S_pad * g.code_bytes;
+    return q;
+}
+
+// scan + select for queries [base, base+nq) of the prepared query set
+static int run_batch(dhr_index* h, const QuerySet& qs, int base, int nq, int k, bool masked, bool safe, int qb,
+                     float* d_scores, int64_t* d_rows, int32_t* d_counts, cudaStream_t st) {
+    const Geometry& g = h->g;
+    TopkState t = h->topk;
+    init_slots_kernel<<<1, kMaxInflight, 0, st>>>(t, kMaxInflight);
+    DHR_CUDA(cudaGetLastError());
+    h->stats.n_kernel_launches++;
+    const std::vector<long long> bounds = chunk_schedule(h->n_rows, k, kCandCap, safe);
+    ScanArgs a{};
+    a.lexv = h->lexv; a.lexi = h->lexi; a.dns = h->dns;
+    a.S_pad = g.S_pad; a.D_pad = g.D_pad; a.C_pad = g.C_pad; a.n_units = g.n_units; a.n_chunks = g.n_chunks;
+    a.q_lex = qs.lex + (size_t)base * qs.lex_stride;
+    a.q_code = qs.code + (size_t)base * qs.code_stride;
+    a.q_dns = qs.dns + (size_t)base * qs.dns_stride;
+    a.n_queries = nq;
+    a.n_groups = (nq + qb - 1) / qb;
+    a.masked = masked ? 1 : 0;
+    a.tau = t.tau; a.cnt = t.cnt; a.cand_score = t.cand_score; a.cand_row = t.cand_row; a.cap = kCandCap;
+    a.rows_per_cta = 128;
+    a.tile_rows = 16;
+    int variant = h->opt_scan_variant;
+    if (variant == 1) {
+        int stages = 4;
+        while (stages > 1 && scan_tma_smem_bytes(g, qb, qs.f32, a.tile_rows, stages) > 200 * 1024) --stages;
+        if (scan_tma_smem_bytes(g, qb, qs.f32, a.tile_rows, stages) > 200 * 1024 || stages < 2) variant = 0;   // rows too wide
+        a.n_stages = stages;
+    }
+    const size_t direct_smem = (size_t)qb * (qs.lex_stride + qs.code_stride + qs.dns_stride);
+    if (variant == 0 && direct_smem > 200 * 1024) return DHR_ERR_UNSUPPORTED;
+    const size_t n_chunks = bounds.size() - 1;
+    for (size_t c = 0; c < n_chunks; ++c) {
+        a.row_begin = bounds[c];
+        a.row_end = bounds[c + 1];
+        cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+        if (h->opt_profile) { e0 = h->events.get(); e1 = h->events.get(); e2 = h->events.get(); cudaEventRecord(e0, st); }
+        DHR_TRY(launch_scan(h, a, qb, qs.f32, variant, st));
+        if (h->opt_profile) cudaEventRecord(e1, st);
+        const bool final_pass = (c + 1 == n_chunks);
+        DHR_TRY(launch_select(t, nq, k, kCandCap, final_pass, h->row_offset, d_scores, d_rows, d_counts, base, st));
+        if (h->opt_profile) cudaEventRecord(e2, st);
+        h->stats.n_scan_launches++;
+        h->stats.n_select_launches++;
+        h->stats.n_kernel_launches += 2;
+        h->stats.corpus_passes += (double)(a.row_end - a.row_begin) * a.n_groups / (double)std::max<int64_t>(1, h->n_rows);
+    }
+    if (n_chunks == 0) {   // empty index: all padding
+        DHR_TRY(launch_select(t, nq, k, kCandCap, true, h->row_offset, d_scores, d_rows, d_counts, base, st));
+        h->stats.n_select_launches++;
+        h->stats.n_kernel_launches++;
+    }
+    h->stats.scan_variant = variant;
+    return DHR_OK;
+}
+
+// the select kernel sets the sticky per-slot overflow flag; copy it to the per-query array
+__global__ void carry_overflow_kernel(const uint32_t* slot_flags, uint32_t* per_query, int base, int nq) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq && slot_flags[i]) per_query[base + i] = 1u;
+}
+
+static int stage_queries_to_device(dhr_index* h, int n, int val_dtype, const void* q_vals, int64_t vstride, int idx_dtype,
+                                   const void* q_idx, int64_t istride, const void** d_vals, int64_t* d_vstride,
+                                   const void** d_idx, int64_t* d_istride, cudaStream_t st) {
+    const Geometry& g = h->g;
+    const int W = g.S * g.G + g.C;
+    const size_t vsz = val_dtype == DHR_VAL_F16 ? 2 : 4;
+    if (is_device_pointer(q_vals)) { *d_vals = q_vals; *d_vstride = vstride; }
+    else {
+        DHR_TRY(ensure_device_buffer(&h->stage_a, &h->stage_a_bytes, (size_t)n * W * vsz));
+        DHR_CUDA(cudaMemcpy2DAsync(h->stage_a, (size_t)W * vsz, q_vals, (size_t)vstride * vsz, (size_t)W * vsz, (size_t)n,
+                                   cudaMemcpyHostToDevice, st));
+        *d_vals = h->stage_a; *d_vstride = W;
+    }
+    *d_idx = nullptr; *d_istride = 0;
+    if (g.S > 0 && q_idx) {
+        size_t isz = 1;
+        switch (idx_dtype) { case DHR_IDX_I16: case DHR_IDX_U16: isz = 2; break; case DHR_IDX_I32: isz = 4; break; case DHR_IDX_I64: isz = 8; break; default: break; }
+        if (is_device_pointer(q_idx)) { *d_idx = q_idx; *d_istride = istride; }
+        else {
+            DHR_TRY(ensure_device_buffer(&h->stage_b, &h->stage_b_bytes, (size_t)n * g.S * isz));
+            DHR_CUDA(cudaMemcpy2DAsync(h->stage_b, (size_t)g.S * isz, q_idx, (size_t)istride * isz, (size_t)g.S * isz, (size_t)n,
+                                       cudaMemcpyHostToDevice, st));
+            *d_idx = h->stage_b; *d_istride = g.S;
+        }
+    }
+    return DHR_OK;
+}
+
+static int validate_query_args(const dhr_index* h, int n_queries, int q_val_dtype, const void* q_vals, int64_t vstride,
+                               int q_idx_dtype, const void* q_idx, int64_t istride, int k, bool masked) {
+    if (!h) return DHR_ERR_INVALID;
+    if (!h->finalized) return DHR_ERR_STATE;
+    const Geometry& g = h->g;
+    const int W = g.S * g.G + g.C;
+    if (n_queries < 0 || k < 1) return DHR_ERR_INVALID;
+    if (k > DHR_MAX_K) return DHR_ERR_UNSUPPORTED;
+    if (n_queries == 0) return DHR_OK;
+    if (!q_vals || vstride < W) return DHR_ERR_INVALID;
+    if (q_val_dtype != DHR_VAL_F16 && q_val_dtype != DHR_VAL_F32) return DHR_ERR_INVALID;
+    if (g.S > 0 && masked) {
+        if (!q_idx || istride < g.S) return DHR_ERR_INVALID;
+        if (q_idx_dtype < DHR_IDX_U8 || q_idx_dtype > DHR_IDX_I64) return DHR_ERR_INVALID;
+    }
+    return DHR_OK;
+}
+
+}  // namespace dhr
+
+using namespace dhr;
+
+extern "C" int dhr_search(dhr_index* h, int n_queries, int q_val_dtype, const void* q_vals, int64_t vstride, int q_idx_dtype,
+                          const void* q_idx, int64_t istride, float lamda, int k, unsigned flags, float* out_scores,
+                          int64_t* out_rows, int32_t* out_counts, void* stream) {
+    const bool masked = !(flags & DHR_SEARCH_UNMASKED);
+    DHR_TRY(validate_query_args(h, n_queries, q_val_dtype, q_vals, vstride, q_idx_dtype, q_idx, istride, k, masked));
+    if (!out_scores || !out_rows) return DHR_ERR_INVALID;
+    if (n_queries == 0) return DHR_OK;
+    DHR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Geometry& g = h->g;
+
+    h->stats = dhr_stats{};
+    h->stats.n_queries = n_queries;
+    h->stats.bytes_per_pass = (double)h->n_rows * (double)g.row_bytes();
+    h->events.reset();
+
+    DHR_TRY(ensure_query_workspace(h, n_queries));
+    DHR_TRY(ensure_topk_state(h));
+    DHR_CUDA(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(int), st));
+
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    if (h->opt_profile) { ev_begin = h->events.get(); ev_end = h->events.get(); cudaEventRecord(ev_begin, st); }
+
+    const void* d_vals; const void* d_idx; int64_t d_vs, d_is;
+    DHR_TRY(stage_queries_to_device(h, n_queries, q_val_dtype, q_vals, vstride, q_idx_dtype, masked ? q_idx : nullptr, istride,
+                                    &d_vals, &d_vs, &d_idx, &d_is, st));
+    DHR_TRY(launch_prep_queries(h, n_queries, q_val_dtype, d_vals, d_vs, q_idx_dtype, d_idx, d_is, lamda, st));
+    int need_f32 = 0;
+    DHR_CUDA(cudaMemcpyAsync(&need_f32, h->d_flags + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DHR_CUDA(cudaStreamSynchronize(st));
+
+    const bool out_dev = is_device_pointer(out_scores) && is_device_pointer(out_rows) &&
+                         (!out_counts || is_device_pointer(out_counts));
+    float* d_scores = out_scores; int64_t* d_rows = out_rows; int32_t* d_counts = out_counts;
+    if (!out_dev) {
+        DHR_TRY(ensure_out_buffers(h, (size_t)n_queries, k));
+        d_scores = h->d_out_scores; d_rows = h->d_out_rows; d_counts = h->d_out_counts;
+    }
+    uint32_t* d_overflow = nullptr;
+    DHR_CUDA(cudaMalloc(&d_overflow, (size_t)n_queries * sizeof(uint32_t)));
+    int status = DHR_OK;
+    std::vector<uint32_t> h_overflow((size_t)n_queries, 0u);
+    do {
+        if ((status = (cudaMemsetAsync(d_overflow, 0, (size_t)n_queries * sizeof(uint32_t), st) == cudaSuccess) ? DHR_OK : DHR_ERR_CUDA)) break;
+        const QuerySet qs = query_set(h, need_f32 != 0);
+        const int qb = h->opt_query_block;
+        int groups = h->opt_query_groups;
+        if (qb * groups > kMaxInflight) groups = kMaxInflight / qb;
+        const int slots = qb * groups;
+        h->stats.query_block = qb;
+        h->stats.query_groups = groups;
+        for (int base = 0; base < n_queries && status == DHR_OK; base += slots) {
+            const int nq = std::min(slots, n_queries - base);
+            status = run_batch(h, qs, base, nq, k, masked, false, qb, d_scores, d_rows, d_counts, st);
+            if (status == DHR_OK) {
+                carry_overflow_kernel<<<1, kMaxInflight, 0, st>>>(h->topk.overflow, d_overflow, base, nq);
+                h->stats.n_kernel_launches++;
+                if (cudaGetLastError() != cudaSuccess) status = DHR_ERR_CUDA;
+            }
+        }
+        if (status != DHR_OK) break;
+        if (cudaMemcpyAsync(h_overflow.data(), d_overflow, (size_t)n_queries * sizeof(uint32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) { status = DHR_ERR_CUDA; break; }
+        for (int q = 0; q < n_queries && status == DHR_OK; ++q) {
+            if (!h_overflow[q]) continue;
+            h->stats.n_fallback_queries++;
+            status = run_batch(h, qs, q, 1, k, masked, true, 1, d_scores, d_rows, d_counts, st);
+        }
+    } while (0);
+    if (status == DHR_OK && h->opt_profile) cudaEventRecord(ev_end, st);
+    if (status == DHR_OK && !out_dev) {
+        const size_t n = (size_t)n_queries * k;
+        if (cudaMemcpyAsync(out_scores, d_scores, n * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(out_rows, d_rows, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            (out_counts && cudaMemcpyAsync(out_counts, d_counts, (size_t)n_queries * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess))
+            status = DHR_ERR_CUDA;
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess && status == DHR_OK) status = DHR_ERR_CUDA;
+    cudaFree(d_overflow);
+    if (status == DHR_ERR_CUDA) { set_cuda_error(cudaGetLastError(), "dhr_search", __FILE__, __LINE__); return status; }
+    if (status != DHR_OK) return status;
+
+    if (h->opt_profile) {
+        // events were taken in triples (scan begin, scan end, select end) after the two bracket events
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev_begin, ev_end);
+        h->stats.total_ms = ms;
+        for (size_t i = 2; i + 2 < h->events.used; i += 3) {
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, h->events.ev[i], h->events.ev[i + 1]);
+            cudaEventElapsedTime(&b, h->events.ev[i + 1], h->events.ev[i + 2]);
+            h->stats.scan_ms += a;
+            h->stats.select_ms += b;
+        }
+    }
+    return DHR_OK;
+}
+
+extern "C" int dhr_rerank(dhr_index* h, int n_queries, int q_val_dtype, const void* q_vals, int64_t vstride, int q_idx_dtype,
+                          const void* q_idx, int64_t istride, float lamda, const int64_t* cand_rows, int n_cand, int k,
+                          float* out_scores, int64_t* out_rows, int32_t* out_counts, void* stream) {
+    DHR_TRY(validate_query_args(h, n_queries, q_val_dtype, q_vals, vstride, q_idx_dtype, q_idx, istride, k, true));
+    if (!out_scores || !out_rows || !cand_rows || n_cand < 1) return DHR_ERR_INVALID;
+    if (n_cand > kCandCap) return DHR_ERR_UNSUPPORTED;
+    if (n_queries == 0) return DHR_OK;
+    DHR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Geometry& g = h->g;
+    h->stats = dhr_stats{};
+    h->stats.n_queries = n_queries;
+    DHR_TRY(ensure_query_workspace(h, n_queries));
+    DHR_TRY(ensure_topk_state(h));
+    DHR_CUDA(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(int), st));
+    const void* d_vals; const void* d_idx; int64_t d_vs, d_is;
+    DHR_TRY(stage_queries_to_device(h, n_queries, q_val_dtype, q_vals, vstride, q_idx_dtype, q_idx, istride, &d_vals, &d_vs,
+                                    &d_idx, &d_is, st));
+    DHR_TRY(launch_prep_queries(h, n_queries, q_val_dtype, d_vals, d_vs, q_idx_dtype, d_idx, d_is, lamda, st));
+    int need_f32 = 0;
+    DHR_CUDA(cudaMemcpyAsync(&need_f32, h->d_flags + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DHR_CUDA(cudaStreamSynchronize(st));
+
+    const bool out_dev = is_device_pointer(out_scores) && is_device_pointer(out_rows) &&
+                         (!out_counts || is_device_pointer(out_counts));
+    float* d_scores = out_scores; int64_t* d_rows = out_rows; int32_t* d_counts = out_counts;
+    if (!out_dev) {
+        DHR_TRY(ensure_out_buffers(h, (size_t)n_queries, k));
+        d_scores = h->d_out_scores; d_rows = h->d_out_rows; d_counts = h->d_out_counts;
+    }
+    const long long* d_cand = (const long long*)cand_rows;
+    long long* d_cand_owned = nullptr;
+    if (!is_device_pointer(cand_rows)) {
+        DHR_CUDA(cudaMalloc(&d_cand_owned, (size_t)n_queries * n_cand * sizeof(long long)));
+        cudaError_t e = cudaMemcpyAsync(d_cand_owned, cand_rows, (size_t)n_queries * n_cand * sizeof(long long), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { cudaFree(d_cand_owned); set_cuda_error(e, "cudaMemcpyAsync(cand)", __FILE__, __LINE__); return DHR_ERR_CUDA; }
+        d_cand = d_cand_owned;
+    }
+    const QuerySet qs = query_set(h, need_f32 != 0);
+    int status = DHR_OK;
+    for (int base = 0; base < n_queries && status == DHR_OK; base += kMaxInflight) {
+        const int nq = std::min(kMaxInflight, n_queries - base);
+        TopkState t = h->topk;
+        init_slots_kernel<<<1, kMaxInflight, 0, st>>>(t, kMaxInflight);
+        h->stats.n_kernel_launches += 3;
+        ScanArgs a{};
+        a.lexv = h->lexv; a.lexi = h->lexi; a.dns = h->dns;
+        a.S_pad = g.S_pad; a.D_pad = g.D_pad; a.C_pad = g.C_pad; a.n_units = g.n_units; a.n_chunks = g.n_chunks;
+        a.q_lex = qs.lex + (size_t)base * qs.lex_stride;
+        a.q_code = qs.code + (size_t)base * qs.code_stride;
+        a.q_dns = qs.dns + (size_t)base * qs.dns_stride;
+        a.n_queries = nq; a.n_groups = nq; a.masked = 1;
+        a.tau = t.tau; a.cnt = t.cnt; a.cand_score = t.cand_score; a.cand_row = t.cand_row; a.cap = kCandCap;
+        status = launch_rerank(h, a, qs.f32, d_cand + (size_t)base * n_cand, n_cand, st);
+        if (status == DHR_OK)
+            status = launch_select(t, nq, k, kCandCap, true, h->row_offset, d_scores, d_rows, d_counts, base, st);
+        h->stats.n_scan_launches++;
+        h->stats.n_select_launches++;
+    }
+    if (status == DHR_OK && !out_dev) {
+        const size_t n = (size_t)n_queries * k;
+        if (cudaMemcpyAsync(out_scores, d_scores, n * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(out_rows, d_rows, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            (out_counts && cudaMemcpyAsync(out_counts, d_counts, (size_t)n_queries * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess))
+            status = DHR_ERR_CUDA;
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess && status == DHR_OK) status = DHR_ERR_CUDA;
+    if (d_cand_owned) cudaFree(d_cand_owned);
+    if (status == DHR_ERR_CUDA) set_cuda_error(cudaGetLastError(), "dhr_rerank", __FILE__, __LINE__);
+    return status;
+}

@@ -1,0 +1,219 @@
+"""Drop-in mirror of castorini/dhr ``retrieval/gip_retrieval.py`` on the B200 CUDA path.
+
+Same function names, argument meaning, return types and command line as the reference
+(``GIP_retrieval`` :88-165, ``IP_retrieval`` :60-85, ``main`` :233-344); the per-query
+torch loop is replaced by the HBM-resident index and fused scan/top-k kernels behind the C ABI
+(include/dhr_b200.h).  ``python -m dhr_b200.gip_retrieval`` accepts the reference's flags verbatim
+(misspellings included: --total_shrad, --shrad, --lamda) and reads / writes the same files.
+
+Differences, all deliberate:
+  * ties are ordered (score desc, row asc); torch.topk's tie order is unspecified,
+  * ``PQ_IP_retrieval`` (faiss product quantisation, :167-231) is out of scope -> --PQIP raises,
+  * ``--use_gpu`` is accepted and ignored (this implementation always runs on the GPU); the
+    extra flag ``--device`` selects the CUDA device (the reference hard-wires 0, :261).
+"""
+from __future__ import annotations
+
+import argparse
+import pickle
+import time
+
+import numpy as np
+
+from .index import GipIndex
+
+try:
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _to_numpy_or_tensor(x):
+    return x
+
+
+def _as_lists(scores, rows, counts, qids, local_offset=0):
+    """[Q,k] arrays -> the reference's two dicts (qid -> list[int], qid -> list[float])."""
+    if torch is not None and isinstance(scores, torch.Tensor):
+        scores, rows, counts = scores.cpu().numpy(), rows.cpu().numpy(), counts.cpu().numpy()
+    all_results, all_scores = {}, {}
+    for i, qid in enumerate(qids):
+        n = int(counts[i])
+        all_scores[qid] = scores[i, :n].tolist()
+        all_results[qid] = (rows[i, :n] - local_offset).tolist()
+    return all_results, all_scores
+
+
+def _n_rows(x):
+    return len(x) if isinstance(x, GipIndex) else x.shape[0]
+
+
+def _open_index(corpus_embs, corpus_arg_idxs, emb_dim, device=0):
+    """corpus_embs may already be a GipIndex (extension: lets callers keep the corpus resident)."""
+    if isinstance(corpus_embs, GipIndex):
+        return corpus_embs, False
+    if corpus_arg_idxs is None:
+        return GipIndex.from_arrays(corpus_embs, None, device=device), True
+    return GipIndex.from_arrays(corpus_embs, corpus_arg_idxs, n_slices=emb_dim, group=1, device=device), True
+
+
+def IP_retrieval(qids, query_embs, corpus_embs, args):
+    """Brute-force inner-product search (gip_retrieval.py:60-85): top ``args.topk`` rows per query.
+
+    Like the reference's ``argsort(...)[:topk]`` this never fails for topk > N; it returns N rows."""
+    description = 'Brute force IP search'
+    index, owned = _open_index(corpus_embs, None, 0, getattr(args, 'device', 0))
+    try:
+        start_time = time.time()
+        k = max(1, min(int(args.topk), max(1, len(index))))
+        scores, rows, counts = index.search(query_embs, None, k)
+        all_results, all_scores = _as_lists(scores, rows, counts, qids, index.row_offset)
+        time_per_query = (time.time() - start_time) / max(1, len(qids))
+        print('Retrieving {} queries ({:0.3f} s/query), average number of index use {}'.format(
+            len(qids), time_per_query, 0.0))
+    finally:
+        if owned:
+            index.close()
+    del description
+    return all_results, all_scores
+
+
+def _prune_query(query_embs, theta):
+    """theta pruning of :130-131: keep the dimensions whose query value exceeds theta (all columns,
+    [CLS] tail included), zero the rest -- identical to restricting the sum to the kept columns."""
+    if torch is not None and isinstance(query_embs, torch.Tensor):
+        return torch.where(query_embs > theta, query_embs, torch.zeros_like(query_embs))
+    q = np.asarray(query_embs)
+    return np.where(q > theta, q, np.zeros_like(q))
+
+
+def GIP_retrieval(qids, query_embs, query_arg_idxs, corpus_embs, corpus_arg_idxs, args):
+    """Grouped-inner-product search (gip_retrieval.py:88-165).
+
+    args fields read: brute_force, theta, IP, rerank, emb_dim, topk, agip_topk (args.theta is set to 0
+    under --brute_force exactly like :90).  Returns (all_results, all_scores): qid -> list of row
+    indices within the given corpus, qid -> list of fp32 scores, both descending by score."""
+    if args.brute_force:
+        args.theta = 0
+    index, owned = _open_index(corpus_embs, corpus_arg_idxs, args.emb_dim, getattr(args, 'device', 0))
+    try:
+        n = len(index)
+        start_time = time.time()
+        total_num_idx = 0
+        if args.theta == 0:
+            if args.topk > n:      # torch.topk raises here (:123)
+                raise RuntimeError('selected index k out of range')
+            total_num_idx = args.emb_dim * len(qids)
+            scores, rows, counts = index.search(query_embs, query_arg_idxs, args.topk)
+        else:
+            if not args.IP:
+                first = index.search(_prune_query(query_embs, args.theta), query_arg_idxs,
+                                     args.agip_topk if args.rerank else args.topk)      # :135-136
+            else:
+                first = index.search(query_embs, None, args.agip_topk if args.rerank else args.topk,
+                                     masked=False)                                       # :139
+            need = args.agip_topk if args.rerank else args.topk
+            if need > n:
+                raise RuntimeError('selected index k out of range')
+            if args.rerank:                                                              # :142-150
+                if args.topk > args.agip_topk:
+                    raise RuntimeError('selected index k out of range')
+                cand = first[1] - index.row_offset
+                scores, rows, counts = index.rerank(query_embs, query_arg_idxs, cand, args.topk)
+            else:                                                                        # :155-156
+                scores, rows, counts = first
+        all_results, all_scores = _as_lists(scores, rows, counts, qids, index.row_offset)
+        time_per_query = (time.time() - start_time) / max(1, len(qids))
+        print('Retrieving {} queries ({:0.3f} s/query), average number of index use {}'.format(
+            len(qids), time_per_query, total_num_idx / max(1, len(qids))))
+    finally:
+        if owned:
+            index.close()
+    return all_results, all_scores
+
+
+def PQ_IP_retrieval(*_a, **_k):
+    raise NotImplementedError('PQ_IP_retrieval (faiss IndexPQ first stage, gip_retrieval.py:167-231) is out of scope '
+                              'of the B200 path: the exact scan is faster than the PQ approximation it replaced')
+
+
+def build_parser():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--query_emb_path", type=str, required=True)
+    parser.add_argument("--index_path", type=str, required=True)
+    parser.add_argument("--faiss_pq_index_path", type=str, default=None)
+    parser.add_argument("--emb_dim", type=int, default=768, help='DLR dimension')
+    parser.add_argument("--theta", type=float, default=0.1)
+    parser.add_argument("--topk", type=int, default=1000)
+    parser.add_argument("--agip_topk", type=int, default=10000)
+    parser.add_argument("--combine_cls", action='store_true')
+    parser.add_argument("--IP", action='store_true')
+    parser.add_argument("--PQIP", action='store_true')
+    parser.add_argument("--batch", type=int, default=1)
+    parser.add_argument("--brute_force", action='store_true')
+    parser.add_argument("--use_gpu", action='store_true')
+    parser.add_argument("--rerank", action='store_true')
+    parser.add_argument("--lamda", type=float, default=1, help='weight for [CSL] for concatenation')
+    parser.add_argument("--total_shrad", type=int, default=1)
+    parser.add_argument("--shrad", type=int, default=0)
+    parser.add_argument("--run_name", type=str, default='h2oloo')
+    parser.add_argument("--device", type=int, default=0, help='CUDA device (extension; the reference hard-wires 0)')
+    return parser
+
+
+def shard_bounds(n_docs, total_shrad, shrad):
+    """gip_retrieval.py:292-306: floor(N/T) rows per shard, the last shard takes the remainder."""
+    per = n_docs // total_shrad
+    lo = per * shrad
+    hi = n_docs if shrad == total_shrad - 1 else per * (shrad + 1)
+    return lo, hi
+
+
+def write_trec(path, results, scores, docids, run_name):
+    """gip_retrieval.py:329-342: rows whose docid equals the query id are skipped, ranks are NOT renumbered."""
+    with open(path, 'w') as fout:
+        for query_id in results:
+            result, score = results[query_id], scores[query_id]
+            lines = ['{} Q0 {} {} {} {}\n'.format(query_id, docids[docidx], rank + 1, score[rank], run_name)
+                     for rank, docidx in enumerate(result) if docids[docidx] != query_id]
+            fout.write(''.join(lines))
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    if args.PQIP:
+        PQ_IP_retrieval()
+
+    print('Load query embeddings ...')
+    with open(args.query_emb_path, 'rb') as f:
+        query_embs, query_arg_idxs, qids = pickle.load(f)
+    query_embs = np.asarray(query_embs).astype(np.float32)          # :275
+    if not isinstance(query_arg_idxs, np.ndarray):                   # :276-279: anything else means dense-only
+        query_arg_idxs = None
+    cls_dim = query_embs.shape[1] - args.emb_dim
+    if cls_dim > 0:
+        query_embs[:, -cls_dim:] = args.lamda * query_embs[:, -cls_dim:]   # :281-283
+
+    print('Load index ...')
+    with open(args.index_path, 'rb') as f:
+        corpus_embs, corpus_arg_idxs, docids = pickle.load(f)
+    lo, hi = shard_bounds(len(docids), args.total_shrad, args.shrad)
+    corpus_embs = corpus_embs[lo:hi]
+    corpus_arg_idxs = corpus_arg_idxs[lo:hi] if isinstance(corpus_arg_idxs, np.ndarray) else None
+    docids = docids[lo:hi]
+
+    if query_arg_idxs is not None:
+        index = GipIndex.from_arrays(corpus_embs, corpus_arg_idxs, n_slices=args.emb_dim, group=1, device=args.device)
+        results, scores = GIP_retrieval(qids, query_embs, query_arg_idxs, index, None, args)
+    else:
+        index = GipIndex.from_arrays(corpus_embs, None, device=args.device)
+        results, scores = IP_retrieval(qids, query_embs, index, args)
+    index.close()
+
+    out = 'result.trec' if args.total_shrad == 1 else 'result{}.trec'.format(args.shrad)
+    write_trec(out, results, scores, docids, args.run_name)
+    print('finish')
+
+
+if __name__ == "__main__":
+    main()

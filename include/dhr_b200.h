@@ -1,0 +1,144 @@
+/* dhr_b200.h -- C ABI of the B200-native GIP retrieval hot path.
+ *
+ * Drop-in boundary for castorini/dhr `retrieval/gip_retrieval.py` (reference @ e236f3d).
+ * The reference has no FFI of its own (pure Python); these entry points are what a
+ * ctypes / cffi binding of that file's hot functions binds to.  Each entry cites the
+ * reference code it replaces.  Plain pointers and sizes only, no torch types; every
+ * data pointer may be HOST or DEVICE memory (detected with cudaPointerGetAttributes).
+ * All functions return DHR_OK (0) or a DHR_ERR_* code; dhr_strerror() maps codes to text.
+ *
+ * Scoring (gip_retrieval.py:110-125), S slices x G values per slice, C dense columns:
+ *   score[p] = sum_{s<S} [q_idx[s]==p_idx[s]] * sum_{g<G} q_val[s*G+g]*p_val[s*G+g]
+ *            + sum_{c<C} q_val[S*G+c]*p_val[S*G+c]
+ * The reference is the G==1 case.  Top-k order: score descending, row ascending on ties.
+ */
+#ifndef DHR_B200_H
+#define DHR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DHR_B200_VERSION 100
+
+/* status codes */
+#define DHR_OK               0
+#define DHR_ERR_INVALID      1   /* bad argument (NULL, negative size, unknown dtype ...)            */
+#define DHR_ERR_CUDA         2   /* a CUDA runtime call failed; dhr_last_cuda_error() has the text */
+#define DHR_ERR_NOMEM        3   /* device or host allocation failed                                */
+#define DHR_ERR_UNSUPPORTED  4   /* shape outside the supported envelope (group > 8, k > DHR_MAX_K) */
+#define DHR_ERR_LOSSY        5   /* fp32 corpus value not representable in fp16 (index is fp16)     */
+#define DHR_ERR_IDX_RANGE    6   /* corpus slice index negative or above the code range             */
+#define DHR_ERR_STATE        7   /* call order violated (append after finalize, search before ...)  */
+#define DHR_ERR_NO_DEVICE    8   /* no usable CUDA device                                           */
+
+/* slice-index dtypes accepted on either side (encode.py:157,166 uint8; densify_corpus.py:31-34
+ * int16 / int8; densify_query.py:73 int16; north_star uint16).  Equality is on the integer value. */
+#define DHR_IDX_NONE 0
+#define DHR_IDX_U8   1
+#define DHR_IDX_I8   2
+#define DHR_IDX_I16  3
+#define DHR_IDX_U16  4
+#define DHR_IDX_I32  5
+#define DHR_IDX_I64  6
+
+/* value dtypes: the on-disk index is fp16 (encode.py:156,165); the reference CPU path hands
+ * fp32 copies of the same numbers to GIP_retrieval (gip_retrieval.py:275,313). */
+#define DHR_VAL_F16 0
+#define DHR_VAL_F32 1
+
+/* dhr_search flags */
+#define DHR_SEARCH_UNMASKED 1u   /* --IP first stage (gip_retrieval.py:139): plain inner product over all columns */
+
+/* dhr_index_create flags */
+#define DHR_INDEX_NARROW_CODES 1u /* store 16-bit slice indices as 8-bit codes (all values must be < 254) */
+
+#define DHR_MAX_K     12288      /* largest k handled by the fused selection (candidate capacity 16384) */
+#define DHR_MAX_GROUP 8
+
+typedef struct dhr_index dhr_index;
+
+/* timing / accounting of the last dhr_search on an index (filled when profiling is enabled) */
+typedef struct dhr_stats {
+    int32_t  n_queries;
+    int32_t  query_block;        /* QB: queries scored per corpus row visit by one scan CTA          */
+    int32_t  query_groups;       /* groups of QB queries sharing one launch                          */
+    int32_t  scan_variant;       /* 0 = direct 128-bit loads, 1 = TMA bulk (cp.async.bulk) staging   */
+    int32_t  n_scan_launches;
+    int32_t  n_select_launches;
+    int32_t  n_prep_launches;
+    int32_t  n_fallback_queries; /* queries re-run with the overflow-proof chunk schedule            */
+    int32_t  n_kernel_launches;  /* every kernel launched by the call (prep, init, scan, select, ...)   */
+    int32_t  reserved0;
+    double   scan_ms;            /* sum of CUDA-event durations of the scan launches                 */
+    double   select_ms;          /* ... of the top-k selection launches                              */
+    double   total_ms;           /* first launch to last launch of the search, CUDA events           */
+    double   corpus_passes;      /* logical corpus passes made by the scan launches (sum rows*groups / N) */
+    double   bytes_per_pass;     /* N * row_bytes of the HBM-resident layout                         */
+} dhr_stats;
+
+int         dhr_version(void);
+const char* dhr_strerror(int status);
+const char* dhr_last_cuda_error(void);
+int         dhr_device_count(int* count);
+
+/* ---- index lifetime -----------------------------------------------------------------------
+ * Replaces the load + H2D of gip_retrieval.py:289-315 (pickle -> slice shard -> .cuda()).
+ * The index keeps its own HBM-resident copy: fp16 lexical values, slice-index codes and the
+ * fp16 dense block in three row-major arrays (see DESIGN.md "HBM layout").
+ * row_offset is the global id of local row 0: a range shard built by the rule of
+ * gip_retrieval.py:292-306 passes its first row here so results carry global rows. */
+int dhr_index_create(dhr_index** out, int device, int64_t n_rows_capacity, int n_slices, int group,
+                     int n_dense, int idx_dtype, int64_t row_offset, unsigned flags);
+/* Append n rows.  vals: [n, n_slices*group + n_dense] (row stride in ELEMENTS), idx: [n, n_slices]
+ * (ignored when n_slices == 0).  Host or device pointers. */
+int dhr_index_append(dhr_index* h, int64_t n, int val_dtype, const void* vals, int64_t val_row_stride,
+                     int idx_dtype, const void* idx, int64_t idx_row_stride);
+/* Validates what was appended (fp16 representability, index range) and makes the index searchable. */
+int dhr_index_finalize(dhr_index* h);
+/* create + append + finalize in one call */
+int dhr_index_open(dhr_index** out, int device, int64_t n_rows, int n_slices, int group, int n_dense,
+                   int val_dtype, const void* vals, int64_t val_row_stride,
+                   int idx_dtype, const void* idx, int64_t idx_row_stride, int64_t row_offset, unsigned flags);
+int dhr_index_close(dhr_index* h);
+int dhr_index_rows(const dhr_index* h, int64_t* n_rows);
+int dhr_index_row_bytes(const dhr_index* h, int64_t* bytes);   /* HBM bytes per row of the resident layout */
+
+/* options: "scan_variant" (0|1), "query_block" (1|2|4|8), "query_groups" (1..64), "profile" (0|1) */
+int dhr_index_set_option(dhr_index* h, const char* name, int64_t value);
+int dhr_index_get_stats(const dhr_index* h, dhr_stats* out);
+
+/* ---- search -------------------------------------------------------------------------------
+ * Replaces GIP_retrieval exact branch (gip_retrieval.py:88-126,158-165), IP_retrieval (:60-85,
+ * pass n_slices==0 index / q_idx NULL) and, with DHR_SEARCH_UNMASKED, the --IP first stage (:139).
+ * q_vals [Q, W] fp16 or fp32 (the reference passes fp32), q_idx [Q, n_slices] any DHR_IDX_* dtype.
+ * lamda multiplies the last n_dense query columns in fp32 exactly like :281-283 (pass 1 if the
+ * caller already scaled).  Outputs [Q, k]: scores fp32, rows int64 (global = row_offset + local),
+ * sorted by (score desc, row asc); when the index holds fewer than k rows the tail is
+ * (-inf, -1) and out_counts[q] (optional) holds the number of valid entries.
+ * Stream-ordered on `stream` (a cudaStream_t, NULL = default stream); the call returns after the
+ * results have reached out_scores/out_rows. One search at a time per index. */
+int dhr_search(dhr_index* h, int n_queries, int q_val_dtype, const void* q_vals, int64_t q_val_row_stride,
+               int q_idx_dtype, const void* q_idx, int64_t q_idx_row_stride, float lamda, int k,
+               unsigned flags, float* out_scores, int64_t* out_rows, int32_t* out_counts, void* stream);
+
+/* Exact GIP on given candidate rows (rerank, gip_retrieval.py:142-150 and :205-215):
+ * cand_rows [Q, M] LOCAL row ids (< 0 = skip).  Outputs as dhr_search (rows are global). */
+int dhr_rerank(dhr_index* h, int n_queries, int q_val_dtype, const void* q_vals, int64_t q_val_row_stride,
+               int q_idx_dtype, const void* q_idx, int64_t q_idx_row_stride, float lamda,
+               const int64_t* cand_rows, int n_cand, int k, float* out_scores, int64_t* out_rows,
+               int32_t* out_counts, void* stream);
+
+/* Merge P per-shard top-k lists (replaces retrieval/merge.result.py:20-43 and is the step after
+ * the NCCL all-gather): scores/rows [P, Q, k] -> [Q, k] by (score desc, row asc); rows < 0 are padding.
+ * Runs on `device`; pointers may be host or device. */
+int dhr_topk_merge(int device, int n_parts, int n_queries, int k, const float* scores, const int64_t* rows,
+                   float* out_scores, int64_t* out_rows, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DHR_B200_H */

@@ -1,0 +1,274 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden vectors produced by the real
+reference and against the CPU oracle on seeded inputs.  Run on the B200 box: pytest -m gpu."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, has_cuda
+from helpers import make_case, assert_matches_oracle, tie_groups_equal
+
+pytestmark = pytest.mark.gpu
+
+if has_cuda():
+    import torch
+    from dhr_b200 import GipIndex, topk_merge, _cabi as C
+    from oracle import gip_oracle as go
+
+
+def _golden_queries(g):
+    return g['q_vals'].astype(np.float32)
+
+
+GRID = ['delade_g1_u8_grid', 'bm25_i16_grid', 'unicoil_i8_i16_grid', 'grouped_g6_u16_grid', 'grouped_g3_u16_grid',
+        'delade_lamda_grid']
+
+
+@pytest.mark.parametrize('variant', [0, 1])
+@pytest.mark.parametrize('name', GRID)
+def test_golden_grid_bit_exact(name, variant):
+    """Grid fixtures: the reference's fp32 scores are order-independent, so our score lists must be
+    bit-identical to the reference's and rows must agree inside tie groups."""
+    g = load_golden(name)
+    S, G, k = int(g['S']), int(g['G']), int(g['topk'])
+    lam = float(g['lamda']) if 'lamda' in g else 1.0
+    with GipIndex.from_arrays(g['c_vals'], g['c_idx'], n_slices=S, group=G) as ix:
+        ix.set_option('scan_variant', variant)
+        scores, rows, counts = ix.search(_golden_queries(g), g['q_idx'], k, lamda=lam)
+    assert np.array_equal(scores.astype(np.float64), g['ref_scores'])
+    for i in range(rows.shape[0]):
+        assert tie_groups_equal(rows[i], g['ref_rows'][i], scores[i])
+    case = dict(S=S, G=G, C=int(g['C']), c_vals=g['c_vals'], c_idx=g['c_idx'], q_vals=g['q_vals'], q_idx=g['q_idx'])
+    assert_matches_oracle(case, scores, rows, counts, k, lamda=lam, exact=True)
+
+
+@pytest.mark.parametrize('variant', [0, 1])
+def test_golden_gauss_within_tolerance(variant):
+    g = load_golden('delade_g1_u8_gauss')
+    S, G, k = int(g['S']), int(g['G']), int(g['topk'])
+    with GipIndex.from_arrays(g['c_vals'], g['c_idx'], n_slices=S, group=G) as ix:
+        ix.set_option('scan_variant', variant)
+        scores, rows, counts = ix.search(_golden_queries(g), g['q_idx'], k)
+    assert np.abs(scores - g['ref_scores']).max() < 1e-3          # north_star tolerance
+    assert np.mean(rows == g['ref_rows']) > 0.99                  # ranks identical outside fp32-noise ties
+    case = dict(S=S, G=G, C=int(g['C']), c_vals=g['c_vals'], c_idx=g['c_idx'], q_vals=g['q_vals'], q_idx=g['q_idx'])
+    assert_matches_oracle(case, scores, rows, counts, k)
+
+
+@pytest.mark.parametrize('name', ['dense_ip_gauss', 'dense_ip_grid_k_gt_n'])
+def test_golden_dense_only(name):
+    g = load_golden(name)
+    k = int(g['topk'])
+    n = g['c_vals'].shape[0]
+    with GipIndex.from_arrays(g['c_vals'], None) as ix:
+        scores, rows, counts = ix.search(_golden_queries(g), None, min(k, C.MAX_K))
+    kk = min(k, n)
+    assert np.all(counts == kk)
+    assert np.abs(scores[:, :kk] - g['ref_scores']).max() < 1e-3
+    case = dict(S=0, G=1, C=int(g['C']), c_vals=g['c_vals'], c_idx=None, q_vals=g['q_vals'], q_idx=None)
+    assert_matches_oracle(case, scores, rows, counts, min(k, C.MAX_K))
+
+
+SHAPES = [
+    # S, G, C, R, c_idx dtype, q_idx dtype
+    (64, 1, 32, 39, np.uint8, np.uint8),
+    (40, 1, 0, 39, np.int8, np.int16),          # S not a multiple of 16 -> padded slices
+    (48, 2, 16, 100, np.int16, np.int16),
+    (32, 3, 0, 3466, np.uint16, np.uint16),
+    (24, 4, 24, 39, np.uint8, np.int64),
+    (16, 5, 8, 39, np.int32, np.int32),
+    (128, 6, 768, 39, np.uint16, np.uint16),    # BASELINE config 2 row shape
+    (16, 7, 100, 39, np.uint8, np.uint8),       # C not a multiple of 8 -> padded columns
+    (24, 8, 40, 39, np.uint16, np.uint8),
+    (0, 1, 768, 1, np.uint8, np.uint8),         # dense only
+    (768, 1, 128, 39, np.uint8, np.uint8),      # reference-true DeLADE shape
+]
+
+
+@pytest.mark.parametrize('variant', [0, 1])
+@pytest.mark.parametrize('qb', [1, 2, 4, 8])
+@pytest.mark.parametrize('shape', SHAPES)
+def test_oracle_parity_shapes(shape, qb, variant):
+    S, G, Cd, R, cdt, qdt = shape
+    case = make_case(100 + S + G + Cd, 3000, 11, S, G, Cd, R, cdt, qdt)
+    k = 100
+    with GipIndex.from_arrays(case['c_vals'], case['c_idx'] if S else None, n_slices=S, group=G) as ix:
+        ix.set_option('scan_variant', variant)
+        ix.set_option('query_block', qb)
+        scores, rows, counts = ix.search(case['q_vals'], case['q_idx'] if S else None, k)
+    assert_matches_oracle(case, scores, rows, counts, k)
+
+
+@pytest.mark.parametrize('variant', [0, 1])
+@pytest.mark.parametrize('qb', [1, 4])
+def test_fp32_queries_lamda_and_unmasked(qb, variant):
+    case = make_case(7, 4000, 9, 64, 3, 40, 39, np.uint8, np.int16, q_fp32_noise=True)
+    k = 50
+    with GipIndex.from_arrays(case['c_vals'], case['c_idx'], n_slices=64, group=3) as ix:
+        ix.set_option('scan_variant', variant)
+        ix.set_option('query_block', qb)
+        s1, r1, c1 = ix.search(case['q_vals'], case['q_idx'], k, lamda=0.37)
+        s2, r2, c2 = ix.search(case['q_vals'], None, k, masked=False)
+    assert_matches_oracle(case, s1, r1, c1, k, lamda=0.37)
+    assert_matches_oracle(case, s2, r2, c2, k, masked=False)
+
+
+def test_grid_many_shapes_bit_exact():
+    """Exact-arithmetic inputs: every kernel variant must give the identical, deterministic answer."""
+    for (S, G, Cd) in [(32, 1, 16), (16, 6, 64), (32, 3, 0)]:
+        case = make_case(5 + G, 5000, 10, S, G, Cd, 8, np.uint8, np.uint8, c_density=0.5, q_density=0.5, grid=True)
+        k = 200
+        outs = []
+        with GipIndex.from_arrays(case['c_vals'], case['c_idx'], n_slices=S, group=G) as ix:
+            for variant in (0, 1):
+                for qb in (1, 2, 4, 8):
+                    ix.set_option('scan_variant', variant)
+                    ix.set_option('query_block', qb)
+                    outs.append(ix.search(case['q_vals'], case['q_idx'], k))
+        assert_matches_oracle(case, *outs[0], k, exact=True)
+        for o in outs[1:]:
+            assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])
+
+
+def test_edge_cases_k_gt_n_single_row_all_ties():
+    case = make_case(3, 37, 5, 16, 1, 8, 5, grid=True)
+    with GipIndex.from_arrays(case['c_vals'], case['c_idx'], n_slices=16) as ix:
+        s, r, c = ix.search(case['q_vals'], case['q_idx'], 100)
+        assert_matches_oracle(case, s, r, c, 100, exact=True)
+    one = make_case(4, 1, 3, 16, 1, 8, 5, grid=True)
+    with GipIndex.from_arrays(one['c_vals'], one['c_idx'], n_slices=16) as ix:
+        s, r, c = ix.search(one['q_vals'], one['q_idx'], 1)
+        assert_matches_oracle(one, s, r, c, 1, exact=True)
+    # all scores equal (zero queries): ties must resolve to the lowest rows
+    z = make_case(5, 50000, 3, 16, 1, 8, 5, grid=True)
+    z['q_vals'][:] = 0
+    with GipIndex.from_arrays(z['c_vals'], z['c_idx'], n_slices=16) as ix:
+        s, r, c = ix.search(z['q_vals'], z['q_idx'], 1000)
+    assert np.all(s == 0) and np.array_equal(r, np.tile(np.arange(1000), (3, 1)))
+
+
+def test_adversarial_ascending_scores_use_overflow_fallback():
+    """Scores increase with the row index, so every row beats the running threshold: the candidate buffer
+    overflows and the query is re-run with the overflow-proof schedule.  Result must still be exact."""
+    n = 120000
+    c_vals = np.zeros((n, 8), np.float16)
+    c_vals[:, 0] = (np.arange(n) // 64).astype(np.float16)        # non-decreasing, many ties, exact in fp16
+    q_vals = np.zeros((2, 8), np.float32)
+    q_vals[0, 0] = 1.0
+    q_vals[1, 0] = -1.0                                           # descending for the second query: no overflow
+    case = dict(S=0, G=1, C=8, c_vals=c_vals, c_idx=None, q_vals=q_vals, q_idx=None)
+    with GipIndex.from_arrays(c_vals, None) as ix:
+        s, r, c = ix.search(q_vals, None, 1000)
+        st = ix.stats()
+    assert st['n_fallback_queries'] >= 1
+    assert_matches_oracle(case, s, r, c, 1000, exact=True)
+
+
+@pytest.mark.parametrize('k', [1, 1000, 4096, 10000])
+def test_k_range(k):
+    case = make_case(11, 60000, 3, 32, 1, 16, 39)
+    with GipIndex.from_arrays(case['c_vals'], case['c_idx'], n_slices=32) as ix:
+        s, r, c = ix.search(case['q_vals'], case['q_idx'], k)
+    assert_matches_oracle(case, s, r, c, k)
+
+
+def test_device_pointers_and_strided_inputs():
+    case = make_case(13, 5000, 6, 32, 2, 16, 39, np.int16, np.int16)
+    dev = torch.device('cuda', 0)
+    cv = torch.from_numpy(case['c_vals']).to(dev)
+    ci = torch.from_numpy(case['c_idx']).to(dev)
+    wide = torch.zeros((6, case['q_vals'].shape[1] + 5), dtype=torch.float32, device=dev)
+    wide[:, :case['q_vals'].shape[1]] = torch.from_numpy(case['q_vals']).to(dev)
+    qv = wide[:, :case['q_vals'].shape[1]]                        # row stride > width
+    qi = torch.from_numpy(case['q_idx']).to(dev)
+    with GipIndex.from_arrays(cv, ci, n_slices=32, group=2) as ix:
+        s, r, c = ix.search(qv, qi, 64)
+        assert s.is_cuda and r.is_cuda
+        assert_matches_oracle(case, s.cpu().numpy(), r.cpu().numpy(), c.cpu().numpy(), 64)
+        # fp16 queries from the host give the same answer
+        s2, r2, c2 = ix.search(case['q_vals'].astype(np.float16), case['q_idx'], 64)
+    assert np.array_equal(r2, r.cpu().numpy())
+
+
+def test_fp32_corpus_lossless_and_lossy():
+    case = make_case(17, 2000, 4, 16, 1, 8, 39)
+    with GipIndex.from_arrays(case['c_vals'].astype(np.float32), case['c_idx'], n_slices=16) as ix:
+        s, r, c = ix.search(case['q_vals'], case['q_idx'], 20)
+    assert_matches_oracle(case, s, r, c, 20)
+    bad = case['c_vals'].astype(np.float32)
+    bad[5, 3] = 0.1                                               # not an fp16 number
+    with pytest.raises(C.DhrError) as e:
+        GipIndex.from_arrays(bad, case['c_idx'], n_slices=16)
+    assert e.value.status == C.ERR_LOSSY
+
+
+def test_error_paths():
+    case = make_case(19, 100, 2, 16, 1, 8, 39)
+    with GipIndex.from_arrays(case['c_vals'], case['c_idx'], n_slices=16) as ix:
+        with pytest.raises(C.DhrError) as e:
+            ix.search(case['q_vals'], case['q_idx'], C.MAX_K + 1)
+        assert e.value.status == C.ERR_UNSUPPORTED
+        with pytest.raises(ValueError):
+            ix.search(case['q_vals'][:, :-1], case['q_idx'], 5)
+        with pytest.raises(C.DhrError):
+            ix.search(case['q_vals'], case['q_idx'], 0)
+    big = case['c_idx'].astype(np.uint8).copy()
+    big[0, 0] = 255
+    cv = case['c_vals'].copy()
+    cv[0, 0] = 1.0
+    with pytest.raises(C.DhrError) as e:
+        GipIndex.from_arrays(cv, big, n_slices=16)
+    assert e.value.status == C.ERR_IDX_RANGE
+    ix = GipIndex(16, 8, capacity=10)
+    with pytest.raises(C.DhrError) as e:                          # search before finalize
+        ix.search(case['q_vals'], case['q_idx'], 5)
+    assert e.value.status == C.ERR_STATE
+    ix.close()
+
+
+def test_rerank_and_merge():
+    case = make_case(23, 8000, 5, 32, 1, 16, 39, grid=True)
+    k = 40
+    rng = np.random.default_rng(0)
+    cand = np.stack([rng.choice(8000, size=500, replace=False) for _ in range(5)]).astype(np.int64)
+    with GipIndex.from_arrays(case['c_vals'], case['c_idx'], n_slices=32) as ix:
+        s, r, c = ix.rerank(case['q_vals'], case['q_idx'], cand, k)
+        full = ix.search(case['q_vals'], case['q_idx'], k)
+    ex = go.gip_scores_f64(case['q_vals'], case['q_idx'], case['c_vals'], case['c_idx'], 32, 1)
+    for i in range(5):
+        sub = ex[i][cand[i]]
+        order = np.lexsort((cand[i], -sub))[:k]
+        assert np.array_equal(r[i], cand[i][order]) and np.array_equal(s[i].astype(np.float64), sub[order])
+    # shard merge == single shard (same tie rule)
+    parts_s, parts_r = [], []
+    for sh in range(3):
+        lo, hi = go.shard_bounds(8000, 3, sh)
+        with GipIndex.from_arrays(case['c_vals'][lo:hi], case['c_idx'][lo:hi], n_slices=32, row_offset=lo) as ix:
+            ps, pr, _ = ix.search(case['q_vals'], case['q_idx'], k)
+        parts_s.append(ps)
+        parts_r.append(pr)
+    ms, mr = topk_merge(np.stack(parts_s), np.stack(parts_r))
+    assert np.array_equal(ms, full[0]) and np.array_equal(mr, full[1])
+    ms2, mr2 = topk_merge(torch.from_numpy(np.stack(parts_s)).cuda(), torch.from_numpy(np.stack(parts_r)).cuda())
+    assert np.array_equal(ms2.cpu().numpy(), full[0]) and np.array_equal(mr2.cpu().numpy(), full[1])
+
+
+def test_medium_config2_shape_against_c_oracle():
+    """BASELINE config 2 row shape at 200k rows, 12 queries, top-1000, every query block and both variants."""
+    from dhr_b200 import synth
+    cv, ci = synth.corpus_numpy('delade_cls', 0, 200000)
+    qv, qi = synth.queries_numpy('delade_cls', 12)
+    case = dict(S=128, G=6, C=768, c_vals=cv, c_idx=ci, q_vals=qv.astype(np.float32), q_idx=qi)
+    with GipIndex.from_arrays(cv, ci, n_slices=128, group=6) as ix:
+        assert ix.row_bytes == 3328
+        base = None
+        for variant in (0, 1):
+            for qb in (1, 4, 8):
+                ix.set_option('scan_variant', variant)
+                ix.set_option('query_block', qb)
+                out = ix.search(qv, qi, 1000)
+                if base is None:
+                    base = out
+                    assert_matches_oracle(case, *out, 1000)
+                else:
+                    assert np.array_equal(out[1], base[1]) and np.array_equal(out[0], base[0])
