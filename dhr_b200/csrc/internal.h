@@ -59,9 +59,9 @@ struct dhr_index {
     dhr::TopkState topk;
     float* d_out_scores = nullptr; int64_t* d_out_rows = nullptr; int32_t* d_out_counts = nullptr; size_t out_capacity = 0;
     // options
-    int opt_scan_variant = 0;
-    int opt_query_block = 4;
-    int opt_query_groups = 16;
+    int opt_scan_variant = 1;            // TMA bulk staging (measured faster than direct loads at QB=1 and QB=8)
+    int opt_query_block = 8;
+    int opt_query_groups = 8;
     int opt_profile = 0;
     int num_sms = 148;
     dhr_stats stats{};
