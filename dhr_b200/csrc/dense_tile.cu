@@ -1,0 +1,303 @@
+// dense_tile.cu -- K2: dense [CLS] x corpus block on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
+//
+// Replaces the dense part of the masked row dot of castorini/dhr retrieval/gip_retrieval.py:119-120
+// (the always-matching [CLS] tail, :110-113) and IP_retrieval's einsum (:74) for a tile of 64
+// queries at once: D[128 passages x 64 queries] (fp32, TMEM) = A[128 x C] (corpus rows, fp16,
+// K-major, TMA 128B-swizzled tiles streamed through a ring) x B[64 x C]^T (queries, resident in
+// shared memory for the whole launch).  One thread issues tcgen05.mma; accumulators are double
+// buffered in TMEM and drained with tcgen05.ld by four epilogue warps that either
+//   - apply the strict admission threshold and append candidates (dense-only index), or
+//   - write the tile to the L2-resident scratch consumed by the lexical kernel K1t (hybrid index).
+// Warp roles: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..5 epilogue.
+#include <cuda.h>
+
+#include "internal.h"
+
+namespace dhr {
+
+constexpr int kDT_M = 128;             // passages per tile (UMMA M)
+constexpr int kDT_N = 64;              // queries per tile (UMMA N)
+constexpr int kDT_KB = 64;             // fp16 elements per K block = 128 bytes = one swizzle atom row
+constexpr int kDT_ABytes = kDT_M * kDT_KB * 2;   // 16 KiB per A stage
+constexpr int kDT_BBytes = kDT_N * kDT_KB * 2;   //  8 KiB per resident B block
+constexpr int kDT_Threads = 192;
+constexpr int kDT_MaxStages = 8;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives lane (base_lane + i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile whose rows are 128 bytes apart (8-row groups 1024 bytes apart):
+// start address >> 4 | LBO = 1 (ignored for swizzled K-major) | SBO = 1024 >> 4 | version 1 | SWIZZLE_128B (2)
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16: fp16 A and B, fp32 accumulate, both K-major, M = 128, N = 64
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct DenseTileArgs {
+    long long row_begin, row_end;      // rows of this launch; row_begin is a multiple of 128 relative to tile_row0
+    long long tile_row0;               // first row of tile 0
+    int n_tiles;                       // 128-row tiles in the launch
+    int n_kblocks;                     // ceil(C_pad / 64)
+    int n_stages;
+    int n_qtiles;                      // 64-query tiles in flight
+    int n_queries;                     // valid queries in flight (slots)
+    int mode;                          // 0 = filter + append, 1 = write scratch
+    float* scratch;                    // [slot][scratch_rows]  (mode 1), rows relative to tile_row0
+    long long scratch_rows;
+    float* tau; uint32_t* cnt; float* cand_score; int32_t* cand_row; int cap;
+};
+
+__global__ void __launch_bounds__(kDT_Threads, 1)
+dense_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const DenseTileArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[kDT_MaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kDT_MaxStages];
+    __shared__ __align__(8) uint64_t b_bar;
+    __shared__ __align__(8) uint64_t tfull_bar[2];
+    __shared__ __align__(8) uint64_t tempty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ float tau_s[kDT_N];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x % a.n_qtiles;
+    const int cta_in_q = blockIdx.x / a.n_qtiles;
+    const int ctas_per_q = gridDim.x / a.n_qtiles;
+
+    // SWIZZLE_128B operand tiles must sit on 1024-byte boundaries of the shared address space
+    uint8_t* smem_b = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);   // n_kblocks x 8 KiB
+    uint8_t* smem_a = smem_b + (size_t)a.n_kblocks * kDT_BBytes;       // n_stages x 16 KiB
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&b_bar, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        mbar_fence_init();
+    }
+    if (threadIdx.x < kDT_N) {
+        const int q = qt * kDT_N + threadIdx.x;
+        tau_s[threadIdx.x] = (q < a.n_queries && a.mode == 0) ? a.tau[q] : INFINITY;
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, 2 * kDT_N);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&b_bar, (uint32_t)a.n_kblocks * kDT_BBytes);
+            for (int kb = 0; kb < a.n_kblocks; ++kb)
+                tma_load_2d(smem_b + (size_t)kb * kDT_BBytes, &tmap_b, &b_bar, kb * kDT_KB, qt * kDT_N);
+            int s = 0; uint32_t ph = 0;
+            for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q) {
+                const int row0 = (int)(a.tile_row0 + (long long)t * kDT_M);
+                for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    mbar_arrive_expect_tx(&full_bar[s], kDT_ABytes);
+                    tma_load_2d(smem_a + (size_t)s * kDT_ABytes, &tmap_a, &full_bar[s], kb * kDT_KB, row0);
+                    if (++s == a.n_stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(kDT_M, kDT_N);
+            mbar_wait(&b_bar, 0);
+            tc_fence_after();
+            int s = 0; uint32_t ph = 0;
+            int i = 0;
+            for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q, ++i) {
+                const int buf = i & 1;
+                mbar_wait(&tempty_bar[buf], (((uint32_t)i >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)buf * kDT_N;
+                for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem_a + (size_t)s * kDT_ABytes);
+                    const uint32_t b_addr = smem_u32(smem_b + (size_t)kb * kDT_BBytes);
+#pragma unroll
+                    for (int k = 0; k < kDT_KB / 16; ++k) {
+                        umma_f16(d_tmem, umma_smem_desc(a_addr + k * 32), umma_smem_desc(b_addr + k * 32), idesc,
+                                 (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[s]);          // frees the A stage once these MMAs have read it
+                    if (++s == a.n_stages) { s = 0; ph ^= 1u; }
+                }
+                umma_commit(&tfull_bar[buf]);            // accumulator tile complete
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM lane quarter = warp % 4 =====
+        const int quarter = warp & 3;
+        const int p = quarter * 32 + lane;               // row of the tile owned by this thread
+        int i = 0;
+        for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q, ++i) {
+            const int buf = i & 1;
+            mbar_wait(&tfull_bar[buf], ((uint32_t)i >> 1) & 1u);
+            tc_fence_after();
+            uint32_t v0[32], v1[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * kDT_N;
+            tmem_ld_32x32(taddr, v0);
+            tmem_ld_32x32(taddr + 32, v1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+            const long long row = a.tile_row0 + (long long)t * kDT_M + p;
+            const bool row_ok = row >= a.row_begin && row < a.row_end;
+            if (a.mode == 1) {
+                if (row_ok) {
+                    float* dst = a.scratch + (size_t)(qt * kDT_N) * a.scratch_rows + (size_t)(row - a.tile_row0);
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) dst[(size_t)q * a.scratch_rows] = __uint_as_float(v0[q]);
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) dst[(size_t)(q + 32) * a.scratch_rows] = __uint_as_float(v1[q]);
+                }
+            } else if (row_ok) {
+#pragma unroll
+                for (int q = 0; q < kDT_N; ++q) {
+                    const float sc = __uint_as_float(q < 32 ? v0[q & 31] : v1[q & 31]) + 0.0f;
+                    if (sc > tau_s[q]) {
+                        const int slot = qt * kDT_N + q;
+                        const uint32_t pos = atomicAdd(a.cnt + slot, 1u);
+                        if (pos < (uint32_t)a.cap) {
+                            a.cand_score[(size_t)slot * a.cap + pos] = sc;
+                            a.cand_row[(size_t)slot * a.cap + pos] = (int32_t)row;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * kDT_N);
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) { cudaGetLastError(); return nullptr; }
+    fn = (EncodeTiledFn)p;
+    return fn;
+}
+
+// 2-D fp16 row-major tensor [rows][cols] with row pitch `pitch_elems`; box = 64 columns x box_rows, 128B swizzle
+static int make_tmap_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return DHR_ERR_CUDA;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {pitch_elems * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kDT_KB, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled", __FILE__, __LINE__);
+        return DHR_ERR_CUDA;
+    }
+    return DHR_OK;
+}
+
+bool dense_tile_supported(const Geometry& g, int* n_stages_out) {
+    if (g.C_pad <= 0) return false;
+    const int nkb = (g.C_pad + kDT_KB - 1) / kDT_KB;
+    const size_t budget = 220 * 1024;
+    const size_t b_bytes = (size_t)nkb * kDT_BBytes;
+    if (b_bytes + 2 * (size_t)kDT_ABytes > budget) return false;
+    int stages = (int)((budget - b_bytes) / kDT_ABytes);
+    if (stages > kDT_MaxStages) stages = kDT_MaxStages;
+    if (n_stages_out) *n_stages_out = stages;
+    return true;
+}
+
+// Launch K2 over rows [row_begin, row_end) (row_begin aligned to 128 from tile_row0) for `n_queries` in-flight queries
+// whose fp16 dense block starts at q_dns16 (row pitch C_pad).
+int launch_dense_tile(const dhr_index* h, const void* q_dns16, int n_queries, long long tile_row0, long long row_begin,
+                      long long row_end, int mode, float* scratch, long long scratch_rows, const TopkState& t, int cap,
+                      cudaStream_t st) {
+    const Geometry& g = h->g;
+    int stages = 0;
+    if (!dense_tile_supported(g, &stages)) return DHR_ERR_UNSUPPORTED;
+    if (row_end <= row_begin || n_queries <= 0) return DHR_OK;
+    CUtensorMap tmap_a, tmap_b;
+    DHR_TRY(make_tmap_f16(&tmap_a, h->dns, (uint64_t)h->n_rows, (uint64_t)g.C_pad, (uint64_t)g.C_pad, kDT_M));
+    DHR_TRY(make_tmap_f16(&tmap_b, q_dns16, (uint64_t)n_queries, (uint64_t)g.C_pad, (uint64_t)g.C_pad, kDT_N));
+    DenseTileArgs a{};
+    a.row_begin = row_begin; a.row_end = row_end; a.tile_row0 = tile_row0;
+    const long long first_tile = (row_begin - tile_row0) / kDT_M;
+    a.tile_row0 = tile_row0 + first_tile * kDT_M;
+    a.n_tiles = (int)((row_end - a.tile_row0 + kDT_M - 1) / kDT_M);
+    a.n_kblocks = (g.C_pad + kDT_KB - 1) / kDT_KB;
+    a.n_stages = stages;
+    a.n_qtiles = (n_queries + kDT_N - 1) / kDT_N;
+    a.n_queries = n_queries;
+    a.mode = mode;
+    a.scratch = scratch ? scratch + (a.tile_row0 - tile_row0) : nullptr;
+    a.scratch_rows = scratch_rows;
+    a.tau = t.tau; a.cnt = t.cnt; a.cand_score = t.cand_score; a.cand_row = t.cand_row; a.cap = cap;
+    const size_t smem = (size_t)a.n_kblocks * kDT_BBytes + (size_t)stages * kDT_ABytes + 1024;
+    DHR_CUDA(cudaFuncSetAttribute(dense_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_q = h->num_sms / a.n_qtiles;
+    if (per_q < 1) per_q = 1;
+    if (per_q > a.n_tiles) per_q = a.n_tiles;
+    dense_tile_kernel<<<(unsigned)(per_q * a.n_qtiles), kDT_Threads, smem, st>>>(tmap_a, tmap_b, a);
+    DHR_CUDA(cudaGetLastError());
+    return DHR_OK;
+}
+
+}  // namespace dhr

@@ -7,7 +7,8 @@
 namespace dhr {
 
 constexpr int kCandCap = 16384;          // candidate slots per in-flight query (fits a 128 KiB smem sort)
-constexpr int kMaxInflight = 64;         // query slots per super-batch (query_block * query_groups)
+constexpr int kMaxInflight = 256;        // query slots per super-batch
+constexpr int kMaxScanInflight = 64;     // row-scan path: query_block * query_groups
 
 struct Geometry {
     int S = 0, G = 1, C = 0;             // slices, values per slice, dense columns (user shape)
@@ -63,6 +64,7 @@ struct dhr_index {
     int opt_query_block = 8;
     int opt_query_groups = 8;
     int opt_profile = 0;
+    int opt_tile_mode = 1;               // use the tensor-core tile kernels when the shape allows
     int num_sms = 148;
     dhr_stats stats{};
     dhr::EventPool events;
@@ -95,6 +97,11 @@ int launch_prep_queries(dhr_index* h, int n, int val_dtype, const void* vals, in
                         const void* idx, int64_t istride, float lamda, cudaStream_t st);
 
 int launch_rerank(const dhr_index* h, const ScanArgs& a, bool q_f32, const long long* d_cand, int n_cand, cudaStream_t st);
+
+bool dense_tile_supported(const Geometry& g, int* n_stages_out);
+int launch_dense_tile(const dhr_index* h, const void* q_dns16, int n_queries, long long tile_row0, long long row_begin,
+                      long long row_end, int mode, float* scratch, long long scratch_rows, const TopkState& t, int cap,
+                      cudaStream_t st);
 
 int ensure_device_buffer(void** p, size_t* cur, size_t need);
 bool is_device_pointer(const void* p);

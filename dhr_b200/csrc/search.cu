@@ -159,21 +159,21 @@ static int ensure_out_buffers(dhr_index* h, size_t n_queries, int k) {
 }
 
 // chunk boundaries (row indices).  growth <= 1 selects the overflow-proof uniform schedule.
-static std::vector<long long> chunk_schedule(long long n_rows, int k, int cap, bool safe) {
+static std::vector<long long> chunk_schedule(long long n_rows, int k, int cap, bool safe, long long align = 1) {
     std::vector<long long> b;
     b.push_back(0);
-    const long long first = std::min<long long>(n_rows, (long long)cap - k);
+    const long long first = std::min<long long>(n_rows, ((long long)cap - k) / align * align);
     if (n_rows == 0) return b;
     b.push_back(first);
     if (safe) {
-        while (b.back() < n_rows) b.push_back(std::min<long long>(n_rows, b.back() + (cap - k)));
+        while (b.back() < n_rows) b.push_back(std::min<long long>(n_rows, b.back() + (cap - k) / align * align));
         return b;
     }
     double growth = 1.0 + (double)(cap - k) / (2.0 * k);
     growth = std::min(8.0, std::max(1.25, growth));
     while (b.back() < n_rows) {
-        long long next = (long long)ceil((double)b.back() * growth);
-        if (next <= b.back()) next = b.back() + 1;
+        long long next = (long long)ceil((double)b.back() * growth) / align * align;
+        if (next <= b.back()) next = b.back() + align;
         b.push_back(std::min(n_rows, next));
     }
     return b;
@@ -250,6 +250,37 @@ static int run_batch(dhr_index* h, const QuerySet& qs, int base, int nq, int k, 
         h->stats.n_kernel_launches++;
     }
     h->stats.scan_variant = variant;
+    return DHR_OK;
+}
+
+// dense-only index on the tensor-core tile kernel (K2): same chunk schedule, 128-row aligned
+static int run_batch_dense_tile(dhr_index* h, const QuerySet& qs, int base, int nq, int k, float* d_scores, int64_t* d_rows,
+                                int32_t* d_counts, cudaStream_t st) {
+    TopkState t = h->topk;
+    init_slots_kernel<<<1, kMaxInflight, 0, st>>>(t, kMaxInflight);
+    DHR_CUDA(cudaGetLastError());
+    h->stats.n_kernel_launches++;
+    const std::vector<long long> bounds = chunk_schedule(h->n_rows, k, kCandCap, false, 128);
+    const size_t n_chunks = bounds.size() - 1;
+    const void* q16 = qs.dns + (size_t)base * qs.dns_stride;
+    for (size_t c = 0; c < n_chunks; ++c) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+        if (h->opt_profile) { e0 = h->events.get(); e1 = h->events.get(); e2 = h->events.get(); cudaEventRecord(e0, st); }
+        DHR_TRY(launch_dense_tile(h, q16, nq, 0, bounds[c], bounds[c + 1], 0, nullptr, 0, t, kCandCap, st));
+        if (h->opt_profile) cudaEventRecord(e1, st);
+        DHR_TRY(launch_select(t, nq, k, kCandCap, c + 1 == n_chunks, h->row_offset, d_scores, d_rows, d_counts, base, st));
+        if (h->opt_profile) cudaEventRecord(e2, st);
+        h->stats.n_scan_launches++;
+        h->stats.n_select_launches++;
+        h->stats.n_kernel_launches += 2;
+        h->stats.corpus_passes += (double)(bounds[c + 1] - bounds[c]) * ((nq + 63) / 64) / (double)std::max<int64_t>(1, h->n_rows);
+    }
+    if (n_chunks == 0) {
+        DHR_TRY(launch_select(t, nq, k, kCandCap, true, h->row_offset, d_scores, d_rows, d_counts, base, st));
+        h->stats.n_select_launches++;
+        h->stats.n_kernel_launches++;
+    }
+    h->stats.scan_variant = 2;
     return DHR_OK;
 }
 
@@ -354,15 +385,20 @@ extern "C" int dhr_search(dhr_index* h, int n_queries, int q_val_dtype, const vo
     do {
         if ((status = (cudaMemsetAsync(d_overflow, 0, (size_t)n_queries * sizeof(uint32_t), st) == cudaSuccess) ? DHR_OK : DHR_ERR_CUDA)) break;
         const QuerySet qs = query_set(h, need_f32 != 0);
-        const int qb = h->opt_query_block;
+        int qb = h->opt_query_block;
         int groups = h->opt_query_groups;
-        if (qb * groups > kMaxInflight) groups = kMaxInflight / qb;
-        const int slots = qb * groups;
+        if (qb * groups > kMaxScanInflight) groups = kMaxScanInflight / qb;
+        int slots = qb * groups;
+        // tensor-core tile path: dense-only index (or unmasked search of an index without lexical part),
+        // queries exactly representable in fp16
+        const bool tile_dense = h->opt_tile_mode && g.S == 0 && !qs.f32 && dense_tile_supported(g, nullptr);
+        if (tile_dense) { slots = kMaxInflight; qb = 64; groups = kMaxInflight / 64; }
         h->stats.query_block = qb;
         h->stats.query_groups = groups;
         for (int base = 0; base < n_queries && status == DHR_OK; base += slots) {
             const int nq = std::min(slots, n_queries - base);
-            status = run_batch(h, qs, base, nq, k, masked, false, qb, d_scores, d_rows, d_counts, st);
+            status = tile_dense ? run_batch_dense_tile(h, qs, base, nq, k, d_scores, d_rows, d_counts, st)
+                                : run_batch(h, qs, base, nq, k, masked, false, qb, d_scores, d_rows, d_counts, st);
             if (status == DHR_OK) {
                 carry_overflow_kernel<<<1, kMaxInflight, 0, st>>>(h->topk.overflow, d_overflow, base, nq);
                 h->stats.n_kernel_launches++;

@@ -272,3 +272,29 @@ def test_medium_config2_shape_against_c_oracle():
                     assert_matches_oracle(case, *out, 1000)
                 else:
                     assert np.array_equal(out[1], base[1]) and np.array_equal(out[0], base[0])
+
+
+@pytest.mark.parametrize('cdim', [768, 64, 100, 200])
+def test_dense_tile_tensor_core_path(cdim):
+    """Dense-only index: the tcgen05 tile kernel (K2) must agree with the oracle and with the SIMT row scan."""
+    case = make_case(31 + cdim, 70000, 150, 0, 1, cdim, 1)
+    k = 100
+    with GipIndex.from_arrays(case['c_vals'], None) as ix:
+        ix.set_option('tile_mode', 1)
+        s1, r1, c1 = ix.search(case['q_vals'], None, k)
+        st = ix.stats()
+        ix.set_option('tile_mode', 0)
+        s0, r0, c0 = ix.search(case['q_vals'], None, k)
+    assert st['scan_variant'] == 2, 'tile path not taken'
+    assert_matches_oracle(case, s1, r1, c1, k)
+    assert np.abs(s1 - s0).max() < 1e-4
+    assert np.mean(r1 == r0) > 0.995
+
+
+def test_dense_tile_grid_bit_exact_and_ties():
+    case = make_case(37, 40000, 70, 0, 1, 128, 1, grid=True)
+    k = 500
+    with GipIndex.from_arrays(case['c_vals'], None) as ix:
+        s1, r1, c1 = ix.search(case['q_vals'], None, k)
+        assert ix.stats()['scan_variant'] == 2
+    assert_matches_oracle(case, s1, r1, c1, k, exact=True)
