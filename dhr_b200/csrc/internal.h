@@ -50,6 +50,9 @@ struct dhr_index {
     __half* lexv = nullptr;              // [capacity][D_pad]
     uint8_t* lexi = nullptr;             // [capacity][S_pad] codes (uint8 or uint16)
     __half* dns = nullptr;               // [capacity][C_pad]
+    uint8_t* lext = nullptr;             // tiled lexical copy for K1t: [tile of 256 rows][8-slice chunk]{codes[256][8] | vals[8][256][G]}
+    size_t lext_bytes = 0;
+    int max_code = -1;                   // largest slice code stored (known after finalize)
     int* d_flags = nullptr;              // [4] device-side validation flags (lossy, idx range, query needs fp32, spare)
     // staging for host -> device appends / queries
     void* stage_a = nullptr; size_t stage_a_bytes = 0;
@@ -58,6 +61,10 @@ struct dhr_index {
     void* q_lex16 = nullptr; void* q_lex32 = nullptr; void* q_dns16 = nullptr; void* q_dns32 = nullptr; void* q_code = nullptr;
     int q_capacity = 0;
     dhr::TopkState topk;
+    // tile-mode workspace
+    uint8_t* qblocks = nullptr; size_t qblocks_bytes = 0;
+    uint32_t* qblock_bytes = nullptr; size_t qblock_bytes_cap = 0;
+    float* scratch = nullptr; size_t scratch_bytes = 0;
     float* d_out_scores = nullptr; int64_t* d_out_rows = nullptr; int32_t* d_out_counts = nullptr; size_t out_capacity = 0;
     // options
     int opt_scan_variant = 1;            // TMA bulk staging (measured faster than direct loads at QB=1 and QB=8)
@@ -97,6 +104,21 @@ int launch_prep_queries(dhr_index* h, int n, int val_dtype, const void* vals, in
                         const void* idx, int64_t istride, float lamda, cudaStream_t st);
 
 int launch_rerank(const dhr_index* h, const ScanArgs& a, bool q_f32, const long long* d_cand, int n_cand, cudaStream_t st);
+
+struct LexTileGeom {
+    int G, code_bytes, n_chunks, rt;
+    int pblock_bytes, qoff_bytes, qblock_stride, stage_bytes;
+};
+constexpr int kLexTileRows = 256;        // passages per K1t tile
+constexpr int kLexTileQueries = 128;     // queries per K1t tile
+constexpr int kLexTileSlices = 8;        // slices per chunk
+LexTileGeom lex_tile_geom(const Geometry& g, int rt);
+bool lex_tile_supported(const Geometry& g, int rt);
+int launch_lex_tile_prep(const dhr_index* h, const LexTileGeom& t, const void* q_lex16, const void* q_code, int n_queries,
+                         uint8_t* qblocks, uint32_t* qblock_bytes, cudaStream_t st);
+int launch_lex_tile(const dhr_index* h, const LexTileGeom& t, const uint8_t* qblocks, const uint32_t* qblock_bytes, int n_queries,
+                    long long row_begin, long long row_end, const float* scratch, long long scratch_rows, long long scratch_row0,
+                    const TopkState& tk, int cap, cudaStream_t st);
 
 bool dense_tile_supported(const Geometry& g, int* n_stages_out);
 int launch_dense_tile(const dhr_index* h, const void* q_dns16, int n_queries, long long tile_row0, long long row_begin,

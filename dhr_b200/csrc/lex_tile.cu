@@ -1,0 +1,347 @@
+// lex_tile.cu -- K1t: tiled lexical match-and-MAC for a tile of 128 queries, fused with the
+// admission filter.  Throughput-mode counterpart of the row scan K1 (scan_rows.cuh).
+//
+// Replaces, for 128 queries at once, the masked product + row dot of castorini/dhr
+// retrieval/gip_retrieval.py:119-120 restricted to the lexical columns:
+//     lex[q][p] = sum_s [q_idx[s] == p_idx[s]] * sum_g q_val[s,g] * p_val[s,g]
+// without comparing every (query, passage, slice) triple: per query tile and slice the queries are
+// bucketed by their slice index (code) -- an offset table off[slice][code] over a packed entry list
+// {query id, G fp16 values} -- so a passage thread looks up the bucket of ITS code and touches only
+// the queries that really match.  Work is O(matches), not O(Q*N*S).
+//
+// Data movement: one producer warp streams, per (passage tile, 8-slice chunk), the tiled corpus
+// block (codes [256][8] | values [8][256][G]) and the query-tile block (offsets | entries) with
+// TMA bulk copies (cp.async.bulk + mbarrier ring) into shared memory; 256 consumer threads own one
+// passage each and keep acc[128 queries][256 passages] fp32 in shared memory (column p is private
+// to thread p: conflict-free, no atomics, deterministic summation order).  acc is initialised
+// from the dense scores written by K2 (hybrid index) or zero, and after the last chunk each thread
+// applies the strict threshold tau[q] and appends winners to the candidate lists.
+#include "internal.h"
+
+namespace dhr {
+
+constexpr int kLT_PT = kLexTileRows;    // passages per tile = consumer threads
+constexpr int kLT_QT = kLexTileQueries; // queries per tile
+constexpr int kLT_SC = kLexTileSlices;  // slices per chunk
+constexpr int kLT_Stages = 2;
+constexpr int kLT_Threads = kLT_PT + 32;
+
+__host__ __device__ constexpr int lt_entry_words(int G) { return (G + 2) / 2; }          // {qid, v0..vG-1} as fp16 pairs
+__host__ __device__ constexpr int lt_pval_words(int G) { return (G + 1) / 2; }
+
+
+LexTileGeom lex_tile_geom(const Geometry& g, int rt) {
+    LexTileGeom t{};
+    t.G = g.G; t.code_bytes = g.code_bytes; t.n_chunks = g.S_pad / kLT_SC; t.rt = rt;
+    t.pblock_bytes = kLT_PT * kLT_SC * (g.code_bytes + 2 * g.G);
+    t.qoff_bytes = (int)round_up((int64_t)kLT_SC * (rt + 1) * 2, 16);
+    t.qblock_stride = t.qoff_bytes + kLT_SC * kLT_QT * lt_entry_words(g.G) * 4;
+    t.stage_bytes = (int)round_up(t.pblock_bytes, 128) + (int)round_up(t.qblock_stride, 128);
+    return t;
+}
+
+size_t lex_tile_smem_bytes(const LexTileGeom& t) {
+    return (size_t)kLT_QT * kLT_PT * 4 + (size_t)kLT_Stages * t.stage_bytes + 128;
+}
+
+bool lex_tile_supported(const Geometry& g, int rt) {
+    if (g.S_pad <= 0 || g.S_pad % kLT_SC != 0 || rt < 1 || rt > 256 || g.G > 8) return false;
+    return lex_tile_smem_bytes(lex_tile_geom(g, rt)) <= 227 * 1024;
+}
+
+// ---- query-tile preparation: one CTA per (chunk, query tile) builds offsets + entries ------------
+// Entries of a bucket are ordered by query id, buckets by (slice, code).
+template <typename CodeT>
+__global__ void __launch_bounds__(256)
+lex_tile_prep_kernel(const __half* __restrict__ q_lex16, const CodeT* __restrict__ q_code, int n_queries, int S_pad, int G,
+                     int rt, int qoff_bytes, int qblock_stride, uint8_t* __restrict__ qblocks, uint32_t* __restrict__ qblock_bytes) {
+    extern __shared__ uint32_t hist[];             // [SC][rt + 1] counts, then exclusive offsets
+    const int chunk = blockIdx.x, qt = blockIdx.y;
+    const int n_chunks = gridDim.x;
+    const int q0 = qt * kLT_QT;
+    const int nq = min(kLT_QT, n_queries - q0);
+    const int tbl = kLT_SC * (rt + 1);
+    for (int i = threadIdx.x; i < tbl; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nq * kLT_SC; i += blockDim.x) {
+        const int q = i / kLT_SC, j = i % kLT_SC;
+        const uint32_t code = q_code[(size_t)(q0 + q) * S_pad + chunk * kLT_SC + j];
+        if (code < (uint32_t)rt) atomicAdd(&hist[j * (rt + 1) + code], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                        // exclusive scan over (slice, code); bucket rt of every slice = end marker
+        uint32_t run = 0;
+        for (int i = 0; i < tbl; ++i) { const uint32_t c = hist[i]; hist[i] = run; run += c; }
+    }
+    __syncthreads();
+    uint8_t* blk = qblocks + ((size_t)qt * n_chunks + chunk) * qblock_stride;
+    uint16_t* off = (uint16_t*)blk;
+    for (int i = threadIdx.x; i < tbl; i += blockDim.x) off[i] = (uint16_t)hist[i];
+    const int EW = lt_entry_words(G);
+    uint32_t* ent = (uint32_t*)(blk + qoff_bytes);
+    if (threadIdx.x < kLT_SC) {                    // placement, sequential in q so that buckets are ordered by query id
+        const int j = threadIdx.x;
+        const int s = chunk * kLT_SC + j;
+        for (int q = 0; q < nq; ++q) {
+            const uint32_t code = q_code[(size_t)(q0 + q) * S_pad + s];
+            if (code >= (uint32_t)rt) continue;
+            const uint32_t pos = hist[j * (rt + 1) + code]++;
+            const __half* v = q_lex16 + ((size_t)(q0 + q) * S_pad + s) * G;
+            uint32_t* e = ent + (size_t)pos * EW;
+            uint32_t w = (uint32_t)q;
+            for (int g = 0; g < G; ++g) {          // half index g + 1 of the entry
+                const uint32_t hv = __half_as_ushort(v[g]);
+                if ((g + 1) & 1) { w |= hv << 16; e[(g + 1) >> 1] = w; w = 0; }
+                else w = hv;
+            }
+            if (((G + 1) & 1) == 0) { /* last half landed in a high slot: already stored */ }
+            else e[(G + 1) >> 1] = w;              // trailing low half (+ zero pad)
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // total entries = offset of the end marker of the last slice after placement == final hist value there
+        const uint32_t total = hist[(kLT_SC - 1) * (rt + 1) + rt];
+        qblock_bytes[(size_t)qt * n_chunks + chunk] = ((uint32_t)qoff_bytes + total * (uint32_t)EW * 4u + 15u) & ~15u;
+    }
+}
+
+// f32 += f16 * f16 with independent half selection of both operands
+template <bool AHI, bool BHI>
+__device__ __forceinline__ float fma_h_sel(uint32_t a, uint32_t b, float c) {
+    float d;
+    if constexpr (AHI && BHI)
+        asm("{\n\t.reg .f16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\tfma.rn.f32.f16 %0, ah, bh, %3;\n\t}" : "=f"(d) : "r"(a), "r"(b), "f"(c));
+    else if constexpr (AHI && !BHI)
+        asm("{\n\t.reg .f16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\tfma.rn.f32.f16 %0, ah, bl, %3;\n\t}" : "=f"(d) : "r"(a), "r"(b), "f"(c));
+    else if constexpr (!AHI && BHI)
+        asm("{\n\t.reg .f16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\tfma.rn.f32.f16 %0, al, bh, %3;\n\t}" : "=f"(d) : "r"(a), "r"(b), "f"(c));
+    else
+        asm("{\n\t.reg .f16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\tfma.rn.f32.f16 %0, al, bl, %3;\n\t}" : "=f"(d) : "r"(a), "r"(b), "f"(c));
+    return d;
+}
+
+template <int G, int g>
+__device__ __forceinline__ float entry_dot(const uint32_t* e, const uint32_t* pv, float t) {
+    if constexpr (g < G) {
+        t = fma_h_sel<((g + 1) & 1) != 0, (g & 1) != 0>(e[(g + 1) >> 1], pv[g >> 1], t);
+        return entry_dot<G, g + 1>(e, pv, t);
+    } else {
+        return t;
+    }
+}
+
+struct LexTileArgs {
+    const uint8_t* lext;               // tiled corpus blocks [tile][chunk]
+    const uint8_t* qblocks;            // query blocks [qtile][chunk] (stride qblock_stride)
+    const uint32_t* qblock_bytes;      // bytes to copy per query block
+    long long row_begin, row_end;      // rows handled by this launch (row_begin multiple of 256)
+    long long n_rows;
+    int n_tiles;                       // tiles in [row_begin, row_end)
+    int n_chunks, rt;
+    int pblock_bytes, qoff_bytes, qblock_stride, stage_bytes, pblock_smem;
+    int n_qtiles;                      // query tiles in flight
+    int n_queries;                     // valid in-flight queries (slots)
+    const float* scratch;              // dense scores [slot][scratch_rows] or nullptr
+    long long scratch_rows; long long scratch_row0;
+    float* tau; uint32_t* cnt; float* cand_score; int32_t* cand_row; int cap;
+};
+
+template <int G, typename CodeT>
+__global__ void __launch_bounds__(kLT_Threads, 1) lex_tile_kernel(const __grid_constant__ LexTileArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[kLT_Stages];
+    __shared__ __align__(8) uint64_t empty_bar[kLT_Stages];
+    __shared__ float tau_s[kLT_QT];
+
+    constexpr int EW = lt_entry_words(G);
+    constexpr int PW = lt_pval_words(G);
+    float* acc = (float*)smem;                                            // [QT][PT]
+    uint8_t* stages = smem + (size_t)kLT_QT * kLT_PT * 4;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x % a.n_qtiles;
+    const int cta_in_q = blockIdx.x / a.n_qtiles;
+    const int ctas_per_q = gridDim.x / a.n_qtiles;
+    const int q0 = qt * kLT_QT;
+    const int nq = min(kLT_QT, a.n_queries - q0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kLT_Stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kLT_PT / 32); }
+        mbar_fence_init();
+    }
+    if (threadIdx.x < kLT_QT) tau_s[threadIdx.x] = threadIdx.x < nq ? a.tau[q0 + threadIdx.x] : INFINITY;
+    __syncthreads();
+
+    const long long tile0 = a.row_begin / kLT_PT;
+
+    if (warp == kLT_PT / 32) {
+        // ===== producer warp =====
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q) {
+                const uint8_t* ptile = a.lext + (size_t)(tile0 + t) * a.n_chunks * a.pblock_bytes;
+                for (int c = 0; c < a.n_chunks; ++c) {
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    const uint32_t qb = a.qblock_bytes[(size_t)qt * a.n_chunks + c];
+                    uint8_t* dst = stages + (size_t)s * a.stage_bytes;
+                    mbar_arrive_expect_tx(&full_bar[s], (uint32_t)a.pblock_bytes + qb);
+                    bulk_g2s(dst, ptile + (size_t)c * a.pblock_bytes, (uint32_t)a.pblock_bytes, &full_bar[s]);
+                    bulk_g2s(dst + a.pblock_smem, a.qblocks + ((size_t)qt * a.n_chunks + c) * a.qblock_stride, qb, &full_bar[s]);
+                    if (++s == kLT_Stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers: thread p owns passage p of the tile =====
+    const int p = threadIdx.x;
+    const int offs_per_slice = a.rt + 1;
+    int s = 0; uint32_t ph = 0;
+    for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q) {
+        const long long row = (tile0 + t) * kLT_PT + p;
+        const bool row_ok = row >= a.row_begin && row < a.row_end && row < a.n_rows;
+        // acc init: dense score of (q, row) from K2 or zero
+        if (a.scratch && row_ok) {
+            const float* src = a.scratch + (size_t)q0 * a.scratch_rows + (size_t)(row - a.scratch_row0);
+            for (int q = 0; q < nq; ++q) acc[q * kLT_PT + p] = src[(size_t)q * a.scratch_rows];
+            for (int q = nq; q < kLT_QT; ++q) acc[q * kLT_PT + p] = 0.f;
+        } else {
+            for (int q = 0; q < kLT_QT; ++q) acc[q * kLT_PT + p] = 0.f;
+        }
+        for (int c = 0; c < a.n_chunks; ++c) {
+            mbar_wait(&full_bar[s], ph);
+            const uint8_t* st = stages + (size_t)s * a.stage_bytes;
+            const CodeT* codes = (const CodeT*)st + (size_t)p * kLT_SC;
+            const uint32_t* pvals = (const uint32_t*)(st + (size_t)kLT_PT * kLT_SC * sizeof(CodeT));
+            const uint16_t* off = (const uint16_t*)(st + a.pblock_smem);
+            const uint32_t* ent = (const uint32_t*)(st + a.pblock_smem + a.qoff_bytes);
+            uint32_t cw[kLT_SC * sizeof(CodeT) / 4];
+            if constexpr (sizeof(CodeT) == 1) { const uint2 v = *(const uint2*)codes; cw[0] = v.x; cw[1] = v.y; }
+            else { const uint4 v = *(const uint4*)codes; cw[0] = v.x; cw[1] = v.y; cw[2] = v.z; cw[3] = v.w; }
+#pragma unroll
+            for (int j = 0; j < kLT_SC; ++j) {
+                uint32_t code;
+                if constexpr (sizeof(CodeT) == 1) code = (cw[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                else code = (cw[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+                if (code < (uint32_t)a.rt) {
+                    const uint32_t beg = off[j * offs_per_slice + code], end = off[j * offs_per_slice + code + 1];
+                    if (beg < end) {
+                        uint32_t pv[PW];
+                        const uint32_t* src = pvals + ((size_t)j * kLT_PT + p) * G / 2;
+                        if constexpr (G % 2 == 0) {
+#pragma unroll
+                            for (int w = 0; w < PW; ++w) pv[w] = src[w];
+                        } else {   // odd G: a passage's G halves straddle word boundaries for odd (j*PT + p)
+                            const uint16_t* h16 = (const uint16_t*)pvals + ((size_t)j * kLT_PT + p) * G;
+#pragma unroll
+                            for (int w = 0; w < PW; ++w) {
+                                const uint32_t lo = h16[2 * w];
+                                const uint32_t hi = (2 * w + 1 < G) ? h16[2 * w + 1] : 0u;
+                                pv[w] = lo | (hi << 16);
+                            }
+                        }
+                        for (uint32_t e = beg; e < end; ++e) {
+                            uint32_t ew[EW];
+                            const uint32_t* ep = ent + (size_t)e * EW;
+                            if constexpr (EW == 4) { const uint4 v = *(const uint4*)ep; ew[0] = v.x; ew[1] = v.y; ew[2] = v.z; ew[3] = v.w; }
+                            else if constexpr (EW == 2) { const uint2 v = *(const uint2*)ep; ew[0] = v.x; ew[1] = v.y; }
+                            else {
+#pragma unroll
+                                for (int w = 0; w < EW; ++w) ew[w] = ep[w];
+                            }
+                            const uint32_t q = ew[0] & 0xFFFFu;
+                            float* ap = acc + q * kLT_PT + p;
+                            *ap = entry_dot<G, 0>(ew, pv, *ap);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+            if (++s == kLT_Stages) { s = 0; ph ^= 1u; }
+        }
+        // admission filter
+        if (row_ok) {
+            for (int q = 0; q < nq; ++q) {
+                const float sc = acc[q * kLT_PT + p] + 0.0f;
+                if (sc > tau_s[q]) {
+                    const int slot = q0 + q;
+                    const uint32_t pos = atomicAdd(a.cnt + slot, 1u);
+                    if (pos < (uint32_t)a.cap) {
+                        a.cand_score[(size_t)slot * a.cap + pos] = sc;
+                        a.cand_row[(size_t)slot * a.cap + pos] = (int32_t)row;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+int launch_lex_tile_prep(const dhr_index* h, const LexTileGeom& t, const void* q_lex16, const void* q_code, int n_queries,
+                         uint8_t* qblocks, uint32_t* qblock_bytes, cudaStream_t st) {
+    const Geometry& g = h->g;
+    const int n_qtiles = (n_queries + kLT_QT - 1) / kLT_QT;
+    if (n_qtiles == 0) return DHR_OK;
+    dim3 grid((unsigned)t.n_chunks, (unsigned)n_qtiles);
+    const size_t smem = (size_t)kLT_SC * (t.rt + 1) * sizeof(uint32_t);
+    if (g.code_bytes == 1)
+        lex_tile_prep_kernel<uint8_t><<<grid, 256, smem, st>>>((const __half*)q_lex16, (const uint8_t*)q_code, n_queries, g.S_pad, g.G,
+                                                               t.rt, t.qoff_bytes, t.qblock_stride, qblocks, qblock_bytes);
+    else
+        lex_tile_prep_kernel<uint16_t><<<grid, 256, smem, st>>>((const __half*)q_lex16, (const uint16_t*)q_code, n_queries, g.S_pad, g.G,
+                                                                t.rt, t.qoff_bytes, t.qblock_stride, qblocks, qblock_bytes);
+    DHR_CUDA(cudaGetLastError());
+    return DHR_OK;
+}
+
+template <int G, typename CodeT>
+static int launch_lex_tile_t(const dhr_index* h, const LexTileArgs& a, size_t smem, cudaStream_t st) {
+    auto kern = lex_tile_kernel<G, CodeT>;
+    DHR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_q = h->num_sms / a.n_qtiles;
+    if (per_q < 1) per_q = 1;
+    if (per_q > a.n_tiles) per_q = a.n_tiles;
+    kern<<<(unsigned)(per_q * a.n_qtiles), kLT_Threads, smem, st>>>(a);
+    DHR_CUDA(cudaGetLastError());
+    return DHR_OK;
+}
+
+template <typename CodeT>
+static int launch_lex_tile_g(const dhr_index* h, const LexTileArgs& a, size_t smem, cudaStream_t st) {
+    switch (h->g.G) {
+        case 1: return launch_lex_tile_t<1, CodeT>(h, a, smem, st);
+        case 2: return launch_lex_tile_t<2, CodeT>(h, a, smem, st);
+        case 3: return launch_lex_tile_t<3, CodeT>(h, a, smem, st);
+        case 4: return launch_lex_tile_t<4, CodeT>(h, a, smem, st);
+        case 5: return launch_lex_tile_t<5, CodeT>(h, a, smem, st);
+        case 6: return launch_lex_tile_t<6, CodeT>(h, a, smem, st);
+        case 7: return launch_lex_tile_t<7, CodeT>(h, a, smem, st);
+        case 8: return launch_lex_tile_t<8, CodeT>(h, a, smem, st);
+        default: return DHR_ERR_UNSUPPORTED;
+    }
+}
+
+int launch_lex_tile(const dhr_index* h, const LexTileGeom& t, const uint8_t* qblocks, const uint32_t* qblock_bytes, int n_queries,
+                    long long row_begin, long long row_end, const float* scratch, long long scratch_rows, long long scratch_row0,
+                    const TopkState& tk, int cap, cudaStream_t st) {
+    if (row_end <= row_begin || n_queries <= 0) return DHR_OK;
+    LexTileArgs a{};
+    a.lext = h->lext; a.qblocks = qblocks; a.qblock_bytes = qblock_bytes;
+    a.row_begin = row_begin; a.row_end = row_end; a.n_rows = h->n_rows;
+    a.n_tiles = (int)((row_end - row_begin / kLT_PT * kLT_PT + kLT_PT - 1) / kLT_PT);
+    a.n_chunks = t.n_chunks; a.rt = t.rt;
+    a.pblock_bytes = t.pblock_bytes; a.qoff_bytes = t.qoff_bytes; a.qblock_stride = t.qblock_stride;
+    a.stage_bytes = t.stage_bytes; a.pblock_smem = (int)round_up(t.pblock_bytes, 128);
+    a.n_qtiles = (n_queries + kLT_QT - 1) / kLT_QT;
+    a.n_queries = n_queries;
+    a.scratch = scratch; a.scratch_rows = scratch_rows; a.scratch_row0 = scratch_row0;
+    a.tau = tk.tau; a.cnt = tk.cnt; a.cand_score = tk.cand_score; a.cand_row = tk.cand_row; a.cap = cap;
+    const size_t smem = lex_tile_smem_bytes(t);
+    if (h->g.code_bytes == 1) return launch_lex_tile_g<uint8_t>(h, a, smem, st);
+    return launch_lex_tile_g<uint16_t>(h, a, smem, st);
+}
+
+}  // namespace dhr

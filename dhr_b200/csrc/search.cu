@@ -284,6 +284,80 @@ static int run_batch_dense_tile(dhr_index* h, const QuerySet& qs, int base, int 
     return DHR_OK;
 }
 
+// hybrid / lexical index on the tile kernels: per sub-chunk of rows K2 writes the dense scores of the
+// in-flight queries to an L2-resident scratch, K1t adds the lexical part and filters.
+constexpr long long kTileSubRows = 37888;        // 148 K1t tiles of 256 rows (two per CTA with 2 query tiles in flight)
+
+static int ensure_tile_workspace(dhr_index* h, const LexTileGeom& t, int n_queries) {
+    const size_t n_qtiles = (size_t)(n_queries + kLexTileQueries - 1) / kLexTileQueries + 2;
+    const size_t qb_need = n_qtiles * t.n_chunks * (size_t)t.qblock_stride;
+    if (qb_need > h->qblocks_bytes) {
+        if (h->qblocks) cudaFree(h->qblocks);
+        h->qblocks = nullptr; h->qblocks_bytes = 0;
+        DHR_CUDA(cudaMalloc(&h->qblocks, qb_need));
+        h->qblocks_bytes = qb_need;
+    }
+    const size_t nb_need = n_qtiles * t.n_chunks * sizeof(uint32_t);
+    if (nb_need > h->qblock_bytes_cap) {
+        if (h->qblock_bytes) cudaFree(h->qblock_bytes);
+        h->qblock_bytes = nullptr; h->qblock_bytes_cap = 0;
+        DHR_CUDA(cudaMalloc(&h->qblock_bytes, nb_need));
+        h->qblock_bytes_cap = nb_need;
+    }
+    const size_t sc_need = h->g.C_pad > 0 ? (size_t)kMaxInflight * kTileSubRows * sizeof(float) : 0;
+    if (sc_need > h->scratch_bytes) {
+        if (h->scratch) cudaFree(h->scratch);
+        h->scratch = nullptr; h->scratch_bytes = 0;
+        DHR_CUDA(cudaMalloc(&h->scratch, sc_need));
+        h->scratch_bytes = sc_need;
+    }
+    return DHR_OK;
+}
+
+static int run_batch_hybrid_tile(dhr_index* h, const LexTileGeom& lt, const QuerySet& qs, int base, int nq, int k,
+                                 float* d_scores, int64_t* d_rows, int32_t* d_counts, cudaStream_t st) {
+    const Geometry& g = h->g;
+    TopkState t = h->topk;
+    init_slots_kernel<<<1, kMaxInflight, 0, st>>>(t, kMaxInflight);
+    DHR_CUDA(cudaGetLastError());
+    h->stats.n_kernel_launches++;
+    const std::vector<long long> bounds = chunk_schedule(h->n_rows, k, kCandCap, false, kLexTileRows);
+    const size_t n_chunks = bounds.size() - 1;
+    const void* q16 = qs.dns + (size_t)base * qs.dns_stride;
+    const size_t qt0 = (size_t)base / kLexTileQueries;
+    const uint8_t* qblocks = h->qblocks + qt0 * lt.n_chunks * (size_t)lt.qblock_stride;
+    const uint32_t* qbytes = h->qblock_bytes + qt0 * lt.n_chunks;
+    for (size_t c = 0; c < n_chunks; ++c) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+        if (h->opt_profile) { e0 = h->events.get(); e1 = h->events.get(); e2 = h->events.get(); cudaEventRecord(e0, st); }
+        for (long long r0 = bounds[c]; r0 < bounds[c + 1]; r0 += kTileSubRows) {
+            const long long r1 = std::min(bounds[c + 1], r0 + kTileSubRows);
+            if (g.C_pad > 0) {
+                DHR_TRY(launch_dense_tile(h, q16, nq, r0, r0, r1, 1, h->scratch, kTileSubRows, t, kCandCap, st));
+                h->stats.n_kernel_launches++;
+            }
+            DHR_TRY(launch_lex_tile(h, lt, qblocks, qbytes, nq, r0, r1, g.C_pad > 0 ? h->scratch : nullptr, kTileSubRows, r0, t,
+                                    kCandCap, st));
+            h->stats.n_kernel_launches++;
+            h->stats.n_scan_launches++;
+        }
+        if (h->opt_profile) cudaEventRecord(e1, st);
+        DHR_TRY(launch_select(t, nq, k, kCandCap, c + 1 == n_chunks, h->row_offset, d_scores, d_rows, d_counts, base, st));
+        if (h->opt_profile) cudaEventRecord(e2, st);
+        h->stats.n_select_launches++;
+        h->stats.n_kernel_launches++;
+        h->stats.corpus_passes += (double)(bounds[c + 1] - bounds[c]) * ((nq + kLexTileQueries - 1) / kLexTileQueries) /
+                                  (double)std::max<int64_t>(1, h->n_rows);
+    }
+    if (n_chunks == 0) {
+        DHR_TRY(launch_select(t, nq, k, kCandCap, true, h->row_offset, d_scores, d_rows, d_counts, base, st));
+        h->stats.n_select_launches++;
+        h->stats.n_kernel_launches++;
+    }
+    h->stats.scan_variant = 3;
+    return DHR_OK;
+}
+
 // the select kernel sets the sticky per-slot overflow flag; copy it to the per-query array
 __global__ void carry_overflow_kernel(const uint32_t* slot_flags, uint32_t* per_query, int base, int nq) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -393,12 +467,24 @@ extern "C" int dhr_search(dhr_index* h, int n_queries, int q_val_dtype, const vo
         // queries exactly representable in fp16
         const bool tile_dense = h->opt_tile_mode && g.S == 0 && !qs.f32 && dense_tile_supported(g, nullptr);
         if (tile_dense) { slots = kMaxInflight; qb = 64; groups = kMaxInflight / 64; }
+        const int rt = std::max(1, h->max_code + 1);
+        const bool tile_hybrid = h->opt_tile_mode && g.S > 0 && masked && !qs.f32 && lex_tile_supported(g, rt) &&
+                                 (g.C_pad == 0 || dense_tile_supported(g, nullptr));
+        LexTileGeom lt{};
+        if (tile_hybrid) {
+            lt = lex_tile_geom(g, rt);
+            if ((status = ensure_tile_workspace(h, lt, n_queries)) != DHR_OK) break;
+            if ((status = launch_lex_tile_prep(h, lt, h->q_lex16, h->q_code, n_queries, h->qblocks, h->qblock_bytes, st)) != DHR_OK) break;
+            h->stats.n_prep_launches++; h->stats.n_kernel_launches++;
+            slots = kMaxInflight; qb = kLexTileQueries; groups = kMaxInflight / kLexTileQueries;
+        }
         h->stats.query_block = qb;
         h->stats.query_groups = groups;
         for (int base = 0; base < n_queries && status == DHR_OK; base += slots) {
             const int nq = std::min(slots, n_queries - base);
-            status = tile_dense ? run_batch_dense_tile(h, qs, base, nq, k, d_scores, d_rows, d_counts, st)
-                                : run_batch(h, qs, base, nq, k, masked, false, qb, d_scores, d_rows, d_counts, st);
+            if (tile_dense) status = run_batch_dense_tile(h, qs, base, nq, k, d_scores, d_rows, d_counts, st);
+            else if (tile_hybrid) status = run_batch_hybrid_tile(h, lt, qs, base, nq, k, d_scores, d_rows, d_counts, st);
+            else status = run_batch(h, qs, base, nq, k, masked, false, qb, d_scores, d_rows, d_counts, st);
             if (status == DHR_OK) {
                 carry_overflow_kernel<<<1, kMaxInflight, 0, st>>>(h->topk.overflow, d_overflow, base, nq);
                 h->stats.n_kernel_launches++;

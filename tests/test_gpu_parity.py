@@ -16,6 +16,21 @@ if has_cuda():
     from oracle import gip_oracle as go
 
 
+def configure(ix, mode, qb=None):
+    """mode: 'scan0' / 'scan1' = row-scan kernel K1 (direct loads / TMA bulk staging), 'tile' = tensor-core +
+    bucketed tile kernels (K2 + K1t) when the shape allows (falls back to K1 otherwise)."""
+    if mode == 'tile':
+        ix.set_option('tile_mode', 1)
+    else:
+        ix.set_option('tile_mode', 0)
+        ix.set_option('scan_variant', int(mode[-1]))
+    if qb:
+        ix.set_option('query_block', qb)
+
+
+MODES = ['scan0', 'scan1', 'tile']
+
+
 def _golden_queries(g):
     return g['q_vals'].astype(np.float32)
 
@@ -24,7 +39,7 @@ GRID = ['delade_g1_u8_grid', 'bm25_i16_grid', 'unicoil_i8_i16_grid', 'grouped_g6
         'delade_lamda_grid']
 
 
-@pytest.mark.parametrize('variant', [0, 1])
+@pytest.mark.parametrize('variant', MODES)
 @pytest.mark.parametrize('name', GRID)
 def test_golden_grid_bit_exact(name, variant):
     """Grid fixtures: the reference's fp32 scores are order-independent, so our score lists must be
@@ -33,7 +48,7 @@ def test_golden_grid_bit_exact(name, variant):
     S, G, k = int(g['S']), int(g['G']), int(g['topk'])
     lam = float(g['lamda']) if 'lamda' in g else 1.0
     with GipIndex.from_arrays(g['c_vals'], g['c_idx'], n_slices=S, group=G) as ix:
-        ix.set_option('scan_variant', variant)
+        configure(ix, variant)
         scores, rows, counts = ix.search(_golden_queries(g), g['q_idx'], k, lamda=lam)
     assert np.array_equal(scores.astype(np.float64), g['ref_scores'])
     for i in range(rows.shape[0]):
@@ -42,12 +57,12 @@ def test_golden_grid_bit_exact(name, variant):
     assert_matches_oracle(case, scores, rows, counts, k, lamda=lam, exact=True)
 
 
-@pytest.mark.parametrize('variant', [0, 1])
+@pytest.mark.parametrize('variant', MODES)
 def test_golden_gauss_within_tolerance(variant):
     g = load_golden('delade_g1_u8_gauss')
     S, G, k = int(g['S']), int(g['G']), int(g['topk'])
     with GipIndex.from_arrays(g['c_vals'], g['c_idx'], n_slices=S, group=G) as ix:
-        ix.set_option('scan_variant', variant)
+        configure(ix, variant)
         scores, rows, counts = ix.search(_golden_queries(g), g['q_idx'], k)
     assert np.abs(scores - g['ref_scores']).max() < 1e-3          # north_star tolerance
     assert np.mean(rows == g['ref_rows']) > 0.99                  # ranks identical outside fp32-noise ties
@@ -85,28 +100,28 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize('variant', [0, 1])
+@pytest.mark.parametrize('variant', MODES)
 @pytest.mark.parametrize('qb', [1, 2, 4, 8])
 @pytest.mark.parametrize('shape', SHAPES)
 def test_oracle_parity_shapes(shape, qb, variant):
     S, G, Cd, R, cdt, qdt = shape
+    if variant == 'tile' and qb != 1:
+        pytest.skip('query_block only applies to the row scan')
     case = make_case(100 + S + G + Cd, 3000, 11, S, G, Cd, R, cdt, qdt)
     k = 100
     with GipIndex.from_arrays(case['c_vals'], case['c_idx'] if S else None, n_slices=S, group=G) as ix:
-        ix.set_option('scan_variant', variant)
-        ix.set_option('query_block', qb)
+        configure(ix, variant, qb)
         scores, rows, counts = ix.search(case['q_vals'], case['q_idx'] if S else None, k)
     assert_matches_oracle(case, scores, rows, counts, k)
 
 
-@pytest.mark.parametrize('variant', [0, 1])
+@pytest.mark.parametrize('variant', MODES)
 @pytest.mark.parametrize('qb', [1, 4])
 def test_fp32_queries_lamda_and_unmasked(qb, variant):
     case = make_case(7, 4000, 9, 64, 3, 40, 39, np.uint8, np.int16, q_fp32_noise=True)
     k = 50
     with GipIndex.from_arrays(case['c_vals'], case['c_idx'], n_slices=64, group=3) as ix:
-        ix.set_option('scan_variant', variant)
-        ix.set_option('query_block', qb)
+        configure(ix, variant, qb)
         s1, r1, c1 = ix.search(case['q_vals'], case['q_idx'], k, lamda=0.37)
         s2, r2, c2 = ix.search(case['q_vals'], None, k, masked=False)
     assert_matches_oracle(case, s1, r1, c1, k, lamda=0.37)
@@ -120,11 +135,13 @@ def test_grid_many_shapes_bit_exact():
         k = 200
         outs = []
         with GipIndex.from_arrays(case['c_vals'], case['c_idx'], n_slices=S, group=G) as ix:
-            for variant in (0, 1):
+            for variant in ('scan0', 'scan1'):
                 for qb in (1, 2, 4, 8):
-                    ix.set_option('scan_variant', variant)
-                    ix.set_option('query_block', qb)
+                    configure(ix, variant, qb)
                     outs.append(ix.search(case['q_vals'], case['q_idx'], k))
+            configure(ix, 'tile')
+            outs.append(ix.search(case['q_vals'], case['q_idx'], k))
+            assert ix.stats()['scan_variant'] == 3, 'tile path not taken'
         assert_matches_oracle(case, *outs[0], k, exact=True)
         for o in outs[1:]:
             assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])
@@ -262,16 +279,21 @@ def test_medium_config2_shape_against_c_oracle():
     with GipIndex.from_arrays(cv, ci, n_slices=128, group=6) as ix:
         assert ix.row_bytes == 3328
         base = None
-        for variant in (0, 1):
+        for variant in ('scan0', 'scan1'):
             for qb in (1, 4, 8):
-                ix.set_option('scan_variant', variant)
-                ix.set_option('query_block', qb)
+                configure(ix, variant, qb)
                 out = ix.search(qv, qi, 1000)
                 if base is None:
                     base = out
                     assert_matches_oracle(case, *out, 1000)
                 else:
                     assert np.array_equal(out[1], base[1]) and np.array_equal(out[0], base[0])
+        # tile kernels: different (deterministic) summation order -> compare through the oracle
+        configure(ix, 'tile')
+        out = ix.search(qv, qi, 1000)
+        assert ix.stats()['scan_variant'] == 3, 'tile path not taken'
+        assert_matches_oracle(case, *out, 1000)
+        assert np.abs(out[0] - base[0]).max() < 1e-4
 
 
 @pytest.mark.parametrize('cdim', [768, 64, 100, 200])
@@ -298,3 +320,21 @@ def test_dense_tile_grid_bit_exact_and_ties():
         s1, r1, c1 = ix.search(case['q_vals'], None, k)
         assert ix.stats()['scan_variant'] == 2
     assert_matches_oracle(case, s1, r1, c1, k, exact=True)
+
+
+@pytest.mark.parametrize('shape', [(128, 6, 768, 39, np.uint16), (768, 1, 128, 39, np.uint8), (64, 3, 0, 200, np.uint16),
+                                   (40, 1, 32, 39, np.int8), (24, 8, 40, 39, np.uint16), (16, 5, 8, 39, np.int32),
+                                   (16, 7, 100, 39, np.uint8), (48, 2, 16, 100, np.int16), (24, 4, 24, 39, np.uint8)])
+def test_tile_path_many_queries(shape):
+    """Tile kernels with several query tiles in flight (300 queries -> 3 tiles of 128, two super-batches)."""
+    S, G, Cd, R, cdt = shape
+    case = make_case(900 + S + G, 60000, 300, S, G, Cd, R, cdt, cdt)
+    k = 100
+    with GipIndex.from_arrays(case['c_vals'], case['c_idx'], n_slices=S, group=G) as ix:
+        configure(ix, 'tile')
+        s, r, c = ix.search(case['q_vals'], case['q_idx'], k)
+        assert ix.stats()['scan_variant'] == 3, 'tile path not taken'
+    sub = dict(case)
+    sel = np.r_[0:8, 120:136, 250:260, 292:300]
+    sub['q_vals'], sub['q_idx'] = case['q_vals'][sel], case['q_idx'][sel]
+    assert_matches_oracle(sub, s[sel], r[sel], c[sel], k)
