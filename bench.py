@@ -102,34 +102,44 @@ class ClockSampler:
                 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
-def cpu_port_throughput(workload, n_total, rows, n_queries, topk, threads, repeats=1):
-    """Torch-op port of the reference loop (gip_retrieval.py:110-126 / :70-79) on `rows` rows; the
+class CpuPort:
+    """Torch-op port of the reference loop (gip_retrieval.py:110-126 / :70-79) on a bounded sample of `rows` rows; the
     algorithm is exactly linear in N, so q/s at n_total rows = measured q/s * rows / n_total."""
-    import torch
-    from dhr_b200 import synth
-    from oracle import gip_oracle as go
-    cfg = synth.CONFIGS[workload]
-    torch.set_num_threads(threads)
-    cv, ci = synth.corpus_numpy(workload, 0, rows)
-    qv, qi = synth.queries_numpy(workload, n_queries)
-    G = cfg['G']
-    c = torch.from_numpy(cv.astype(np.float32))                    # :313 CPU path works on fp32 copies
-    q = torch.from_numpy(qv.astype(np.float32))
-    qids = list(range(n_queries))
-    k = min(topk, rows)
-    best = None
-    for _ in range(repeats):
+
+    def __init__(self, workload, rows, n_queries, topk, threads):
+        import torch
+        from dhr_b200 import synth
+        from oracle import gip_oracle as go
+        self.go, self.torch = go, torch
+        self.cfg = cfg = synth.CONFIGS[workload]
+        torch.set_num_threads(threads)
+        cv, ci = synth.corpus_numpy(workload, 0, rows)
+        qv, qi = synth.queries_numpy(workload, n_queries)
+        G = cfg['G']
+        self.c = torch.from_numpy(cv.astype(np.float32))              # :313 the CPU path works on fp32 copies
+        self.q = torch.from_numpy(qv.astype(np.float32))
+        self.qids = list(range(n_queries))
+        self.k = min(topk, rows)
+        if cfg['S'] > 0:                                              # G > 1: one idx per value column (SURVEY 8d)
+            self.cidx = torch.from_numpy(np.repeat(ci, G, axis=1).astype(np.int16))
+            self.qidx = torch.from_numpy(np.repeat(qi, G, axis=1).astype(np.int16))
+
+    def run(self):
+        go, cfg = self.go, self.cfg
         t0 = time.perf_counter()
         if cfg['S'] > 0:
-            cidx = torch.from_numpy(np.repeat(ci, G, axis=1).astype(np.int16))   # G>1: one idx per value column
-            qidx = torch.from_numpy(np.repeat(qi, G, axis=1).astype(np.int16))
-            go.GIP_retrieval_port(qids, q, qidx, c, cidx, go.make_args(emb_dim=cfg['S'] * G, topk=k, brute_force=True))
+            go.GIP_retrieval_port(self.qids, self.q, self.qidx, self.c, self.cidx,
+                                  go.make_args(emb_dim=cfg['S'] * cfg['G'], topk=self.k, brute_force=True))
         else:
-            go.IP_retrieval_port(qids, q, c, go.make_args(topk=k))
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    qps_sample = n_queries / best
-    return qps_sample * rows / n_total, best
+            go.IP_retrieval_port(self.qids, self.q, self.c, go.make_args(topk=self.k))
+        return time.perf_counter() - t0
+
+
+def workload_string(workload, n_total, n_q, k):
+    from dhr_b200 import synth
+    cfg = synth.CONFIGS[workload]
+    return '%s: %d passages, %d queries, S=%d x G=%d lexical (%s idx) + %d dense fp16, top-%d' % (
+        workload, n_total, n_q, cfg['S'], cfg['G'], cfg['idx'], cfg['C'], k)
 
 
 def run_reference(args):
@@ -143,22 +153,22 @@ def run_reference(args):
     n_total = args.rows or synth.N_MSMARCO
     threads = os.cpu_count() or 1
     rows = min(args.cpu_rows, n_total)
+    n_q = args.queries or synth.Q_MSMARCO
+    port = CpuPort(args.workload, rows, args.cpu_queries, args.topk, threads)
     times = []
     for i in range(args.warmup + args.steps):
-        _, dt = cpu_port_throughput(args.workload, n_total, rows, args.cpu_queries, args.topk, threads)
+        dt = port.run()
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
     qps = args.cpu_queries / (ms / 1e3) * rows / n_total
-    cfg = synth.CONFIGS[args.workload]
     sample = '%d queries x %d rows per step, torch %s CPU, %d threads, scaled linearly to %d rows' % (
         args.cpu_queries, rows, torch.__version__, threads, n_total)
     line = {
         'impl': 'reference', 'metric': 'queries/sec', 'value': qps, 'unit': 'queries/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': '%s: %d passages, S=%d x G=%d lexical + %d dense, top-%d' % (
-            args.workload, n_total, cfg['S'], cfg['G'], cfg['C'], args.topk)},
+        'config': {'workload': workload_string(args.workload, n_total, n_q, args.topk)},
         'cpu_baseline': {'value': qps, 'unit': 'queries/s', 'cores': threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': qps, 'unit': 'queries/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
@@ -264,6 +274,16 @@ def main():
     step(True)
     ms_e2e, _ = timed(args.steps, True)
 
+    # HBM-bound operating point of the scan (K1, one query per corpus pass, one group per launch): bounded sample
+    qb1 = None
+    if cfg['S'] > 0 or True:
+        n_s = min(8, n_q)
+        ix.set_option('tile_mode', 0); ix.set_option('query_block', 1); ix.set_option('query_groups', 1); ix.set_option('scan_variant', 1)
+        ix.search(qv_dev[:n_s], qi_dev[:n_s] if qi_dev is not None else None, k, out=tuple(o[:n_s] for o in out_dev))
+        ix.search(qv_dev[:n_s], qi_dev[:n_s] if qi_dev is not None else None, k, out=tuple(o[:n_s] for o in out_dev))
+        s1 = ix.stats()
+        qb1 = {'scan_ms': s1['scan_ms'], 'passes': s1['corpus_passes'], 'queries': n_s, 'total_ms': s1['total_ms']}
+
     # ---- roofline of the dominant kernel (K1 scan), from CUDA events inside the library ----
     scan_ms = sum(s['scan_ms'] for s in stats)
     select_ms = sum(s['select_ms'] for s in stats)
@@ -293,15 +313,19 @@ def main():
             'dtype': 'f32',  # fp16 storage, exact fp16 x fp16 products accumulated in fp32 (FHFMA)
             'data': 'synthetic',
             'config': {
-                'workload': '%s: %d passages, %d queries, S=%d x G=%d lexical (%s idx) + %d dense fp16, top-%d' % (
-                    args.workload, n_total, n_q, cfg['S'], cfg['G'], cfg['idx'], cfg['C'], k),
+                'workload': workload_string(args.workload, n_total, n_q, k),
                 'row_bytes': ix.row_bytes, 'corpus_bytes': ix.row_bytes * n_total, 'parallelism': 'range-shard x%d' % world,
                 'query_block': stats[0]['query_block'], 'query_groups': stats[0]['query_groups'], 'scan_variant': stats[0]['scan_variant'],
                 'l2': 'inputs (%.1f GB per GPU) far exceed the 126 MB L2' % (ix.row_bytes * (hi - lo) / 1e9),
                 'index_build_s': t_build,
             },
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'],
-                         'traffic': traffic, 'peak_source': peak_src, 'kernel': 'gip_scan (K1)',
+                         'traffic': traffic, 'peak_source': peak_src,
+                         'kernel': {1: 'gip_scan_tma (K1)', 0: 'gip_scan_direct (K1)', 2: 'dense_tile (K2, tcgen05)',
+                                    3: 'dense_tile (K2, tcgen05) + lex_tile (K1t)'}.get(stats[0]['scan_variant'], '?'),
+                         'queries_per_pass': stats[0]['query_block'],
+                         'note': 'achieved = logical corpus passes (one per query tile of `queries_per_pass`) x N x row_bytes / kernel time; '
+                                 'query tiles in flight share the pass through L2, so DRAM traffic is lower (see traffic)',
                          'bytes_per_launch': passes * bytes_per_pass / max(1, launches), 'launch_ms_avg': scan_ms / max(1, launches),
                          'corpus_passes_per_step': passes / args.steps, 'scan_share_of_step': scan_ms / ms_dev,
                          'select_share_of_step': select_ms / ms_dev},
@@ -311,10 +335,18 @@ def main():
             'clocks': clocks,
             'fallback_queries': int(sum(s['n_fallback_queries'] for s in stats)),
         }
+        if qb1 and qb1['scan_ms'] > 0:
+            a1 = qb1['passes'] * bytes_per_pass / (qb1['scan_ms'] / 1e3) / 1e9
+            line['roofline_qb1'] = {'bound': 'hbm', 'achieved': a1, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': a1 / peaks['hbm_gbs'],
+                                    'kernel': 'gip_scan_tma (K1), one query per corpus pass', 'queries': qb1['queries'],
+                                    'queries_per_sec': qb1['queries'] / (qb1['total_ms'] / 1e3) if qb1['total_ms'] > 0 else None}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             rows = min(args.cpu_rows, n_total)
-            v, dt = cpu_port_throughput(args.workload, n_total, rows, args.cpu_queries, k, threads, repeats=2)
+            port = CpuPort(args.workload, rows, args.cpu_queries, k, threads)
+            port.run()
+            dt = min(port.run(), port.run())
+            v = args.cpu_queries / dt * rows / n_total
             line['cpu_baseline'] = {
                 'value': v, 'unit': 'queries/s', 'cores': threads, 'kind': 'port',
                 'sample': '%d queries x %d rows (%.1f s), torch-op port of gip_retrieval.py:110-126, scaled linearly to %d rows' % (

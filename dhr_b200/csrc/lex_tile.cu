@@ -202,12 +202,18 @@ __global__ void __launch_bounds__(kLT_Threads, 1) lex_tile_kernel(const __grid_c
     for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q) {
         const long long row = (tile0 + t) * kLT_PT + p;
         const bool row_ok = row >= a.row_begin && row < a.row_end && row < a.n_rows;
-        // acc init: dense score of (q, row) from K2 or zero
+        // acc init: dense score of (q, row) from K2 or zero; loads are issued 16 at a time so their latency overlaps
         if (a.scratch && row_ok) {
             const float* src = a.scratch + (size_t)q0 * a.scratch_rows + (size_t)(row - a.scratch_row0);
-            for (int q = 0; q < nq; ++q) acc[q * kLT_PT + p] = src[(size_t)q * a.scratch_rows];
-            for (int q = nq; q < kLT_QT; ++q) acc[q * kLT_PT + p] = 0.f;
+            for (int qb = 0; qb < kLT_QT; qb += 16) {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = (qb + i < nq) ? __ldcs(src + (size_t)(qb + i) * a.scratch_rows) : 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[(qb + i) * kLT_PT + p] = v[i];
+            }
         } else {
+#pragma unroll 16
             for (int q = 0; q < kLT_QT; ++q) acc[q * kLT_PT + p] = 0.f;
         }
         for (int c = 0; c < a.n_chunks; ++c) {

@@ -1,0 +1,124 @@
+"""GPU tests of the reference-facing API: the Python mirror of gip_retrieval.py (functions, CLI, files)."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, has_cuda
+from helpers import tie_groups_equal
+from oracle import gip_oracle as go
+
+pytestmark = pytest.mark.gpu
+
+if has_cuda():
+    import torch
+    import dhr_b200
+    from dhr_b200 import gip_retrieval as gr
+
+
+def _q(g, lam=1.0):
+    q = g['q_vals'].astype(np.float32)
+    C = int(g['C'])
+    if C > 0:
+        q[:, -C:] = np.float32(lam) * q[:, -C:]
+    return q
+
+
+def test_gip_retrieval_function_matches_reference_exact_branch():
+    g = load_golden('delade_g1_u8_grid')
+    S, k = int(g['S']), int(g['topk'])
+    qids = list(range(100, 100 + g['q_vals'].shape[0]))
+    args = go.make_args(emb_dim=S, topk=k, brute_force=True, theta=0.3)
+    res, sc = gr.GIP_retrieval(qids, torch.from_numpy(_q(g)), torch.from_numpy(g['q_idx']),
+                               torch.from_numpy(g['c_vals'].astype(np.float32)), torch.from_numpy(g['c_idx']), args)
+    assert args.theta == 0                                        # mutated like gip_retrieval.py:90
+    assert list(res.keys()) == qids and isinstance(res[qids[0]], list) and isinstance(sc[qids[0]][0], float)
+    for i, qid in enumerate(qids):
+        assert np.array_equal(np.array(sc[qid]), g['ref_scores'][i])
+        assert tie_groups_equal(np.array(res[qid]), g['ref_rows'][i], np.array(sc[qid]))
+    with pytest.raises(RuntimeError):                             # torch.topk raises for k > N (:123)
+        gr.GIP_retrieval(qids, torch.from_numpy(_q(g)), torch.from_numpy(g['q_idx']),
+                         torch.from_numpy(g['c_vals'].astype(np.float32)), torch.from_numpy(g['c_idx']),
+                         go.make_args(emb_dim=S, topk=g['c_vals'].shape[0] + 1, brute_force=True))
+
+
+def test_ip_retrieval_function_matches_reference():
+    for name in ('dense_ip_gauss', 'dense_ip_grid_k_gt_n'):
+        g = load_golden(name)
+        k = int(g['topk'])
+        qids = ['q%d' % i for i in range(g['q_vals'].shape[0])]
+        res, sc = gr.IP_retrieval(qids, torch.from_numpy(_q(g)), torch.from_numpy(g['c_vals'].astype(np.float32)), go.make_args(topk=k))
+        for i, qid in enumerate(qids):
+            assert len(res[qid]) == g['ref_rows'].shape[1]        # argsort[:k] never fails for k > N
+            assert np.abs(np.array(sc[qid]) - g['ref_scores'][i]).max() < 1e-3
+            assert np.mean(np.array(res[qid]) == g['ref_rows'][i]) > 0.98
+
+
+@pytest.mark.parametrize('tag,kw', [('theta', dict(theta=0.8)), ('theta_rerank', dict(theta=0.8, rerank=True, agip_topk=400)),
+                                     ('ip', dict(theta=0.8, IP=True)), ('ip_rerank', dict(theta=0.8, IP=True, rerank=True, agip_topk=400))])
+def test_approximate_modes_match_reference(tag, kw):
+    g = load_golden('delade_approx_grid')
+    S, k = int(g['S']), int(g['topk'])
+    qids = list(range(g['q_vals'].shape[0]))
+    res, sc = gr.GIP_retrieval(qids, torch.from_numpy(_q(g)), torch.from_numpy(g['q_idx']),
+                               torch.from_numpy(g['c_vals'].astype(np.float32)), torch.from_numpy(g['c_idx']),
+                               go.make_args(emb_dim=S, topk=k, **kw))
+    got = np.array([sc[i] for i in qids])
+    rows = np.array([res[i] for i in qids])
+    if 'rerank' not in tag:
+        # first-stage only: identical score lists (grid inputs), rows agree inside tie groups
+        assert np.array_equal(got, g['ref_scores_' + tag])
+        for i in qids:
+            assert tie_groups_equal(rows[i], g['ref_rows_' + tag][i], got[i])
+    else:
+        # the reference's candidate set is cut at an arbitrary point inside a tie group (torch.topk), ours at the
+        # lowest rows; every returned score must be the exact GIP score of that row and lists must agree where the
+        # candidate cut does not interfere (top of the list)
+        ex = go.gip_scores_f64(_q(g), g['q_idx'], g['c_vals'], g['c_idx'], S, 1)
+        for i in qids:
+            assert np.array_equal(ex[i][rows[i]], got[i])
+            assert np.array_equal(got[i][:10], g['ref_scores_' + tag][i][:10])
+
+
+def test_cli_main_round_trip(tmp_path, monkeypatch):
+    g = load_golden('main_trec_grid')
+    docids = [str(x) for x in g['docids']]
+    qids = [str(x) for x in g['qids']]
+    qp, ip = tmp_path / 'q.pt', tmp_path / 'c.index.pt'
+    with open(qp, 'wb') as f:
+        pickle.dump([g['q_vals'], g['q_idx'], qids], f, protocol=4)
+    with open(ip, 'wb') as f:
+        pickle.dump([g['c_vals'], g['c_idx'], docids], f, protocol=4)
+    monkeypatch.chdir(tmp_path)
+    base = ['--query_emb_path', str(qp), '--index_path', str(ip), '--emb_dim', str(int(g['S'])), '--brute_force', '--topk',
+            str(int(g['topk'])), '--lamda', str(float(g['lamda'])), '--run_name', 'golden']
+
+    def check(fn, ref_text):
+        ours = open(fn).read().splitlines()
+        ref = str(ref_text).splitlines()
+        assert len(ours) == len(ref)
+        key = lambda l: tuple(l.split(' ')[i] for i in (0, 1, 3, 4, 5))
+        assert [key(l) for l in ours] == [key(l) for l in ref]    # qid, Q0, rank, score text, run name identical
+        last = {l.split(' ')[0]: l.split(' ')[4] for l in ref}
+        grp = lambda ls: {(l.split(' ')[0], l.split(' ')[4]): set() for l in ls}
+        ga, gb = grp(ref), grp(ours)
+        for l in ref:
+            ga[(l.split(' ')[0], l.split(' ')[4])].add(l.split(' ')[2])
+        for l in ours:
+            gb[(l.split(' ')[0], l.split(' ')[4])].add(l.split(' ')[2])
+        assert all(ga[kk] == gb[kk] for kk in ga if last[kk[0]] != kk[1])
+
+    gr.main(base)
+    check('result.trec', g['trec_single'])
+    for sh in range(3):
+        gr.main(base + ['--total_shrad', '3', '--shrad', str(sh)])
+        check('result%d.trec' % sh, g['trec_shard%d' % sh])
+    # dense-only index through the CLI (idx entries None / 0)
+    d = load_golden('main_trec_dense_grid')
+    with open(qp, 'wb') as f:
+        pickle.dump([d['q_vals'], None, [str(x) for x in d['qids']]], f, protocol=4)
+    with open(ip, 'wb') as f:
+        pickle.dump([d['c_vals'], 0, [str(x) for x in d['docids']]], f, protocol=4)
+    gr.main(['--query_emb_path', str(qp), '--index_path', str(ip), '--topk', str(int(d['topk'])), '--run_name', 'golden'])
+    check('result.trec', d['trec_single'])

@@ -1,0 +1,112 @@
+"""CPU-only tests: host-side logic of the product, and that the C-ABI library loads and exports every symbol
+include/dhr_b200.h declares (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+from oracle import gip_oracle as go
+
+
+def test_cabi_exports_every_declared_symbol():
+    from dhr_b200 import _cabi as C
+    hdr = open(os.path.join(ROOT, 'include', 'dhr_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(dhr_[a-z_0-9]+)\s*\(', hdr))
+    assert declared, 'no declarations parsed'
+    lib = C.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), 'libdhr_b200.so does not export ' + name
+    assert declared == set(C.EXPORTS)
+    assert lib.dhr_version() >= 100
+    assert lib.dhr_strerror(0) == b'ok' and b'fp16' in lib.dhr_strerror(C.ERR_LOSSY)
+
+
+def test_constants_match_header():
+    from dhr_b200 import _cabi as C
+    hdr = open(os.path.join(ROOT, 'include', 'dhr_b200.h')).read()
+    defs = dict(re.findall(r'#define\s+(DHR_[A-Z_0-9]+)\s+(\d+)u?\b', hdr))
+    assert int(defs['DHR_MAX_K']) == C.MAX_K and int(defs['DHR_MAX_GROUP']) == C.MAX_GROUP
+    for name, val in [('DHR_IDX_U8', C.IDX_U8), ('DHR_IDX_I8', C.IDX_I8), ('DHR_IDX_I16', C.IDX_I16), ('DHR_IDX_U16', C.IDX_U16),
+                      ('DHR_IDX_I32', C.IDX_I32), ('DHR_IDX_I64', C.IDX_I64), ('DHR_VAL_F16', C.VAL_F16), ('DHR_VAL_F32', C.VAL_F32),
+                      ('DHR_ERR_LOSSY', C.ERR_LOSSY), ('DHR_ERR_IDX_RANGE', C.ERR_IDX_RANGE), ('DHR_ERR_NO_DEVICE', C.ERR_NO_DEVICE)]:
+        assert int(defs[name]) == val
+    assert ctypes.sizeof(C.DhrStats) == 10 * 4 + 5 * 8
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from dhr_b200 import GipIndex, _cabi as C
+    with pytest.raises(C.DhrError) as e:
+        GipIndex.from_arrays(np.zeros((4, 8), np.float16), None)
+    assert e.value.status == C.ERR_NO_DEVICE
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'dhr_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'oracle' not in src.replace('# oracle', ''), f + ' mentions the oracle'
+
+
+def test_shard_bounds_match_reference_rule():
+    from dhr_b200 import shard_bounds
+    for n in (0, 1, 7, 400, 8841823):
+        for t in (1, 2, 3, 8, 16):
+            covered = []
+            for s in range(t):
+                assert shard_bounds(n, t, s) == go.shard_bounds(n, t, s)
+                covered.append(shard_bounds(n, t, s))
+            assert covered[0][0] == 0 and covered[-1][1] == n
+            assert all(covered[i][1] == covered[i + 1][0] for i in range(t - 1))
+    assert shard_bounds(8841823, 8, 7) == (7736589, 8841823)      # last shard takes the remainder (1,105,234 rows)
+
+
+def test_write_trec_matches_reference_format(tmp_path):
+    from dhr_b200 import write_trec
+    g = load_golden('main_trec_grid')
+    docids = [str(x) for x in g['docids']]
+    qids = [str(x) for x in g['qids']]
+    S, k, lam = int(g['S']), int(g['topk']), float(g['lamda'])
+    q = g['q_vals'].astype(np.float32)
+    q[:, -int(g['C']):] *= np.float32(lam)
+    rows, vals = go.search_f64(q, g['q_idx'], g['c_vals'], g['c_idx'], S, 1, k)
+    res = {qid: rows[i].tolist() for i, qid in enumerate(qids)}
+    sc = {qid: vals[i].astype(np.float32).tolist() for i, qid in enumerate(qids)}
+    out = tmp_path / 'result.trec'
+    write_trec(str(out), res, sc, docids, 'golden')
+    ours = out.read_text().splitlines()
+    ref = str(g['trec_single']).splitlines()
+    assert len(ours) == len(ref)
+    key = lambda l: (l.split(' ')[0], l.split(' ')[1], l.split(' ')[3], l.split(' ')[4], l.split(' ')[5])
+    assert [key(l) for l in ours] == [key(l) for l in ref]        # qid, Q0, rank (not renumbered), score text, run name
+
+
+def test_synth_is_shard_consistent_and_has_reference_conventions():
+    from dhr_b200 import synth
+    full_v, full_i = synth.corpus_numpy('delade_cls', 0, 70000)
+    a_v, a_i = synth.corpus_numpy('delade_cls', 65000, 70000)
+    assert np.array_equal(full_v[65000:], a_v) and np.array_equal(full_i[65000:], a_i)
+    S, G = 128, 6
+    lex = full_v[:, :S * G].reshape(-1, S, G)
+    empty = (lex == 0).all(axis=2)
+    assert 0.25 < empty.mean() < 0.35 and np.all(full_i[empty] == 0)       # empty slice = value 0 AND idx 0
+    assert full_i.max() < 39 and full_v.dtype == np.float16 and full_i.dtype == np.uint16
+    qv, qi = synth.queries_numpy('bm25', 16)
+    nz = (qv.reshape(16, 256, 3) != 0).any(axis=2).sum(axis=1)
+    assert np.all(nz <= 8)
+
+
+def test_cli_parser_accepts_reference_flags_verbatim():
+    from dhr_b200.gip_retrieval import build_parser
+    a = build_parser().parse_args(['--query_emb_path', 'q', '--index_path', 'i', '--emb_dim', '768', '--theta', '0.3', '--rerank',
+                                   '--use_gpu', '--combine_cls', '--topk', '1000', '--total_shrad', '2', '--shrad', '1',
+                                   '--lamda', '0.5', '--agip_topk', '10000', '--IP', '--brute_force', '--batch', '4',
+                                   '--run_name', 'x', '--faiss_pq_index_path', 'p'])
+    assert a.total_shrad == 2 and a.shrad == 1 and a.lamda == 0.5 and a.rerank and a.IP and a.brute_force
