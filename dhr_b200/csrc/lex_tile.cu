@@ -25,6 +25,7 @@ constexpr int kLT_QT = kLexTileQueries; // queries per tile
 constexpr int kLT_SC = kLexTileSlices;  // slices per chunk
 constexpr int kLT_Stages = 2;
 constexpr int kLT_Threads = kLT_PT + 32;
+constexpr int kLT_QCap = 256;           // per-warp match queue capacity (items per slice step)
 
 __host__ __device__ constexpr int lt_entry_words(int G) { return (G + 2) / 2; }          // {qid, v0..vG-1} as fp16 pairs
 __host__ __device__ constexpr int lt_pval_words(int G) { return (G + 1) / 2; }
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(kLT_Threads, 1) lex_tile_kernel(const __grid_c
     __shared__ __align__(8) uint64_t full_bar[kLT_Stages];
     __shared__ __align__(8) uint64_t empty_bar[kLT_Stages];
     __shared__ float tau_s[kLT_QT];
+    __shared__ uint16_t wq_all[(kLT_PT / 32) * kLT_QCap];
 
     constexpr int EW = lt_entry_words(G);
     constexpr int PW = lt_pval_words(G);
@@ -198,6 +200,7 @@ __global__ void __launch_bounds__(kLT_Threads, 1) lex_tile_kernel(const __grid_c
     // ===== consumers: thread p owns passage p of the tile =====
     const int p = threadIdx.x;
     const int offs_per_slice = a.rt + 1;
+    uint16_t* wq = wq_all + warp * kLT_QCap;
     int s = 0; uint32_t ph = 0;
     for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q) {
         const long long row = (tile0 + t) * kLT_PT + p;
@@ -226,20 +229,76 @@ __global__ void __launch_bounds__(kLT_Threads, 1) lex_tile_kernel(const __grid_c
             uint32_t cw[kLT_SC * sizeof(CodeT) / 4];
             if constexpr (sizeof(CodeT) == 1) { const uint2 v = *(const uint2*)codes; cw[0] = v.x; cw[1] = v.y; }
             else { const uint4 v = *(const uint4*)codes; cw[0] = v.x; cw[1] = v.y; cw[2] = v.z; cw[3] = v.w; }
+            // Per slice: (A) every lane looks up the bucket of ITS passage's code and the warp flattens all
+            // (passage, entry) matches of its 32 passages into a small queue; (B) the queue is consumed 32 items
+            // at a time, one match per lane, so lanes stay busy regardless of how bucket lengths are distributed.
+            // Items of one slice never share a (query, passage) pair, and slices are separated by __syncwarp, so the
+            // plain read-modify-write of acc is race-free and the summation order is fixed.
 #pragma unroll
             for (int j = 0; j < kLT_SC; ++j) {
                 uint32_t code;
                 if constexpr (sizeof(CodeT) == 1) code = (cw[j >> 2] >> (8 * (j & 3))) & 0xFFu;
                 else code = (cw[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+                uint32_t beg = 0, len = 0;
                 if (code < (uint32_t)a.rt) {
-                    const uint32_t beg = off[j * offs_per_slice + code], end = off[j * offs_per_slice + code + 1];
-                    if (beg < end) {
+                    beg = off[j * offs_per_slice + code];
+                    len = off[j * offs_per_slice + code + 1] - beg;
+                }
+                uint32_t incl = len;                                   // warp inclusive scan of len
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                    if (lane >= d) incl += n;
+                }
+                const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                if (total == 0) continue;
+                const uint32_t* pv_slice = pvals + (size_t)j * kLT_PT * G / 2;      // even G (odd G handled below)
+                if (total <= (uint32_t)kLT_QCap) {
+                    uint32_t pos = incl - len;
+                    const uint32_t tag = (uint32_t)lane << 10;
+                    for (uint32_t k = 0; k < len; ++k) wq[pos + k] = (uint16_t)(tag | (beg + k));
+                    __syncwarp();
+                    for (uint32_t base = 0; base < total; base += 32) {
+                        const uint32_t i = base + lane;
+                        if (i < total) {
+                            const uint32_t it = wq[i];
+                            const uint32_t e = it & 0x3FFu;
+                            const int pp = (warp << 5) + (int)(it >> 10);
+                            uint32_t ew[EW], pv[PW];
+                            const uint32_t* ep = ent + (size_t)e * EW;
+                            if constexpr (EW == 4) { const uint4 v = *(const uint4*)ep; ew[0] = v.x; ew[1] = v.y; ew[2] = v.z; ew[3] = v.w; }
+                            else if constexpr (EW == 2) { const uint2 v = *(const uint2*)ep; ew[0] = v.x; ew[1] = v.y; }
+                            else {
+#pragma unroll
+                                for (int w = 0; w < EW; ++w) ew[w] = ep[w];
+                            }
+                            if constexpr (G % 2 == 0) {
+                                const uint32_t* src = pv_slice + (size_t)pp * (G / 2);
+#pragma unroll
+                                for (int w = 0; w < PW; ++w) pv[w] = src[w];
+                            } else {
+                                const uint16_t* h16 = (const uint16_t*)pvals + ((size_t)j * kLT_PT + pp) * G;
+#pragma unroll
+                                for (int w = 0; w < PW; ++w) {
+                                    const uint32_t lo = h16[2 * w];
+                                    const uint32_t hi = (2 * w + 1 < G) ? h16[2 * w + 1] : 0u;
+                                    pv[w] = lo | (hi << 16);
+                                }
+                            }
+                            float* ap = acc + (ew[0] & 0xFFFFu) * kLT_PT + pp;
+                            *ap = entry_dot<G, 0>(ew, pv, *ap);
+                        }
+                    }
+                    __syncwarp();
+                } else {
+                    // queue would overflow (degenerate code distribution): each lane walks its own bucket
+                    if (len) {
                         uint32_t pv[PW];
-                        const uint32_t* src = pvals + ((size_t)j * kLT_PT + p) * G / 2;
                         if constexpr (G % 2 == 0) {
+                            const uint32_t* src = pv_slice + (size_t)p * (G / 2);
 #pragma unroll
                             for (int w = 0; w < PW; ++w) pv[w] = src[w];
-                        } else {   // odd G: a passage's G halves straddle word boundaries for odd (j*PT + p)
+                        } else {
                             const uint16_t* h16 = (const uint16_t*)pvals + ((size_t)j * kLT_PT + p) * G;
 #pragma unroll
                             for (int w = 0; w < PW; ++w) {
@@ -248,20 +307,15 @@ __global__ void __launch_bounds__(kLT_Threads, 1) lex_tile_kernel(const __grid_c
                                 pv[w] = lo | (hi << 16);
                             }
                         }
-                        for (uint32_t e = beg; e < end; ++e) {
+                        for (uint32_t e = beg; e < beg + len; ++e) {
                             uint32_t ew[EW];
-                            const uint32_t* ep = ent + (size_t)e * EW;
-                            if constexpr (EW == 4) { const uint4 v = *(const uint4*)ep; ew[0] = v.x; ew[1] = v.y; ew[2] = v.z; ew[3] = v.w; }
-                            else if constexpr (EW == 2) { const uint2 v = *(const uint2*)ep; ew[0] = v.x; ew[1] = v.y; }
-                            else {
 #pragma unroll
-                                for (int w = 0; w < EW; ++w) ew[w] = ep[w];
-                            }
-                            const uint32_t q = ew[0] & 0xFFFFu;
-                            float* ap = acc + q * kLT_PT + p;
+                            for (int w = 0; w < EW; ++w) ew[w] = ent[(size_t)e * EW + w];
+                            float* ap = acc + (ew[0] & 0xFFFFu) * kLT_PT + p;
                             *ap = entry_dot<G, 0>(ew, pv, *ap);
                         }
                     }
+                    __syncwarp();
                 }
             }
             __syncwarp();
