@@ -8,6 +8,7 @@
 //    lexv [N][D_pad] fp16    lexical values, D_pad = S_pad*G
 //    lexi [N][S_pad] codes   uint8 or uint16; all-zero slices are stored as CODE_EMPTY
 //    dns  [N][C_pad] fp16    dense [CLS] block
+#include <algorithm>
 #include <mutex>
 #include <string.h>
 #include <string>
@@ -89,32 +90,22 @@ __device__ __forceinline__ __half load_value_as_half(const void* base, int dtype
 template <typename CodeT>
 __global__ void ingest_lexical_kernel(long long n, int S, int G, int S_pad, int W, int val_dtype, const void* vals,
                                       long long vstride, int idx_dtype, const void* idx, long long istride,
-                                      __half* lexv, CodeT* lexi, uint8_t* lext, long long row_base, int* flags) {
+                                      __half* lexv, CodeT* lexi, long long row_base, int* flags) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * S_pad) return;
     const long long r = i / S_pad;
     const int s = (int)(i % S_pad);
     __half* out = lexv + ((size_t)(row_base + r) * S_pad + s) * G;
     CodeT* oc = lexi + (size_t)(row_base + r) * S_pad + s;
-    // second, tiled copy for K1t: [tile of 256 rows][chunk of 8 slices]{codes[256][8] | vals[8][256][G]}
-    const long long grow = row_base + r;
-    const long long tile = grow / kLexTileRows;
-    const int tp = (int)(grow % kLexTileRows), chunk = s / kLexTileSlices, tj = s % kLexTileSlices;
-    const size_t pblock = (size_t)kLexTileRows * kLexTileSlices * (sizeof(CodeT) + 2 * (size_t)G);
-    uint8_t* blk = lext + ((size_t)tile * (S_pad / kLexTileSlices) + chunk) * pblock;
-    CodeT* tc = (CodeT*)blk + (size_t)tp * kLexTileSlices + tj;
-    __half* tv = (__half*)(blk + (size_t)kLexTileRows * kLexTileSlices * sizeof(CodeT)) + ((size_t)tj * kLexTileRows + tp) * G;
     if (s >= S) {
-        for (int g = 0; g < G; ++g) { out[g] = __float2half_rn(0.f); tv[g] = __float2half_rn(0.f); }
+        for (int g = 0; g < G; ++g) out[g] = __float2half_rn(0.f);
         *oc = (CodeT)CodeTraits<CodeT>::kEmpty;
-        *tc = (CodeT)CodeTraits<CodeT>::kEmpty;
         return;
     }
     bool lossy = false, nonzero = false;
     for (int g = 0; g < G; ++g) {
         const __half h = load_value_as_half(vals, val_dtype, (size_t)r * vstride + (size_t)s * G + g, &lossy);
         out[g] = h;
-        tv[g] = h;
         nonzero |= (__half_as_ushort(h) & 0x7FFFu) != 0;
     }
     if (lossy) atomicOr(flags + 0, 1);
@@ -125,7 +116,6 @@ __global__ void ingest_lexical_kernel(long long n, int S, int G, int S_pad, int 
         else { code = (uint32_t)v; atomicMax(flags + 3, (int)code + 1); }
     }
     *oc = (CodeT)code;
-    *tc = (CodeT)code;
 }
 
 __global__ void ingest_dense_kernel(long long n, int D, int C, int C_pad, int val_dtype, const void* vals, long long vstride,
@@ -141,6 +131,33 @@ __global__ void ingest_dense_kernel(long long n, int D, int C, int C_pad, int va
     if (lossy) atomicOr(flags + 0, 1);
 }
 
+// Tiled lexical copy for K1t, built once at finalize from the row-major arrays:
+//   [tile of 256 rows][chunk of 8 slices]{ codes u8 [256][8] | vals fp16 [8][256][G] }
+// Codes are always 8-bit here (the tile path requires max code <= 253); CODE_EMPTY/NOMATCH map to 0xFF.
+template <typename CodeT>
+__global__ void build_lext_kernel(long long n_rows, long long n_rows_pad, int S_pad, int G, const __half* __restrict__ lexv,
+                                  const CodeT* __restrict__ lexi, uint8_t* __restrict__ lext) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows_pad * S_pad) return;
+    const long long r = i / S_pad;
+    const int s = (int)(i % S_pad);
+    const long long tile = r / kLexTileRows;
+    const int tp = (int)(r % kLexTileRows), chunk = s / kLexTileSlices, tj = s % kLexTileSlices;
+    const size_t pblock = (size_t)kLexTileRows * kLexTileSlices * (1 + 2 * (size_t)G);
+    uint8_t* blk = lext + ((size_t)tile * (S_pad / kLexTileSlices) + chunk) * pblock;
+    uint8_t* tc = blk + (size_t)tp * kLexTileSlices + tj;
+    __half* tv = (__half*)(blk + (size_t)kLexTileRows * kLexTileSlices) + ((size_t)tj * kLexTileRows + tp) * G;
+    if (r >= n_rows) {
+        *tc = 0xFF;
+        for (int g = 0; g < G; ++g) tv[g] = __float2half_rn(0.f);
+        return;
+    }
+    const uint32_t code = lexi[(size_t)r * S_pad + s];
+    *tc = code > 253u ? (uint8_t)0xFF : (uint8_t)code;
+    const __half* src = lexv + ((size_t)r * S_pad + s) * G;
+    for (int g = 0; g < G; ++g) tv[g] = src[g];
+}
+
 static int ingest_device(dhr_index* h, long long n, int val_dtype, const void* d_vals, long long vstride, int idx_dtype,
                          const void* d_idx, long long istride) {
     const Geometry& g = h->g;
@@ -150,10 +167,10 @@ static int ingest_device(dhr_index* h, long long n, int val_dtype, const void* d
         const unsigned blocks = (unsigned)((total + 255) / 256);
         if (g.code_bytes == 1)
             ingest_lexical_kernel<uint8_t><<<blocks, 256>>>(n, g.S, g.G, g.S_pad, W, val_dtype, d_vals, vstride, idx_dtype, d_idx,
-                                                            istride, h->lexv, (uint8_t*)h->lexi, h->lext, h->n_rows, h->d_flags);
+                                                            istride, h->lexv, (uint8_t*)h->lexi, h->n_rows, h->d_flags);
         else
             ingest_lexical_kernel<uint16_t><<<blocks, 256>>>(n, g.S, g.G, g.S_pad, W, val_dtype, d_vals, vstride, idx_dtype, d_idx,
-                                                             istride, h->lexv, (uint16_t*)h->lexi, h->lext, h->n_rows, h->d_flags);
+                                                             istride, h->lexv, (uint16_t*)h->lexi, h->n_rows, h->d_flags);
         DHR_CUDA(cudaGetLastError());
     }
     if (g.C_pad > 0) {
@@ -237,10 +254,6 @@ int dhr_index_create(dhr_index** out, int device, int64_t cap_rows, int n_slices
     if (g.D_pad > 0) {
         if (cudaMalloc(&h->lexv, rows * g.D_pad * 2) != cudaSuccess) return fail(DHR_ERR_NOMEM);
         if (cudaMalloc(&h->lexi, rows * g.S_pad * g.code_bytes) != cudaSuccess) return fail(DHR_ERR_NOMEM);
-        const size_t tiles = (rows + kLexTileRows - 1) / kLexTileRows;
-        h->lext_bytes = tiles * (size_t)kLexTileRows * g.S_pad * (g.code_bytes + 2 * (size_t)g.G);
-        if (cudaMalloc(&h->lext, h->lext_bytes) != cudaSuccess) return fail(DHR_ERR_NOMEM);
-        if (cudaMemset(h->lext, 0xFF, h->lext_bytes) != cudaSuccess) return fail(DHR_ERR_CUDA);   // rows never appended: CODE_EMPTY
     }
     if (g.C_pad > 0 && cudaMalloc(&h->dns, rows * g.C_pad * 2) != cudaSuccess) return fail(DHR_ERR_NOMEM);
     if (cudaMalloc(&h->d_flags, 4 * sizeof(int)) != cudaSuccess) return fail(DHR_ERR_NOMEM);
@@ -310,6 +323,22 @@ int dhr_index_finalize(dhr_index* h) {
     if (flags[0]) return DHR_ERR_LOSSY;
     if (flags[1]) return DHR_ERR_IDX_RANGE;
     h->max_code = flags[3] - 1;
+    if (h->g.S_pad > 0 && h->n_rows > 0 && h->max_code <= 253 && lex_tile_supported(h->g, std::max(1, h->max_code + 1))) {
+        const Geometry& g = h->g;
+        const long long rows_pad = round_up(h->n_rows, kLexTileRows);
+        h->lext_bytes = (size_t)rows_pad * g.S_pad * (1 + 2 * (size_t)g.G);
+        if (cudaMalloc(&h->lext, h->lext_bytes) != cudaSuccess) { cudaGetLastError(); h->lext = nullptr; h->lext_bytes = 0; }   // tile path simply stays off
+        if (h->lext) {
+            const long long total = rows_pad * g.S_pad;
+            const unsigned blocks = (unsigned)((total + 255) / 256);
+            if (g.code_bytes == 1)
+                build_lext_kernel<uint8_t><<<blocks, 256>>>(h->n_rows, rows_pad, g.S_pad, g.G, h->lexv, (const uint8_t*)h->lexi, h->lext);
+            else
+                build_lext_kernel<uint16_t><<<blocks, 256>>>(h->n_rows, rows_pad, g.S_pad, g.G, h->lexv, (const uint16_t*)h->lexi, h->lext);
+            DHR_CUDA(cudaGetLastError());
+            DHR_CUDA(cudaDeviceSynchronize());
+        }
+    }
     // the ingest staging buffers are not needed any more
     if (h->stage_a) { cudaFree(h->stage_a); h->stage_a = nullptr; h->stage_a_bytes = 0; }
     if (h->stage_b) { cudaFree(h->stage_b); h->stage_b = nullptr; h->stage_b_bytes = 0; }

@@ -9,8 +9,13 @@
 // {query id, G fp16 values} -- so a passage thread looks up the bucket of ITS code and touches only
 // the queries that really match.  Work is O(matches), not O(Q*N*S).
 //
+// Per warp and 8-slice chunk: (A) every lane looks up, for each of the 8 slices, the bucket of ITS
+// passage's code; the 8 warp scans that flatten the (passage, entry) matches into per-slice queue
+// segments are independent and interleave; (B) each segment is consumed 32 matches at a time, one
+// per lane, so lanes stay busy however bucket lengths are distributed.
+//
 // Data movement: one producer warp streams, per (passage tile, 8-slice chunk), the tiled corpus
-// block (codes [256][8] | values [8][256][G]) and the query-tile block (offsets | entries) with
+// block (codes u8 [256][8] | values [8][256][G]) and the query-tile block (offsets | entries) with
 // TMA bulk copies (cp.async.bulk + mbarrier ring) into shared memory; 256 consumer threads own one
 // passage each and keep acc[128 queries][256 passages] fp32 in shared memory (column p is private
 // to thread p: conflict-free, no atomics, deterministic summation order).  acc is initialised
@@ -25,7 +30,7 @@ constexpr int kLT_QT = kLexTileQueries; // queries per tile
 constexpr int kLT_SC = kLexTileSlices;  // slices per chunk
 constexpr int kLT_Stages = 2;
 constexpr int kLT_Threads = kLT_PT + 32;
-constexpr int kLT_QCap = 256;           // per-warp match queue capacity (items per slice step)
+constexpr int kLT_Seg = 80;             // per-warp, per-slice match queue segment (items)
 
 __host__ __device__ constexpr int lt_entry_words(int G) { return (G + 2) / 2; }          // {qid, v0..vG-1} as fp16 pairs
 __host__ __device__ constexpr int lt_pval_words(int G) { return (G + 1) / 2; }
@@ -34,7 +39,7 @@ __host__ __device__ constexpr int lt_pval_words(int G) { return (G + 1) / 2; }
 LexTileGeom lex_tile_geom(const Geometry& g, int rt) {
     LexTileGeom t{};
     t.G = g.G; t.code_bytes = g.code_bytes; t.n_chunks = g.S_pad / kLT_SC; t.rt = rt;
-    t.pblock_bytes = kLT_PT * kLT_SC * (g.code_bytes + 2 * g.G);
+    t.pblock_bytes = kLT_PT * kLT_SC * (1 + 2 * g.G);        // tiled copy always stores 8-bit codes
     t.qoff_bytes = (int)round_up((int64_t)kLT_SC * (rt + 1) * 2, 16);
     t.qblock_stride = t.qoff_bytes + kLT_SC * kLT_QT * lt_entry_words(g.G) * 4;
     t.stage_bytes = (int)round_up(t.pblock_bytes, 128) + (int)round_up(t.qblock_stride, 128);
@@ -45,9 +50,11 @@ size_t lex_tile_smem_bytes(const LexTileGeom& t) {
     return (size_t)kLT_QT * kLT_PT * 4 + (size_t)kLT_Stages * t.stage_bytes + 128;
 }
 
+constexpr size_t kLT_StaticSmem = (size_t)(kLT_PT / 32) * kLT_SC * kLT_Seg * 2 + kLT_QT * 4 + 2048;
+
 bool lex_tile_supported(const Geometry& g, int rt) {
-    if (g.S_pad <= 0 || g.S_pad % kLT_SC != 0 || rt < 1 || rt > 256 || g.G > 8) return false;
-    return lex_tile_smem_bytes(lex_tile_geom(g, rt)) <= 227 * 1024;
+    if (g.S_pad <= 0 || g.S_pad % kLT_SC != 0 || rt < 1 || rt > 254 || g.G > 8) return false;
+    return lex_tile_smem_bytes(lex_tile_geom(g, rt)) + kLT_StaticSmem <= 227 * 1024;
 }
 
 // ---- query-tile preparation: one CTA per (chunk, query tile) builds offsets + entries ------------
@@ -148,13 +155,43 @@ struct LexTileArgs {
     float* tau; uint32_t* cnt; float* cand_score; int32_t* cand_row; int cap;
 };
 
-template <int G, typename CodeT>
+template <int G>
+__device__ __forceinline__ void load_pvals(const uint32_t* pvals, int j, int pp, uint32_t (&pv)[lt_pval_words(G)]) {
+    constexpr int PW = lt_pval_words(G);
+    if constexpr (G % 2 == 0) {
+        const uint32_t* src = pvals + ((size_t)j * kLT_PT + pp) * (G / 2);
+#pragma unroll
+        for (int w = 0; w < PW; ++w) pv[w] = src[w];
+    } else {   // odd G: a passage's G halves straddle word boundaries
+        const uint16_t* h16 = (const uint16_t*)pvals + ((size_t)j * kLT_PT + pp) * G;
+#pragma unroll
+        for (int w = 0; w < PW; ++w) {
+            const uint32_t lo = h16[2 * w];
+            const uint32_t hi = (2 * w + 1 < G) ? h16[2 * w + 1] : 0u;
+            pv[w] = lo | (hi << 16);
+        }
+    }
+}
+
+template <int G>
+__device__ __forceinline__ void load_entry(const uint32_t* ent, uint32_t e, uint32_t (&ew)[lt_entry_words(G)]) {
+    constexpr int EW = lt_entry_words(G);
+    const uint32_t* ep = ent + (size_t)e * EW;
+    if constexpr (EW == 4) { const uint4 v = *(const uint4*)ep; ew[0] = v.x; ew[1] = v.y; ew[2] = v.z; ew[3] = v.w; }
+    else if constexpr (EW == 2) { const uint2 v = *(const uint2*)ep; ew[0] = v.x; ew[1] = v.y; }
+    else {
+#pragma unroll
+        for (int w = 0; w < EW; ++w) ew[w] = ep[w];
+    }
+}
+
+template <int G>
 __global__ void __launch_bounds__(kLT_Threads, 1) lex_tile_kernel(const __grid_constant__ LexTileArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar[kLT_Stages];
     __shared__ __align__(8) uint64_t empty_bar[kLT_Stages];
     __shared__ float tau_s[kLT_QT];
-    __shared__ uint16_t wq_all[(kLT_PT / 32) * kLT_QCap];
+    __shared__ uint16_t wq_all[(kLT_PT / 32) * kLT_SC * kLT_Seg];
 
     constexpr int EW = lt_entry_words(G);
     constexpr int PW = lt_pval_words(G);
@@ -184,8 +221,8 @@ __global__ void __launch_bounds__(kLT_Threads, 1) lex_tile_kernel(const __grid_c
             for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q) {
                 const uint8_t* ptile = a.lext + (size_t)(tile0 + t) * a.n_chunks * a.pblock_bytes;
                 for (int c = 0; c < a.n_chunks; ++c) {
+                    const uint32_t qb = __ldg(a.qblock_bytes + (size_t)qt * a.n_chunks + c);
                     mbar_wait(&empty_bar[s], ph ^ 1u);
-                    const uint32_t qb = a.qblock_bytes[(size_t)qt * a.n_chunks + c];
                     uint8_t* dst = stages + (size_t)s * a.stage_bytes;
                     mbar_arrive_expect_tx(&full_bar[s], (uint32_t)a.pblock_bytes + qb);
                     bulk_g2s(dst, ptile + (size_t)c * a.pblock_bytes, (uint32_t)a.pblock_bytes, &full_bar[s]);
@@ -200,7 +237,8 @@ __global__ void __launch_bounds__(kLT_Threads, 1) lex_tile_kernel(const __grid_c
     // ===== consumers: thread p owns passage p of the tile =====
     const int p = threadIdx.x;
     const int offs_per_slice = a.rt + 1;
-    uint16_t* wq = wq_all + warp * kLT_QCap;
+    uint16_t* wq = wq_all + warp * (kLT_SC * kLT_Seg);
+    const uint32_t tag = (uint32_t)lane << 10;
     int s = 0; uint32_t ph = 0;
     for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q) {
         const long long row = (tile0 + t) * kLT_PT + p;
@@ -222,103 +260,76 @@ __global__ void __launch_bounds__(kLT_Threads, 1) lex_tile_kernel(const __grid_c
         for (int c = 0; c < a.n_chunks; ++c) {
             mbar_wait(&full_bar[s], ph);
             const uint8_t* st = stages + (size_t)s * a.stage_bytes;
-            const CodeT* codes = (const CodeT*)st + (size_t)p * kLT_SC;
-            const uint32_t* pvals = (const uint32_t*)(st + (size_t)kLT_PT * kLT_SC * sizeof(CodeT));
+            const uint32_t* pvals = (const uint32_t*)(st + (size_t)kLT_PT * kLT_SC);
             const uint16_t* off = (const uint16_t*)(st + a.pblock_smem);
             const uint32_t* ent = (const uint32_t*)(st + a.pblock_smem + a.qoff_bytes);
-            uint32_t cw[kLT_SC * sizeof(CodeT) / 4];
-            if constexpr (sizeof(CodeT) == 1) { const uint2 v = *(const uint2*)codes; cw[0] = v.x; cw[1] = v.y; }
-            else { const uint4 v = *(const uint4*)codes; cw[0] = v.x; cw[1] = v.y; cw[2] = v.z; cw[3] = v.w; }
-            // Per slice: (A) every lane looks up the bucket of ITS passage's code and the warp flattens all
-            // (passage, entry) matches of its 32 passages into a small queue; (B) the queue is consumed 32 items
-            // at a time, one match per lane, so lanes stay busy regardless of how bucket lengths are distributed.
-            // Items of one slice never share a (query, passage) pair, and slices are separated by __syncwarp, so the
-            // plain read-modify-write of acc is race-free and the summation order is fixed.
+            const uint2 cw = *(const uint2*)(st + (size_t)p * kLT_SC);          // my 8 slice codes
+
+            // ---- phase A: 8 independent bucket lookups + warp scans, matches flattened into per-slice segments ----
+            uint32_t beg[kLT_SC], len[kLT_SC], incl[kLT_SC];
 #pragma unroll
             for (int j = 0; j < kLT_SC; ++j) {
-                uint32_t code;
-                if constexpr (sizeof(CodeT) == 1) code = (cw[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-                else code = (cw[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
-                uint32_t beg = 0, len = 0;
+                const uint32_t code = ((j < 4 ? cw.x : cw.y) >> (8 * (j & 3))) & 0xFFu;
+                beg[j] = 0; len[j] = 0;
                 if (code < (uint32_t)a.rt) {
-                    beg = off[j * offs_per_slice + code];
-                    len = off[j * offs_per_slice + code + 1] - beg;
+                    beg[j] = off[j * offs_per_slice + code];
+                    len[j] = off[j * offs_per_slice + code + 1] - beg[j];
                 }
-                uint32_t incl = len;                                   // warp inclusive scan of len
+                incl[j] = len[j];
+            }
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                    if (lane >= d) incl += n;
+            for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+                for (int j = 0; j < kLT_SC; ++j) {
+                    const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl[j], d);
+                    if (lane >= d) incl[j] += n;
                 }
-                const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                if (total == 0) continue;
-                const uint32_t* pv_slice = pvals + (size_t)j * kLT_PT * G / 2;      // even G (odd G handled below)
-                if (total <= (uint32_t)kLT_QCap) {
-                    uint32_t pos = incl - len;
-                    const uint32_t tag = (uint32_t)lane << 10;
-                    for (uint32_t k = 0; k < len; ++k) wq[pos + k] = (uint16_t)(tag | (beg + k));
-                    __syncwarp();
-                    for (uint32_t base = 0; base < total; base += 32) {
+            }
+            uint32_t total[kLT_SC];
+#pragma unroll
+            for (int j = 0; j < kLT_SC; ++j) {
+                total[j] = __shfl_sync(0xFFFFFFFFu, incl[j], 31);
+                if (total[j] <= (uint32_t)kLT_Seg) {
+                    uint16_t* seg = wq + j * kLT_Seg + (incl[j] - len[j]);
+                    const uint32_t it = tag | beg[j];
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; ++k) if (k < len[j]) seg[k] = (uint16_t)(it + k);
+                    for (uint32_t k = 4; k < len[j]; ++k) seg[k] = (uint16_t)(it + k);
+                }
+            }
+            __syncwarp();
+
+            // ---- phase B: consume the segments, one match per lane; slices are ordered by __syncwarp ----
+#pragma unroll
+            for (int j = 0; j < kLT_SC; ++j) {
+                if (total[j] == 0) continue;
+                if (total[j] <= (uint32_t)kLT_Seg) {
+                    const uint16_t* seg = wq + j * kLT_Seg;
+                    for (uint32_t base = 0; base < total[j]; base += 32) {
                         const uint32_t i = base + lane;
-                        if (i < total) {
-                            const uint32_t it = wq[i];
-                            const uint32_t e = it & 0x3FFu;
+                        if (i < total[j]) {
+                            const uint32_t it = seg[i];
                             const int pp = (warp << 5) + (int)(it >> 10);
                             uint32_t ew[EW], pv[PW];
-                            const uint32_t* ep = ent + (size_t)e * EW;
-                            if constexpr (EW == 4) { const uint4 v = *(const uint4*)ep; ew[0] = v.x; ew[1] = v.y; ew[2] = v.z; ew[3] = v.w; }
-                            else if constexpr (EW == 2) { const uint2 v = *(const uint2*)ep; ew[0] = v.x; ew[1] = v.y; }
-                            else {
-#pragma unroll
-                                for (int w = 0; w < EW; ++w) ew[w] = ep[w];
-                            }
-                            if constexpr (G % 2 == 0) {
-                                const uint32_t* src = pv_slice + (size_t)pp * (G / 2);
-#pragma unroll
-                                for (int w = 0; w < PW; ++w) pv[w] = src[w];
-                            } else {
-                                const uint16_t* h16 = (const uint16_t*)pvals + ((size_t)j * kLT_PT + pp) * G;
-#pragma unroll
-                                for (int w = 0; w < PW; ++w) {
-                                    const uint32_t lo = h16[2 * w];
-                                    const uint32_t hi = (2 * w + 1 < G) ? h16[2 * w + 1] : 0u;
-                                    pv[w] = lo | (hi << 16);
-                                }
-                            }
+                            load_entry<G>(ent, it & 0x3FFu, ew);
+                            load_pvals<G>(pvals, j, pp, pv);
                             float* ap = acc + (ew[0] & 0xFFFFu) * kLT_PT + pp;
                             *ap = entry_dot<G, 0>(ew, pv, *ap);
                         }
                     }
-                    __syncwarp();
-                } else {
-                    // queue would overflow (degenerate code distribution): each lane walks its own bucket
-                    if (len) {
-                        uint32_t pv[PW];
-                        if constexpr (G % 2 == 0) {
-                            const uint32_t* src = pv_slice + (size_t)p * (G / 2);
-#pragma unroll
-                            for (int w = 0; w < PW; ++w) pv[w] = src[w];
-                        } else {
-                            const uint16_t* h16 = (const uint16_t*)pvals + ((size_t)j * kLT_PT + p) * G;
-#pragma unroll
-                            for (int w = 0; w < PW; ++w) {
-                                const uint32_t lo = h16[2 * w];
-                                const uint32_t hi = (2 * w + 1 < G) ? h16[2 * w + 1] : 0u;
-                                pv[w] = lo | (hi << 16);
-                            }
-                        }
-                        for (uint32_t e = beg; e < beg + len; ++e) {
-                            uint32_t ew[EW];
-#pragma unroll
-                            for (int w = 0; w < EW; ++w) ew[w] = ent[(size_t)e * EW + w];
-                            float* ap = acc + (ew[0] & 0xFFFFu) * kLT_PT + p;
-                            *ap = entry_dot<G, 0>(ew, pv, *ap);
-                        }
+                } else if (len[j]) {
+                    // segment would overflow (degenerate code distribution): each lane walks its own bucket
+                    uint32_t pv[PW];
+                    load_pvals<G>(pvals, j, p, pv);
+                    for (uint32_t e = beg[j]; e < beg[j] + len[j]; ++e) {
+                        uint32_t ew[EW];
+                        load_entry<G>(ent, e, ew);
+                        float* ap = acc + (ew[0] & 0xFFFFu) * kLT_PT + p;
+                        *ap = entry_dot<G, 0>(ew, pv, *ap);
                     }
-                    __syncwarp();
                 }
+                __syncwarp();
             }
-            __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
             if (++s == kLT_Stages) { s = 0; ph ^= 1u; }
         }
@@ -336,6 +347,7 @@ __global__ void __launch_bounds__(kLT_Threads, 1) lex_tile_kernel(const __grid_c
                 }
             }
         }
+        __syncwarp();
     }
 }
 
@@ -357,9 +369,9 @@ int launch_lex_tile_prep(const dhr_index* h, const LexTileGeom& t, const void* q
     return DHR_OK;
 }
 
-template <int G, typename CodeT>
+template <int G>
 static int launch_lex_tile_t(const dhr_index* h, const LexTileArgs& a, size_t smem, cudaStream_t st) {
-    auto kern = lex_tile_kernel<G, CodeT>;
+    auto kern = lex_tile_kernel<G>;
     DHR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_q = h->num_sms / a.n_qtiles;
     if (per_q < 1) per_q = 1;
@@ -369,17 +381,16 @@ static int launch_lex_tile_t(const dhr_index* h, const LexTileArgs& a, size_t sm
     return DHR_OK;
 }
 
-template <typename CodeT>
 static int launch_lex_tile_g(const dhr_index* h, const LexTileArgs& a, size_t smem, cudaStream_t st) {
     switch (h->g.G) {
-        case 1: return launch_lex_tile_t<1, CodeT>(h, a, smem, st);
-        case 2: return launch_lex_tile_t<2, CodeT>(h, a, smem, st);
-        case 3: return launch_lex_tile_t<3, CodeT>(h, a, smem, st);
-        case 4: return launch_lex_tile_t<4, CodeT>(h, a, smem, st);
-        case 5: return launch_lex_tile_t<5, CodeT>(h, a, smem, st);
-        case 6: return launch_lex_tile_t<6, CodeT>(h, a, smem, st);
-        case 7: return launch_lex_tile_t<7, CodeT>(h, a, smem, st);
-        case 8: return launch_lex_tile_t<8, CodeT>(h, a, smem, st);
+        case 1: return launch_lex_tile_t<1>(h, a, smem, st);
+        case 2: return launch_lex_tile_t<2>(h, a, smem, st);
+        case 3: return launch_lex_tile_t<3>(h, a, smem, st);
+        case 4: return launch_lex_tile_t<4>(h, a, smem, st);
+        case 5: return launch_lex_tile_t<5>(h, a, smem, st);
+        case 6: return launch_lex_tile_t<6>(h, a, smem, st);
+        case 7: return launch_lex_tile_t<7>(h, a, smem, st);
+        case 8: return launch_lex_tile_t<8>(h, a, smem, st);
         default: return DHR_ERR_UNSUPPORTED;
     }
 }
@@ -399,9 +410,8 @@ int launch_lex_tile(const dhr_index* h, const LexTileGeom& t, const uint8_t* qbl
     a.n_queries = n_queries;
     a.scratch = scratch; a.scratch_rows = scratch_rows; a.scratch_row0 = scratch_row0;
     a.tau = tk.tau; a.cnt = tk.cnt; a.cand_score = tk.cand_score; a.cand_row = tk.cand_row; a.cap = cap;
-    const size_t smem = lex_tile_smem_bytes(t);
-    if (h->g.code_bytes == 1) return launch_lex_tile_g<uint8_t>(h, a, smem, st);
-    return launch_lex_tile_g<uint16_t>(h, a, smem, st);
+    if (!h->lext) return DHR_ERR_STATE;
+    return launch_lex_tile_g(h, a, lex_tile_smem_bytes(t), st);
 }
 
 }  // namespace dhr

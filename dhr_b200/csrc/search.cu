@@ -468,7 +468,7 @@ extern "C" int dhr_search(dhr_index* h, int n_queries, int q_val_dtype, const vo
         const bool tile_dense = h->opt_tile_mode && g.S == 0 && !qs.f32 && dense_tile_supported(g, nullptr);
         if (tile_dense) { slots = kMaxInflight; qb = 64; groups = kMaxInflight / 64; }
         const int rt = std::max(1, h->max_code + 1);
-        const bool tile_hybrid = h->opt_tile_mode && g.S > 0 && masked && !qs.f32 && lex_tile_supported(g, rt) &&
+        const bool tile_hybrid = h->opt_tile_mode && g.S > 0 && masked && !qs.f32 && h->lext && lex_tile_supported(g, rt) &&
                                  (g.C_pad == 0 || dense_tile_supported(g, nullptr));
         LexTileGeom lt{};
         if (tile_hybrid) {
