@@ -227,23 +227,22 @@ def main():
         gat_s = torch.empty((world, n_q, k), dtype=torch.float32, device=dev)
         gat_r = torch.empty((world, n_q, k), dtype=torch.int64, device=dev)
 
+    from dhr_b200.distributed import sharded_search
+
     def step(host_io):
         """one search of all queries over the (sharded) corpus; returns the final [Q,k] (scores, rows)"""
-        if host_io:
-            res = ix.search(qv_host, qi_host, k, out=out_dev if world > 1 else out_host)
+        qv, qi = (qv_host, qi_host) if host_io else (qv_dev, qi_dev)
+        if world == 1:
+            res = ix.search(qv, qi, k, out=out_host if host_io else out_dev)[:2]
+            st = ix.stats()
         else:
-            res = ix.search(qv_dev, qi_dev, k, out=out_dev)
-        st = ix.stats()
-        if world > 1:
-            # exchange step: NCCL all-gather of per-shard top-k over NVLink, then the merge kernel
-            dist.all_gather_into_tensor(gat_s, out_dev[0])
-            dist.all_gather_into_tensor(gat_r, out_dev[1])
-            ms, mr = topk_merge(gat_s, gat_r)
+            # per-shard search, then the exchange step: NCCL all-gather of the [Q,k] lists + merge kernel
+            res = sharded_search(ix, qv, qi, k, local_out=out_dev, gather_out=(gat_s, gat_r))
+            st = ix.stats()
             st['n_kernel_launches'] += 1
             if host_io and rank == 0:
-                out_host[0].copy_(ms, non_blocking=True)
-                out_host[1].copy_(mr, non_blocking=True)
-            res = (ms, mr)
+                out_host[0].copy_(res[0], non_blocking=True)
+                out_host[1].copy_(res[1], non_blocking=True)
         return res, st
 
     def timed(n_steps, host_io):
