@@ -40,7 +40,7 @@ LexTileGeom lex_tile_geom(const Geometry& g, int rt) {
     LexTileGeom t{};
     t.G = g.G; t.code_bytes = g.code_bytes; t.n_chunks = g.S_pad / kLT_SC; t.rt = rt;
     t.pblock_bytes = kLT_PT * kLT_SC * (1 + 2 * g.G);        // tiled copy always stores 8-bit codes
-    t.qoff_bytes = (int)round_up((int64_t)kLT_SC * (rt + 1) * 2, 16);
+    t.qoff_bytes = (int)round_up((int64_t)kLT_SC * (rt + 2) * 2, 16);   // rt buckets + end marker + one duplicate (branch-free clamp)
     t.qblock_stride = t.qoff_bytes + kLT_SC * kLT_QT * lt_entry_words(g.G) * 4;
     t.stage_bytes = (int)round_up(t.pblock_bytes, 128) + (int)round_up(t.qblock_stride, 128);
     return t;
@@ -63,18 +63,18 @@ template <typename CodeT>
 __global__ void __launch_bounds__(256)
 lex_tile_prep_kernel(const __half* __restrict__ q_lex16, const CodeT* __restrict__ q_code, int n_queries, int S_pad, int G,
                      int rt, int qoff_bytes, int qblock_stride, uint8_t* __restrict__ qblocks, uint32_t* __restrict__ qblock_bytes) {
-    extern __shared__ uint32_t hist[];             // [SC][rt + 1] counts, then exclusive offsets
+    extern __shared__ uint32_t hist[];             // [SC][rt + 2] counts, then exclusive offsets (last two per slice stay empty)
     const int chunk = blockIdx.x, qt = blockIdx.y;
     const int n_chunks = gridDim.x;
     const int q0 = qt * kLT_QT;
     const int nq = min(kLT_QT, n_queries - q0);
-    const int tbl = kLT_SC * (rt + 1);
+    const int tbl = kLT_SC * (rt + 2);
     for (int i = threadIdx.x; i < tbl; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < nq * kLT_SC; i += blockDim.x) {
         const int q = i / kLT_SC, j = i % kLT_SC;
         const uint32_t code = q_code[(size_t)(q0 + q) * S_pad + chunk * kLT_SC + j];
-        if (code < (uint32_t)rt) atomicAdd(&hist[j * (rt + 1) + code], 1u);
+        if (code < (uint32_t)rt) atomicAdd(&hist[j * (rt + 2) + code], 1u);
     }
     __syncthreads();
     if (threadIdx.x == 0) {                        // exclusive scan over (slice, code); bucket rt of every slice = end marker
@@ -93,7 +93,7 @@ lex_tile_prep_kernel(const __half* __restrict__ q_lex16, const CodeT* __restrict
         for (int q = 0; q < nq; ++q) {
             const uint32_t code = q_code[(size_t)(q0 + q) * S_pad + s];
             if (code >= (uint32_t)rt) continue;
-            const uint32_t pos = hist[j * (rt + 1) + code]++;
+            const uint32_t pos = hist[j * (rt + 2) + code]++;
             const __half* v = q_lex16 + ((size_t)(q0 + q) * S_pad + s) * G;
             uint32_t* e = ent + (size_t)pos * EW;
             uint32_t w = (uint32_t)q;
@@ -109,7 +109,7 @@ lex_tile_prep_kernel(const __half* __restrict__ q_lex16, const CodeT* __restrict
     __syncthreads();
     if (threadIdx.x == 0) {
         // total entries = offset of the end marker of the last slice after placement == final hist value there
-        const uint32_t total = hist[(kLT_SC - 1) * (rt + 1) + rt];
+        const uint32_t total = hist[(kLT_SC - 1) * (rt + 2) + rt + 1];
         qblock_bytes[(size_t)qt * n_chunks + chunk] = ((uint32_t)qoff_bytes + total * (uint32_t)EW * 4u + 15u) & ~15u;
     }
 }
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(kLT_Threads, 1) lex_tile_kernel(const __grid_c
 
     // ===== consumers: thread p owns passage p of the tile =====
     const int p = threadIdx.x;
-    const int offs_per_slice = a.rt + 1;
+    const int offs_per_slice = a.rt + 2;
     uint16_t* wq = wq_all + warp * (kLT_SC * kLT_Seg);
     const uint32_t tag = (uint32_t)lane << 10;
     int s = 0; uint32_t ph = 0;
@@ -265,67 +265,83 @@ __global__ void __launch_bounds__(kLT_Threads, 1) lex_tile_kernel(const __grid_c
             const uint32_t* ent = (const uint32_t*)(st + a.pblock_smem + a.qoff_bytes);
             const uint2 cw = *(const uint2*)(st + (size_t)p * kLT_SC);          // my 8 slice codes
 
-            // ---- phase A: 8 independent bucket lookups + warp scans, matches flattened into per-slice segments ----
-            uint32_t beg[kLT_SC], len[kLT_SC], incl[kLT_SC];
+            // ---- phase A (straight-line, branch-free): 8 bucket lookups, 4 packed warp scans, item stores ----
+            // The offset table has rt + 2 entries per slice (the last two equal), so clamping the code to rt yields an
+            // empty bucket for CODE_EMPTY without a branch.  Two 16-bit lengths share one register during the scan.
+            uint32_t beg[kLT_SC], lenp[kLT_SC / 2];
 #pragma unroll
             for (int j = 0; j < kLT_SC; ++j) {
-                const uint32_t code = ((j < 4 ? cw.x : cw.y) >> (8 * (j & 3))) & 0xFFu;
-                beg[j] = 0; len[j] = 0;
-                if (code < (uint32_t)a.rt) {
-                    beg[j] = off[j * offs_per_slice + code];
-                    len[j] = off[j * offs_per_slice + code + 1] - beg[j];
-                }
-                incl[j] = len[j];
+                const uint32_t code = min(((j < 4 ? cw.x : cw.y) >> (8 * (j & 3))) & 0xFFu, (uint32_t)a.rt);
+                const uint16_t* o = off + j * offs_per_slice + code;
+                const uint32_t b = o[0], l = (uint32_t)o[1] - b;
+                beg[j] = b;
+                if (j & 1) lenp[j >> 1] |= l << 16; else lenp[j >> 1] = l;
             }
+            uint32_t incp[kLT_SC / 2];
+#pragma unroll
+            for (int k = 0; k < kLT_SC / 2; ++k) incp[k] = lenp[k];
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
 #pragma unroll
-                for (int j = 0; j < kLT_SC; ++j) {
-                    const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl[j], d);
-                    if (lane >= d) incl[j] += n;
+                for (int k = 0; k < kLT_SC / 2; ++k) {
+                    const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incp[k], d);
+                    incp[k] += (lane >= d) ? n : 0u;
                 }
             }
-            uint32_t total[kLT_SC];
+            uint32_t totp[kLT_SC / 2];
+            uint32_t over = 0;
 #pragma unroll
-            for (int j = 0; j < kLT_SC; ++j) {
-                total[j] = __shfl_sync(0xFFFFFFFFu, incl[j], 31);
-                if (total[j] <= (uint32_t)kLT_Seg) {
-                    uint16_t* seg = wq + j * kLT_Seg + (incl[j] - len[j]);
+            for (int k = 0; k < kLT_SC / 2; ++k) {
+                totp[k] = __shfl_sync(0xFFFFFFFFu, incp[k], 31);
+                over |= ((totp[k] & 0xFFFFu) > (uint32_t)kLT_Seg) | ((totp[k] >> 16) > (uint32_t)kLT_Seg);
+            }
+            if (!over) {
+#pragma unroll
+                for (int j = 0; j < kLT_SC; ++j) {
+                    const uint32_t l = (j & 1) ? (lenp[j >> 1] >> 16) : (lenp[j >> 1] & 0xFFFFu);
+                    const uint32_t inc = (j & 1) ? (incp[j >> 1] >> 16) : (incp[j >> 1] & 0xFFFFu);
+                    uint16_t* seg = wq + j * kLT_Seg + (inc - l);
                     const uint32_t it = tag | beg[j];
 #pragma unroll
-                    for (uint32_t k = 0; k < 4; ++k) if (k < len[j]) seg[k] = (uint16_t)(it + k);
-                    for (uint32_t k = 4; k < len[j]; ++k) seg[k] = (uint16_t)(it + k);
+                    for (uint32_t k = 0; k < 4; ++k) if (k < l) seg[k] = (uint16_t)(it + k);
+                    for (uint32_t k = 4; k < l; ++k) seg[k] = (uint16_t)(it + k);
                 }
-            }
-            __syncwarp();
-
-            // ---- phase B: consume the segments, one match per lane; slices are ordered by __syncwarp ----
-#pragma unroll
-            for (int j = 0; j < kLT_SC; ++j) {
-                if (total[j] == 0) continue;
-                if (total[j] <= (uint32_t)kLT_Seg) {
+                __syncwarp();
+                // totals fit in a byte each (<= kLT_Seg): pack the 8 of them for the compact phase-B loop
+                const uint32_t t_lo = (totp[0] & 0xFFu) | ((totp[0] >> 16) << 8) | ((totp[1] & 0xFFu) << 16) | ((totp[1] >> 16) << 24);
+                const uint32_t t_hi = (totp[2] & 0xFFu) | ((totp[2] >> 16) << 8) | ((totp[3] & 0xFFu) << 16) | ((totp[3] >> 16) << 24);
+                // ---- phase B: consume the segments, one match per lane; slices are ordered by __syncwarp ----
+#pragma unroll 1
+                for (int j = 0; j < kLT_SC; ++j) {
+                    const uint32_t tj = ((j < 4 ? t_lo : t_hi) >> (8 * (j & 3))) & 0xFFu;
                     const uint16_t* seg = wq + j * kLT_Seg;
-                    for (uint32_t base = 0; base < total[j]; base += 32) {
-                        const uint32_t i = base + lane;
-                        if (i < total[j]) {
-                            const uint32_t it = seg[i];
-                            const int pp = (warp << 5) + (int)(it >> 10);
-                            uint32_t ew[EW], pv[PW];
-                            load_entry<G>(ent, it & 0x3FFu, ew);
-                            load_pvals<G>(pvals, j, pp, pv);
-                            float* ap = acc + (ew[0] & 0xFFFFu) * kLT_PT + pp;
+                    for (uint32_t i = lane; i < tj; i += 32) {
+                        const uint32_t it = seg[i];
+                        const int pp = (warp << 5) + (int)(it >> 10);
+                        uint32_t ew[EW], pv[PW];
+                        load_entry<G>(ent, it & 0x3FFu, ew);
+                        load_pvals<G>(pvals, j, pp, pv);
+                        float* ap = acc + (ew[0] & 0xFFFFu) * kLT_PT + pp;
+                        *ap = entry_dot<G, 0>(ew, pv, *ap);
+                    }
+                    __syncwarp();
+                }
+            } else {
+                // a queue segment would overflow (degenerate code distribution): every lane walks its own buckets
+#pragma unroll 1
+                for (int j = 0; j < kLT_SC; ++j) {
+                    const uint32_t code = min(((j < 4 ? cw.x : cw.y) >> (8 * (j & 3))) & 0xFFu, (uint32_t)a.rt);
+                    const uint16_t* o = off + j * offs_per_slice + code;
+                    const uint32_t b = o[0], e1 = o[1];
+                    if (b < e1) {
+                        uint32_t pv[PW];
+                        load_pvals<G>(pvals, j, p, pv);
+                        for (uint32_t e = b; e < e1; ++e) {
+                            uint32_t ew[EW];
+                            load_entry<G>(ent, e, ew);
+                            float* ap = acc + (ew[0] & 0xFFFFu) * kLT_PT + p;
                             *ap = entry_dot<G, 0>(ew, pv, *ap);
                         }
-                    }
-                } else if (len[j]) {
-                    // segment would overflow (degenerate code distribution): each lane walks its own bucket
-                    uint32_t pv[PW];
-                    load_pvals<G>(pvals, j, p, pv);
-                    for (uint32_t e = beg[j]; e < beg[j] + len[j]; ++e) {
-                        uint32_t ew[EW];
-                        load_entry<G>(ent, e, ew);
-                        float* ap = acc + (ew[0] & 0xFFFFu) * kLT_PT + p;
-                        *ap = entry_dot<G, 0>(ew, pv, *ap);
                     }
                 }
                 __syncwarp();
@@ -358,7 +374,7 @@ int launch_lex_tile_prep(const dhr_index* h, const LexTileGeom& t, const void* q
     const int n_qtiles = (n_queries + kLT_QT - 1) / kLT_QT;
     if (n_qtiles == 0) return DHR_OK;
     dim3 grid((unsigned)t.n_chunks, (unsigned)n_qtiles);
-    const size_t smem = (size_t)kLT_SC * (t.rt + 1) * sizeof(uint32_t);
+    const size_t smem = (size_t)kLT_SC * (t.rt + 2) * sizeof(uint32_t);
     if (g.code_bytes == 1)
         lex_tile_prep_kernel<uint8_t><<<grid, 256, smem, st>>>((const __half*)q_lex16, (const uint8_t*)q_code, n_queries, g.S_pad, g.G,
                                                                t.rt, t.qoff_bytes, t.qblock_stride, qblocks, qblock_bytes);
