@@ -84,8 +84,8 @@ struct DenseTileArgs {
     int n_qtiles;                      // 64-query tiles in flight
     int n_queries;                     // valid queries in flight (slots)
     int mode;                          // 0 = filter + append, 1 = write scratch
-    float* scratch;                    // [slot][scratch_rows]  (mode 1), rows relative to tile_row0
-    long long scratch_rows;
+    float* scratch;                    // [row - tile_row0][scratch_slots]  (mode 1)
+    long long scratch_slots;           // query slots per scratch row (multiple of 64)
     float* tau; uint32_t* cnt; float* cand_score; int32_t* cand_row; int cap;
 };
 
@@ -191,12 +191,16 @@ dense_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const long long row = a.tile_row0 + (long long)t * kDT_M + p;
             const bool row_ok = row >= a.row_begin && row < a.row_end;
             if (a.mode == 1) {
-                if (row_ok) {
-                    float* dst = a.scratch + (size_t)(qt * kDT_N) * a.scratch_rows + (size_t)(row - a.tile_row0);
+                if (row_ok) {   // scratch[row][slot]: this thread's 64 consecutive query slots = 256 contiguous bytes
+                    float4* dst = (float4*)(a.scratch + (size_t)(row - a.tile_row0) * a.scratch_slots + (size_t)qt * kDT_N);
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) dst[(size_t)q * a.scratch_rows] = __uint_as_float(v0[q]);
+                    for (int q = 0; q < 8; ++q)
+                        dst[q] = make_float4(__uint_as_float(v0[4 * q]), __uint_as_float(v0[4 * q + 1]), __uint_as_float(v0[4 * q + 2]),
+                                             __uint_as_float(v0[4 * q + 3]));
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) dst[(size_t)(q + 32) * a.scratch_rows] = __uint_as_float(v1[q]);
+                    for (int q = 0; q < 8; ++q)
+                        dst[8 + q] = make_float4(__uint_as_float(v1[4 * q]), __uint_as_float(v1[4 * q + 1]), __uint_as_float(v1[4 * q + 2]),
+                                                 __uint_as_float(v1[4 * q + 3]));
                 }
             } else if (row_ok) {
 #pragma unroll
@@ -268,7 +272,7 @@ bool dense_tile_supported(const Geometry& g, int* n_stages_out) {
 // Launch K2 over rows [row_begin, row_end) (row_begin aligned to 128 from tile_row0) for `n_queries` in-flight queries
 // whose fp16 dense block starts at q_dns16 (row pitch C_pad).
 int launch_dense_tile(const dhr_index* h, const void* q_dns16, int n_queries, long long tile_row0, long long row_begin,
-                      long long row_end, int mode, float* scratch, long long scratch_rows, const TopkState& t, int cap,
+                      long long row_end, int mode, float* scratch, long long scratch_slots, const TopkState& t, int cap,
                       cudaStream_t st) {
     const Geometry& g = h->g;
     int stages = 0;
@@ -287,8 +291,8 @@ int launch_dense_tile(const dhr_index* h, const void* q_dns16, int n_queries, lo
     a.n_qtiles = (n_queries + kDT_N - 1) / kDT_N;
     a.n_queries = n_queries;
     a.mode = mode;
-    a.scratch = scratch ? scratch + (a.tile_row0 - tile_row0) : nullptr;
-    a.scratch_rows = scratch_rows;
+    a.scratch = scratch ? scratch + (size_t)(a.tile_row0 - tile_row0) * scratch_slots : nullptr;
+    a.scratch_slots = scratch_slots;
     a.tau = t.tau; a.cnt = t.cnt; a.cand_score = t.cand_score; a.cand_row = t.cand_row; a.cap = cap;
     const size_t smem = (size_t)a.n_kblocks * kDT_BBytes + (size_t)stages * kDT_ABytes + 1024;
     DHR_CUDA(cudaFuncSetAttribute(dense_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -117,12 +117,12 @@ bool lex_tile_supported(const Geometry& g, int rt);
 int launch_lex_tile_prep(const dhr_index* h, const LexTileGeom& t, const void* q_lex16, const void* q_code, int n_queries,
                          uint8_t* qblocks, uint32_t* qblock_bytes, cudaStream_t st);
 int launch_lex_tile(const dhr_index* h, const LexTileGeom& t, const uint8_t* qblocks, const uint32_t* qblock_bytes, int n_queries,
-                    long long row_begin, long long row_end, const float* scratch, long long scratch_rows, long long scratch_row0,
+                    long long row_begin, long long row_end, const float* scratch, long long scratch_slots, long long scratch_row0,
                     const TopkState& tk, int cap, cudaStream_t st);
 
 bool dense_tile_supported(const Geometry& g, int* n_stages_out);
 int launch_dense_tile(const dhr_index* h, const void* q_dns16, int n_queries, long long tile_row0, long long row_begin,
-                      long long row_end, int mode, float* scratch, long long scratch_rows, const TopkState& t, int cap,
+                      long long row_end, int mode, float* scratch, long long scratch_slots, const TopkState& t, int cap,
                       cudaStream_t st);
 
 int ensure_device_buffer(void** p, size_t* cur, size_t need);

@@ -150,8 +150,8 @@ struct LexTileArgs {
     int pblock_bytes, qoff_bytes, qblock_stride, stage_bytes, pblock_smem;
     int n_qtiles;                      // query tiles in flight
     int n_queries;                     // valid in-flight queries (slots)
-    const float* scratch;              // dense scores [slot][scratch_rows] or nullptr
-    long long scratch_rows; long long scratch_row0;
+    const float* scratch;              // dense scores [row - scratch_row0][scratch_slots] or nullptr
+    long long scratch_slots; long long scratch_row0;
     float* tau; uint32_t* cnt; float* cand_score; int32_t* cand_row; int cap;
 };
 
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(kLT_Threads, 1) lex_tile_kernel(const __grid_c
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar[kLT_Stages];
     __shared__ __align__(8) uint64_t empty_bar[kLT_Stages];
-    __shared__ float tau_s[kLT_QT];
+    __shared__ __align__(16) float tau_s[kLT_QT];
     __shared__ uint16_t wq_all[(kLT_PT / 32) * kLT_SC * kLT_Seg];
 
     constexpr int EW = lt_entry_words(G);
@@ -243,15 +243,20 @@ __global__ void __launch_bounds__(kLT_Threads, 1) lex_tile_kernel(const __grid_c
     for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q) {
         const long long row = (tile0 + t) * kLT_PT + p;
         const bool row_ok = row >= a.row_begin && row < a.row_end && row < a.n_rows;
-        // acc init: dense score of (q, row) from K2 or zero; loads are issued 16 at a time so their latency overlaps
+        // acc init: dense scores of (row, q0..q0+127) written by K2 (512 contiguous bytes per row) or zero;
+        // 8 x 128-bit loads are in flight at a time.  Slots beyond nq hold zeros (TMA zero-fills missing queries).
         if (a.scratch && row_ok) {
-            const float* src = a.scratch + (size_t)q0 * a.scratch_rows + (size_t)(row - a.scratch_row0);
-            for (int qb = 0; qb < kLT_QT; qb += 16) {
-                float v[16];
+            const float4* src = (const float4*)(a.scratch + (size_t)(row - a.scratch_row0) * a.scratch_slots + q0);
+#pragma unroll 1
+            for (int qb = 0; qb < kLT_QT / 4; qb += 8) {
+                float4 v[8];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = (qb + i < nq) ? __ldcs(src + (size_t)(qb + i) * a.scratch_rows) : 0.f;
+                for (int i = 0; i < 8; ++i) v[i] = __ldcs(src + qb + i);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) acc[(qb + i) * kLT_PT + p] = v[i];
+                for (int i = 0; i < 8; ++i) {
+                    float* d = acc + (size_t)(4 * (qb + i)) * kLT_PT + p;
+                    d[0] = v[i].x; d[kLT_PT] = v[i].y; d[2 * kLT_PT] = v[i].z; d[3 * kLT_PT] = v[i].w;
+                }
             }
         } else {
 #pragma unroll 16
@@ -315,14 +320,24 @@ __global__ void __launch_bounds__(kLT_Threads, 1) lex_tile_kernel(const __grid_c
                 for (int j = 0; j < kLT_SC; ++j) {
                     const uint32_t tj = ((j < 4 ? t_lo : t_hi) >> (8 * (j & 3))) & 0xFFu;
                     const uint16_t* seg = wq + j * kLT_Seg;
-                    for (uint32_t i = lane; i < tj; i += 32) {
-                        const uint32_t it = seg[i];
-                        const int pp = (warp << 5) + (int)(it >> 10);
-                        uint32_t ew[EW], pv[PW];
-                        load_entry<G>(ent, it & 0x3FFu, ew);
-                        load_pvals<G>(pvals, j, pp, pv);
-                        float* ap = acc + (ew[0] & 0xFFFFu) * kLT_PT + pp;
-                        *ap = entry_dot<G, 0>(ew, pv, *ap);
+                    // two independent matches per lane and iteration (items i and i + 32 never share a (query, passage) pair)
+                    for (uint32_t i = lane; i < tj; i += 64) {
+                        const bool two = i + 32 < tj;
+                        const uint32_t it0 = seg[i];
+                        const uint32_t it1 = two ? seg[i + 32] : it0;
+                        const int pp0 = (warp << 5) + (int)(it0 >> 10), pp1 = (warp << 5) + (int)(it1 >> 10);
+                        uint32_t ew0[EW], ew1[EW], pv0[PW], pv1[PW];
+                        load_entry<G>(ent, it0 & 0x3FFu, ew0);
+                        load_entry<G>(ent, it1 & 0x3FFu, ew1);
+                        load_pvals<G>(pvals, j, pp0, pv0);
+                        load_pvals<G>(pvals, j, pp1, pv1);
+                        float* ap0 = acc + (ew0[0] & 0xFFFFu) * kLT_PT + pp0;
+                        float* ap1 = acc + (ew1[0] & 0xFFFFu) * kLT_PT + pp1;
+                        const float a0 = *ap0, a1 = *ap1;
+                        const float r0 = entry_dot<G, 0>(ew0, pv0, a0);
+                        const float r1 = entry_dot<G, 0>(ew1, pv1, a1);
+                        *ap0 = r0;
+                        if (two) *ap1 = r1;
                     }
                     __syncwarp();
                 }
@@ -351,14 +366,22 @@ __global__ void __launch_bounds__(kLT_Threads, 1) lex_tile_kernel(const __grid_c
         }
         // admission filter
         if (row_ok) {
-            for (int q = 0; q < nq; ++q) {
-                const float sc = acc[q * kLT_PT + p] + 0.0f;
-                if (sc > tau_s[q]) {
-                    const int slot = q0 + q;
-                    const uint32_t pos = atomicAdd(a.cnt + slot, 1u);
-                    if (pos < (uint32_t)a.cap) {
-                        a.cand_score[(size_t)slot * a.cap + pos] = sc;
-                        a.cand_row[(size_t)slot * a.cap + pos] = (int32_t)row;
+#pragma unroll 1
+            for (int qb = 0; qb < nq; qb += 4) {
+                const float4 tq = *(const float4*)(tau_s + qb);                    // tau_s is +inf beyond nq
+                const float tv[4] = {tq.x, tq.y, tq.z, tq.w};
+                float sv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) sv[i] = acc[(qb + i) * kLT_PT + p] + 0.0f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (sv[i] > tv[i]) {
+                        const int slot = q0 + qb + i;
+                        const uint32_t pos = atomicAdd(a.cnt + slot, 1u);
+                        if (pos < (uint32_t)a.cap) {
+                            a.cand_score[(size_t)slot * a.cap + pos] = sv[i];
+                            a.cand_row[(size_t)slot * a.cap + pos] = (int32_t)row;
+                        }
                     }
                 }
             }
@@ -412,7 +435,7 @@ static int launch_lex_tile_g(const dhr_index* h, const LexTileArgs& a, size_t sm
 }
 
 int launch_lex_tile(const dhr_index* h, const LexTileGeom& t, const uint8_t* qblocks, const uint32_t* qblock_bytes, int n_queries,
-                    long long row_begin, long long row_end, const float* scratch, long long scratch_rows, long long scratch_row0,
+                    long long row_begin, long long row_end, const float* scratch, long long scratch_slots, long long scratch_row0,
                     const TopkState& tk, int cap, cudaStream_t st) {
     if (row_end <= row_begin || n_queries <= 0) return DHR_OK;
     LexTileArgs a{};
@@ -424,7 +447,7 @@ int launch_lex_tile(const dhr_index* h, const LexTileGeom& t, const uint8_t* qbl
     a.stage_bytes = t.stage_bytes; a.pblock_smem = (int)round_up(t.pblock_bytes, 128);
     a.n_qtiles = (n_queries + kLT_QT - 1) / kLT_QT;
     a.n_queries = n_queries;
-    a.scratch = scratch; a.scratch_rows = scratch_rows; a.scratch_row0 = scratch_row0;
+    a.scratch = scratch; a.scratch_slots = scratch_slots; a.scratch_row0 = scratch_row0;
     a.tau = tk.tau; a.cnt = tk.cnt; a.cand_score = tk.cand_score; a.cand_row = tk.cand_row; a.cap = cap;
     if (!h->lext) return DHR_ERR_STATE;
     return launch_lex_tile_g(h, a, lex_tile_smem_bytes(t), st);

@@ -333,10 +333,10 @@ static int run_batch_hybrid_tile(dhr_index* h, const LexTileGeom& lt, const Quer
         for (long long r0 = bounds[c]; r0 < bounds[c + 1]; r0 += kTileSubRows) {
             const long long r1 = std::min(bounds[c + 1], r0 + kTileSubRows);
             if (g.C_pad > 0) {
-                DHR_TRY(launch_dense_tile(h, q16, nq, r0, r0, r1, 1, h->scratch, kTileSubRows, t, kCandCap, st));
+                DHR_TRY(launch_dense_tile(h, q16, nq, r0, r0, r1, 1, h->scratch, kMaxInflight, t, kCandCap, st));
                 h->stats.n_kernel_launches++;
             }
-            DHR_TRY(launch_lex_tile(h, lt, qblocks, qbytes, nq, r0, r1, g.C_pad > 0 ? h->scratch : nullptr, kTileSubRows, r0, t,
+            DHR_TRY(launch_lex_tile(h, lt, qblocks, qbytes, nq, r0, r1, g.C_pad > 0 ? h->scratch : nullptr, kMaxInflight, r0, t,
                                     kCandCap, st));
             h->stats.n_kernel_launches++;
             h->stats.n_scan_launches++;
