@@ -110,8 +110,8 @@ struct LexTileGeom {
     int pblock_bytes, qoff_bytes, qblock_stride, stage_bytes;
 };
 constexpr int kLexTileRows = 256;        // passages per K1t tile
-constexpr int kLexTileQueries = 128;     // queries per K1t tile
-constexpr int kLexTileSlices = 8;        // slices per chunk
+constexpr int kLexTileQueries = 64;      // queries per K1t tile (acc[64][256] fp32 = 64 KiB -> two CTAs per SM)
+constexpr int kLexTileSlices = 4;        // slices per chunk
 LexTileGeom lex_tile_geom(const Geometry& g, int rt);
 bool lex_tile_supported(const Geometry& g, int rt);
 int launch_lex_tile_prep(const dhr_index* h, const LexTileGeom& t, const void* q_lex16, const void* q_code, int n_queries,

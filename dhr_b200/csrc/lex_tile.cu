@@ -30,7 +30,10 @@ constexpr int kLT_QT = kLexTileQueries; // queries per tile
 constexpr int kLT_SC = kLexTileSlices;  // slices per chunk
 constexpr int kLT_Stages = 2;
 constexpr int kLT_Threads = kLT_PT + 32;
-constexpr int kLT_Seg = 80;             // per-warp, per-slice match queue segment (items)
+constexpr int kLT_Seg = 48;             // per-warp, per-slice match queue segment (items)
+constexpr int kLT_CtasPerSm = 2;
+static_assert(kLT_SC == 4 || kLT_SC == 8, "chunk of 4 or 8 slices");
+static_assert(kLT_SC * kLT_QT <= 1024, "queue items carry a 10-bit entry index");
 
 __host__ __device__ constexpr int lt_entry_words(int G) { return (G + 2) / 2; }          // {qid, v0..vG-1} as fp16 pairs
 __host__ __device__ constexpr int lt_pval_words(int G) { return (G + 1) / 2; }
@@ -51,10 +54,11 @@ size_t lex_tile_smem_bytes(const LexTileGeom& t) {
 }
 
 constexpr size_t kLT_StaticSmem = (size_t)(kLT_PT / 32) * kLT_SC * kLT_Seg * 2 + kLT_QT * 4 + 2048;
+constexpr size_t kLT_SmemBudget = (size_t)(227 * 1024) / kLT_CtasPerSm - 1024;   // per CTA (1 KiB reserved per CTA by the driver)
 
 bool lex_tile_supported(const Geometry& g, int rt) {
     if (g.S_pad <= 0 || g.S_pad % kLT_SC != 0 || rt < 1 || rt > 254 || g.G > 8) return false;
-    return lex_tile_smem_bytes(lex_tile_geom(g, rt)) + kLT_StaticSmem <= 227 * 1024;
+    return lex_tile_smem_bytes(lex_tile_geom(g, rt)) + kLT_StaticSmem <= kLT_SmemBudget;
 }
 
 // ---- query-tile preparation: one CTA per (chunk, query tile) builds offsets + entries ------------
@@ -186,7 +190,7 @@ __device__ __forceinline__ void load_entry(const uint32_t* ent, uint32_t e, uint
 }
 
 template <int G>
-__global__ void __launch_bounds__(kLT_Threads, 1) lex_tile_kernel(const __grid_constant__ LexTileArgs a) {
+__global__ void __launch_bounds__(kLT_Threads, kLT_CtasPerSm) lex_tile_kernel(const __grid_constant__ LexTileArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar[kLT_Stages];
     __shared__ __align__(8) uint64_t empty_bar[kLT_Stages];
@@ -268,7 +272,9 @@ __global__ void __launch_bounds__(kLT_Threads, 1) lex_tile_kernel(const __grid_c
             const uint32_t* pvals = (const uint32_t*)(st + (size_t)kLT_PT * kLT_SC);
             const uint16_t* off = (const uint16_t*)(st + a.pblock_smem);
             const uint32_t* ent = (const uint32_t*)(st + a.pblock_smem + a.qoff_bytes);
-            const uint2 cw = *(const uint2*)(st + (size_t)p * kLT_SC);          // my 8 slice codes
+            uint2 cw;                                                             // my slice codes (one byte each)
+            if constexpr (kLT_SC == 8) cw = *(const uint2*)(st + (size_t)p * kLT_SC);
+            else { cw.x = *(const uint32_t*)(st + (size_t)p * kLT_SC); cw.y = 0; }
 
             // ---- phase A (straight-line, branch-free): 8 bucket lookups, 4 packed warp scans, item stores ----
             // The offset table has rt + 2 entries per slice (the last two equal), so clamping the code to rt yields an
@@ -314,7 +320,10 @@ __global__ void __launch_bounds__(kLT_Threads, 1) lex_tile_kernel(const __grid_c
                 __syncwarp();
                 // totals fit in a byte each (<= kLT_Seg): pack the 8 of them for the compact phase-B loop
                 const uint32_t t_lo = (totp[0] & 0xFFu) | ((totp[0] >> 16) << 8) | ((totp[1] & 0xFFu) << 16) | ((totp[1] >> 16) << 24);
-                const uint32_t t_hi = (totp[2] & 0xFFu) | ((totp[2] >> 16) << 8) | ((totp[3] & 0xFFu) << 16) | ((totp[3] >> 16) << 24);
+                uint32_t t_hi = 0;
+                if constexpr (kLT_SC == 8)
+                    t_hi = (totp[kLT_SC / 2 - 2] & 0xFFu) | ((totp[kLT_SC / 2 - 2] >> 16) << 8) | ((totp[kLT_SC / 2 - 1] & 0xFFu) << 16) |
+                           ((totp[kLT_SC / 2 - 1] >> 16) << 24);
                 // ---- phase B: consume the segments, one match per lane; slices are ordered by __syncwarp ----
 #pragma unroll 1
                 for (int j = 0; j < kLT_SC; ++j) {
@@ -412,7 +421,7 @@ template <int G>
 static int launch_lex_tile_t(const dhr_index* h, const LexTileArgs& a, size_t smem, cudaStream_t st) {
     auto kern = lex_tile_kernel<G>;
     DHR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_q = h->num_sms / a.n_qtiles;
+    int per_q = h->num_sms * kLT_CtasPerSm / a.n_qtiles;
     if (per_q < 1) per_q = 1;
     if (per_q > a.n_tiles) per_q = a.n_tiles;
     kern<<<(unsigned)(per_q * a.n_qtiles), kLT_Threads, smem, st>>>(a);
