@@ -45,8 +45,8 @@ def parse():
     ap.add_argument('--query-block', type=int, default=None)
     ap.add_argument('--query-groups', type=int, default=None)
     ap.add_argument('--scan-variant', type=int, default=None)
-    ap.add_argument('--cpu-rows', type=int, default=100000, help='rows of the bounded CPU-baseline sample')
-    ap.add_argument('--cpu-queries', type=int, default=4)
+    ap.add_argument('--cpu-rows', type=int, default=400000, help='rows of the bounded CPU-baseline sample')
+    ap.add_argument('--cpu-queries', type=int, default=8)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
 
