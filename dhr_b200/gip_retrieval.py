@@ -15,6 +15,7 @@ Differences, all deliberate:
 from __future__ import annotations
 
 import argparse
+import os
 import pickle
 import time
 
@@ -28,10 +29,6 @@ except Exception:  # pragma: no cover
     torch = None
 
 
-def _to_numpy_or_tensor(x):
-    return x
-
-
 def _as_lists(scores, rows, counts, qids, local_offset=0):
     """[Q,k] arrays -> the reference's two dicts (qid -> list[int], qid -> list[float])."""
     if torch is not None and isinstance(scores, torch.Tensor):
@@ -42,10 +39,6 @@ def _as_lists(scores, rows, counts, qids, local_offset=0):
         all_scores[qid] = scores[i, :n].tolist()
         all_results[qid] = (rows[i, :n] - local_offset).tolist()
     return all_results, all_scores
-
-
-def _n_rows(x):
-    return len(x) if isinstance(x, GipIndex) else x.shape[0]
 
 
 def _open_index(corpus_embs, corpus_arg_idxs, emb_dim, device=0):
@@ -195,18 +188,27 @@ def main(argv=None):
         query_embs[:, -cls_dim:] = args.lamda * query_embs[:, -cls_dim:]   # :281-283
 
     print('Load index ...')
-    with open(args.index_path, 'rb') as f:
-        corpus_embs, corpus_arg_idxs, docids = pickle.load(f)
-    lo, hi = shard_bounds(len(docids), args.total_shrad, args.shrad)
-    corpus_embs = corpus_embs[lo:hi]
-    corpus_arg_idxs = corpus_arg_idxs[lo:hi] if isinstance(corpus_arg_idxs, np.ndarray) else None
-    docids = docids[lo:hi]
+    if os.path.isdir(args.index_path):
+        # mmap-able .npy container (dhr_b200/index_io.py): only this shard's rows are touched
+        from .index_io import open_gip_index
+        index, docids = open_gip_index(args.index_path, args.total_shrad, args.shrad, device=args.device,
+                                       n_slices=args.emb_dim if query_arg_idxs is not None else 0, group=1)
+    else:
+        with open(args.index_path, 'rb') as f:
+            corpus_embs, corpus_arg_idxs, docids = pickle.load(f)
+        lo, hi = shard_bounds(len(docids), args.total_shrad, args.shrad)
+        corpus_embs = corpus_embs[lo:hi]
+        corpus_arg_idxs = corpus_arg_idxs[lo:hi] if isinstance(corpus_arg_idxs, np.ndarray) else None
+        docids = docids[lo:hi]
+        if query_arg_idxs is not None:
+            index = GipIndex.from_arrays(corpus_embs, corpus_arg_idxs, n_slices=args.emb_dim, group=1, device=args.device)
+        else:
+            index = GipIndex.from_arrays(corpus_embs, None, device=args.device)
+        del corpus_embs, corpus_arg_idxs
 
     if query_arg_idxs is not None:
-        index = GipIndex.from_arrays(corpus_embs, corpus_arg_idxs, n_slices=args.emb_dim, group=1, device=args.device)
         results, scores = GIP_retrieval(qids, query_embs, query_arg_idxs, index, None, args)
     else:
-        index = GipIndex.from_arrays(corpus_embs, None, device=args.device)
         results, scores = IP_retrieval(qids, query_embs, index, args)
     index.close()
 

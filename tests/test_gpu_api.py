@@ -115,6 +115,12 @@ def test_cli_main_round_trip(tmp_path, monkeypatch):
 
     gr.main(base)
     check('result.trec', g['trec_single'])
+    # same through the mmap-able .npy container (index_path is a directory)
+    from dhr_b200 import index_io
+    index_io.pickle_to_npy(str(ip), str(tmp_path / 'npy'))
+    for sh in range(3):
+        gr.main([a if a != str(ip) else str(tmp_path / 'npy') for a in base] + ['--total_shrad', '3', '--shrad', str(sh)])
+        check('result%d.trec' % sh, g['trec_shard%d' % sh])
     for sh in range(3):
         gr.main(base + ['--total_shrad', '3', '--shrad', str(sh)])
         check('result%d.trec' % sh, g['trec_shard%d' % sh])

@@ -110,3 +110,48 @@ def test_cli_parser_accepts_reference_flags_verbatim():
                                    '--lamda', '0.5', '--agip_topk', '10000', '--IP', '--brute_force', '--batch', '4',
                                    '--run_name', 'x', '--faiss_pq_index_path', 'p'])
     assert a.total_shrad == 2 and a.shrad == 1 and a.lamda == 0.5 and a.rerank and a.IP and a.brute_force
+
+
+def test_index_container_round_trip(tmp_path):
+    """pickle triple -> mmap-able .npy directory -> pickle triple is lossless; shards map only their rows."""
+    import pickle
+    from dhr_b200 import index_io
+    g = load_golden('main_trec_grid')
+    docids = [str(x) for x in g['docids']]
+    src = tmp_path / 'c.index.pt'
+    with open(src, 'wb') as f:
+        pickle.dump([g['c_vals'], g['c_idx'], docids], f, protocol=4)
+    d = tmp_path / 'npy'
+    index_io.main(['to-npy', str(src), str(d)])
+    back = tmp_path / 'back.index.pt'
+    index_io.main(['to-pickle', str(d), str(back)])
+    with open(back, 'rb') as f:
+        v, i, ids = pickle.load(f)
+    assert np.array_equal(v, g['c_vals']) and v.dtype == np.float16
+    assert np.array_equal(i, g['c_idx']) and i.dtype == g['c_idx'].dtype and ids == docids
+    for sh in range(3):
+        vals, idx, ids, lo = index_io.load_npy(str(d), 3, sh)
+        a, b = go.shard_bounds(len(docids), 3, sh)
+        assert lo == a and np.array_equal(vals, g['c_vals'][a:b]) and np.array_equal(idx, g['c_idx'][a:b]) and ids == docids[a:b]
+    # dense-only index: the reference stores the int 0 in place of idx (index.py:40-43)
+    with open(src, 'wb') as f:
+        pickle.dump([g['c_vals'], 0, list(range(len(docids)))], f, protocol=4)
+    index_io.main(['to-npy', str(src), str(tmp_path / 'dense')])
+    vals, idx, ids, _ = index_io.load_npy(str(tmp_path / 'dense'))
+    assert idx is None and ids == list(range(len(docids)))
+
+
+def test_merge_splits_matches_reference_semantics(tmp_path):
+    import pickle
+    from dhr_b200 import index_io
+    g = load_golden('main_trec_grid')
+    n = g['c_vals'].shape[0]
+    cuts = [0, 150, 290, n]
+    for k in range(3):
+        with open(tmp_path / ('corpus.split%02d.pt' % k), 'wb') as f:
+            pickle.dump([g['c_vals'][cuts[k]:cuts[k + 1]], g['c_idx'][cuts[k]:cuts[k + 1]],
+                         [str(x) for x in g['docids'][cuts[k]:cuts[k + 1]]]], f, protocol=4)
+    out = index_io.merge_splits(str(tmp_path), 'corpus')
+    with open(out, 'rb') as f:
+        v, i, ids = pickle.load(f)
+    assert np.array_equal(v, g['c_vals']) and np.array_equal(i, g['c_idx']) and ids == [str(x) for x in g['docids']]
