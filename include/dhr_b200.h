@@ -138,6 +138,16 @@ int dhr_rerank(dhr_index* h, int n_queries, int q_val_dtype, const void* q_vals,
 int dhr_topk_merge(int device, int n_parts, int n_queries, int k, const float* scores, const int64_t* rows,
                    float* out_scores, int64_t* out_rows, void* stream);
 
+/* ---- next row: densify op on the device --------------------------------------
+ * Replaces tevatron/DHR/utils.py:5-22 `densify` plus the fp16 / uint8 storage conversion of
+ * tevatron/driver/encode.py:155-170,180-195: lexical_reps [batch, vocab] (fp32 or fp16, DEVICE memory) ->
+ * drop the first remove_dims ids -> view(batch, R, dims) -> max over R.  Writes the fp16 values and the uint8
+ * argmax (first maximum) straight into caller-provided DEVICE buffers with the given row strides (elements), e.g.
+ * the value / index blocks of an index under construction. Stream-ordered, asynchronous. */
+int dhr_densify(int device, int batch, int vocab, int dims, int remove_dims, int val_dtype, const void* reps,
+                int64_t reps_row_stride, void* out_vals_f16, int64_t out_val_row_stride, uint8_t* out_idx,
+                int64_t out_idx_row_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -185,6 +185,17 @@ def IP_retrieval_port(qids, query_embs, corpus_embs, args):
     return results, scores_out
 
 
+def densify_port(lexical_reps, dims=768, remove_dims=570):
+    """numpy restatement of tevatron/DHR/utils.py:5-22 + the storage casts of tevatron/driver/encode.py:156-157:
+    drop the first remove_dims ids, view (B, R, dims), max over R; fp16 values, uint8 argmax (first maximum)."""
+    x = np.asarray(lexical_reps, dtype=np.float32)
+    b = x.shape[0]
+    if (x.shape[1] - remove_dims) % dims != 0:
+        raise ValueError('Input lexical representation cannot be densified, please fix dims or remove_dims')
+    v = x[:, remove_dims:].reshape(b, -1, dims)
+    return v.max(axis=1).astype(np.float16), v.argmax(axis=1).astype(np.uint8)
+
+
 def make_args(**kw):
     """Namespace with the defaults of gip_retrieval.py:234-253."""
     d = dict(emb_dim=768, theta=0.1, topk=1000, agip_topk=10000, combine_cls=False, IP=False,

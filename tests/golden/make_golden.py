@@ -219,5 +219,24 @@ def main():
              trec_single=np.array(t['result.trec']))
 
 
+def densify_golden():
+    """tevatron/DHR/utils.py:densify on a small vocabulary (same structure as 30522 = 570 + 39 * 768)."""
+    sys.path.insert(0, refshim.REFERENCE_ROOT)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('ref_dhr_utils', os.path.join(refshim.REFERENCE_ROOT, 'tevatron', 'DHR', 'utils.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(7)
+    x = np.log1p(np.maximum(rng.standard_normal((6, 30 + 39 * 64)).astype(np.float32), 0))      # relu-log style reps, many exact zeros/ties
+    vals, idx = mod.densify(torch.from_numpy(x), dims=64, remove_dims=30)
+    np.savez_compressed(os.path.join(HERE, 'densify_op.npz'), x=x, dims=64, remove_dims=30,
+                        ref_vals=vals.numpy().astype(np.float16), ref_idx=idx.numpy().astype(np.uint8))
+    print('wrote densify_op.npz')
+
+
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'densify':
+        densify_golden()
+    else:
+        main()
+        densify_golden()

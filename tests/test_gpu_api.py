@@ -132,3 +132,50 @@ def test_cli_main_round_trip(tmp_path, monkeypatch):
         pickle.dump([d['c_vals'], 0, [str(x) for x in d['docids']]], f, protocol=4)
     gr.main(['--query_emb_path', str(qp), '--index_path', str(ip), '--topk', str(int(d['topk'])), '--run_name', 'golden'])
     check('result.trec', d['trec_single'])
+
+
+def test_gpu_densify_op_matches_reference():
+    from dhr_b200.densify import densify
+    g = load_golden('densify_op')
+    x = torch.from_numpy(g['x']).cuda()
+    v, i = densify(x, dims=int(g['dims']), remove_dims=int(g['remove_dims']))
+    assert np.array_equal(v.cpu().numpy(), g['ref_vals']) and np.array_equal(i.cpu().numpy(), g['ref_idx'])
+    # reference-sized vocabulary, fp16 input, written into strided views of an index block
+    rng = np.random.default_rng(3)
+    big = np.maximum(rng.standard_normal((33, 30522)).astype(np.float32), 0).astype(np.float16)
+    vals = torch.zeros((33, 896), dtype=torch.float16, device='cuda')
+    idx = torch.zeros((33, 768), dtype=torch.uint8, device='cuda')
+    densify(torch.from_numpy(big).cuda(), out=(vals[:, :768], idx))
+    ev, ei = go.densify_port(big.astype(np.float32))
+    assert np.array_equal(vals[:, :768].cpu().numpy(), ev) and np.array_equal(idx.cpu().numpy(), ei)
+    assert torch.all(vals[:, 768:] == 0)
+    with pytest.raises(ValueError):
+        densify(x, dims=7)
+
+
+def test_merge_result_cli(tmp_path, monkeypatch):
+    """3 shard files written by the CLI merge into the single-shard result (tie groups as sets)."""
+    from dhr_b200 import merge_result
+    g = load_golden('main_trec_grid')
+    monkeypatch.chdir(tmp_path)
+    for sh in range(3):
+        with open('result%d.trec' % sh, 'w') as f:
+            f.write(str(g['trec_shard%d' % sh]))
+    merge_result.main(['--total_shrad', '3', '--topk', str(int(g['topk'])), '--run_name', 'golden'])
+    ours = open('result.trec').read().splitlines()
+    # expected: per query, the best topk of the union by score; compare (qid, rank, score) sequences with an oracle merge
+    exp = {}
+    for sh in range(3):
+        for l in str(g['trec_shard%d' % sh]).splitlines():
+            f = l.split(' ')
+            exp.setdefault(f[0], []).append((float(f[4]), f[2]))
+    k = int(g['topk'])
+    got = {}
+    for l in ours:
+        f = l.split(' ')
+        got.setdefault(f[0], []).append((float(f[4]), f[2], int(f[3])))
+    for q, items in exp.items():
+        want = sorted((s for s, _ in items), reverse=True)[:k]
+        assert [s for s, _, _ in got[q]] == want
+        assert [r for _, _, r in got[q]] == list(range(1, len(want) + 1))
+        assert all((s, d) in items for s, d, _ in got[q])
