@@ -276,54 +276,50 @@ __global__ void __launch_bounds__(kLT_Threads, kLT_CtasPerSm) lex_tile_kernel(co
             if constexpr (kLT_SC == 8) cw = *(const uint2*)(st + (size_t)p * kLT_SC);
             else { cw.x = *(const uint32_t*)(st + (size_t)p * kLT_SC); cw.y = 0; }
 
-            // ---- phase A (straight-line, branch-free): 8 bucket lookups, 4 packed warp scans, item stores ----
+            // ---- phase A: bucket lookups (branch-free) and match flattening into per-slice queue segments ----
             // The offset table has rt + 2 entries per slice (the last two equal), so clamping the code to rt yields an
-            // empty bucket for CODE_EMPTY without a branch.  Two 16-bit lengths share one register during the scan.
-            uint32_t beg[kLT_SC], lenp[kLT_SC / 2];
+            // empty bucket for CODE_EMPTY without a branch.  Items are written k-major (every lane's first match, then
+            // every lane's second match, ...) with ballot/popc ranks: within a round of 32 consecutive items the passages
+            // are distinct, so the acc accesses of phase B hit 32 different banks and lanes that share a code read the
+            // same entry (broadcast).
+            uint32_t beg[kLT_SC], len[kLT_SC], total[kLT_SC];
+            uint32_t over = 0;
 #pragma unroll
             for (int j = 0; j < kLT_SC; ++j) {
                 const uint32_t code = min(((j < 4 ? cw.x : cw.y) >> (8 * (j & 3))) & 0xFFu, (uint32_t)a.rt);
                 const uint16_t* o = off + j * offs_per_slice + code;
-                const uint32_t b = o[0], l = (uint32_t)o[1] - b;
-                beg[j] = b;
-                if (j & 1) lenp[j >> 1] |= l << 16; else lenp[j >> 1] = l;
-            }
-            uint32_t incp[kLT_SC / 2];
-#pragma unroll
-            for (int k = 0; k < kLT_SC / 2; ++k) incp[k] = lenp[k];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-#pragma unroll
-                for (int k = 0; k < kLT_SC / 2; ++k) {
-                    const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incp[k], d);
-                    incp[k] += (lane >= d) ? n : 0u;
-                }
-            }
-            uint32_t totp[kLT_SC / 2];
-            uint32_t over = 0;
-#pragma unroll
-            for (int k = 0; k < kLT_SC / 2; ++k) {
-                totp[k] = __shfl_sync(0xFFFFFFFFu, incp[k], 31);
-                over |= ((totp[k] & 0xFFFFu) > (uint32_t)kLT_Seg) | ((totp[k] >> 16) > (uint32_t)kLT_Seg);
+                beg[j] = o[0];
+                len[j] = (uint32_t)o[1] - beg[j];
+                total[j] = __reduce_add_sync(0xFFFFFFFFu, len[j]);
+                over |= total[j] > (uint32_t)kLT_Seg;
             }
             if (!over) {
+                const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
                 for (int j = 0; j < kLT_SC; ++j) {
-                    const uint32_t l = (j & 1) ? (lenp[j >> 1] >> 16) : (lenp[j >> 1] & 0xFFFFu);
-                    const uint32_t inc = (j & 1) ? (incp[j >> 1] >> 16) : (incp[j >> 1] & 0xFFFFu);
-                    uint16_t* seg = wq + j * kLT_Seg + (inc - l);
+                    uint16_t* seg = wq + j * kLT_Seg;
                     const uint32_t it = tag | beg[j];
+                    uint32_t base = 0;
 #pragma unroll
-                    for (uint32_t k = 0; k < 4; ++k) if (k < l) seg[k] = (uint16_t)(it + k);
-                    for (uint32_t k = 4; k < l; ++k) seg[k] = (uint16_t)(it + k);
+                    for (uint32_t k = 0; k < 3; ++k) {
+                        const bool has = len[j] > k;
+                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, has);
+                        if (has) seg[base + __popc(m & lt_mask)] = (uint16_t)(it + k);
+                        base += __popc(m);
+                    }
+                    for (uint32_t k = 3; base < total[j]; ++k) {               // rare: buckets longer than 3
+                        const bool has = len[j] > k;
+                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, has);
+                        if (has) seg[base + __popc(m & lt_mask)] = (uint16_t)(it + k);
+                        base += __popc(m);
+                    }
                 }
                 __syncwarp();
-                // totals fit in a byte each (<= kLT_Seg): pack the 8 of them for the compact phase-B loop
-                const uint32_t t_lo = (totp[0] & 0xFFu) | ((totp[0] >> 16) << 8) | ((totp[1] & 0xFFu) << 16) | ((totp[1] >> 16) << 24);
-                uint32_t t_hi = 0;
-                if constexpr (kLT_SC == 8)
-                    t_hi = (totp[kLT_SC / 2 - 2] & 0xFFu) | ((totp[kLT_SC / 2 - 2] >> 16) << 8) | ((totp[kLT_SC / 2 - 1] & 0xFFu) << 16) |
-                           ((totp[kLT_SC / 2 - 1] >> 16) << 24);
+                uint32_t t_lo = 0, t_hi = 0;                                    // totals (<= kLT_Seg) packed one byte each
+#pragma unroll
+                for (int j = 0; j < kLT_SC; ++j) {
+                    if (j < 4) t_lo |= total[j] << (8 * j); else t_hi |= total[j] << (8 * (j - 4));
+                }
                 // ---- phase B: consume the segments, one match per lane; slices are ordered by __syncwarp ----
 #pragma unroll 1
                 for (int j = 0; j < kLT_SC; ++j) {
