@@ -53,7 +53,7 @@ size_t lex_tile_smem_bytes(const LexTileGeom& t) {
     return (size_t)kLT_QT * kLT_PT * 4 + (size_t)kLT_Stages * t.stage_bytes + 128;
 }
 
-constexpr size_t kLT_StaticSmem = (size_t)(kLT_PT / 32) * kLT_SC * kLT_Seg * 2 + kLT_QT * 4 + 2048;
+constexpr size_t kLT_StaticSmem = kLT_QT * 4 + 2048;
 constexpr size_t kLT_SmemBudget = (size_t)(227 * 1024) / kLT_CtasPerSm - 1024;   // per CTA (1 KiB reserved per CTA by the driver)
 
 bool lex_tile_supported(const Geometry& g, int rt) {
@@ -195,7 +195,6 @@ __global__ void __launch_bounds__(kLT_Threads, kLT_CtasPerSm) lex_tile_kernel(co
     __shared__ __align__(8) uint64_t full_bar[kLT_Stages];
     __shared__ __align__(8) uint64_t empty_bar[kLT_Stages];
     __shared__ __align__(16) float tau_s[kLT_QT];
-    __shared__ uint16_t wq_all[(kLT_PT / 32) * kLT_SC * kLT_Seg];
 
     constexpr int EW = lt_entry_words(G);
     constexpr int PW = lt_pval_words(G);
@@ -241,8 +240,6 @@ __global__ void __launch_bounds__(kLT_Threads, kLT_CtasPerSm) lex_tile_kernel(co
     // ===== consumers: thread p owns passage p of the tile =====
     const int p = threadIdx.x;
     const int offs_per_slice = a.rt + 2;
-    uint16_t* wq = wq_all + warp * (kLT_SC * kLT_Seg);
-    const uint32_t tag = (uint32_t)lane << 10;
     int s = 0; uint32_t ph = 0;
     for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q) {
         const long long row = (tile0 + t) * kLT_PT + p;
@@ -276,96 +273,42 @@ __global__ void __launch_bounds__(kLT_Threads, kLT_CtasPerSm) lex_tile_kernel(co
             if constexpr (kLT_SC == 8) cw = *(const uint2*)(st + (size_t)p * kLT_SC);
             else { cw.x = *(const uint32_t*)(st + (size_t)p * kLT_SC); cw.y = 0; }
 
-            // ---- phase A: bucket lookups (branch-free) and match flattening into per-slice queue segments ----
+            // ---- bucket lookups (branch-free) ----
             // The offset table has rt + 2 entries per slice (the last two equal), so clamping the code to rt yields an
-            // empty bucket for CODE_EMPTY without a branch.  Items are written k-major (every lane's first match, then
-            // every lane's second match, ...) with ballot/popc ranks: within a round of 32 consecutive items the passages
-            // are distinct, so the acc accesses of phase B hit 32 different banks and lanes that share a code read the
-            // same entry (broadcast).
-            uint32_t beg[kLT_SC], len[kLT_SC], total[kLT_SC];
-            uint32_t over = 0;
+            // empty bucket for CODE_EMPTY without a branch.
+            uint32_t beg[kLT_SC], cum[kLT_SC + 1];
+            cum[0] = 0;
 #pragma unroll
             for (int j = 0; j < kLT_SC; ++j) {
                 const uint32_t code = min(((j < 4 ? cw.x : cw.y) >> (8 * (j & 3))) & 0xFFu, (uint32_t)a.rt);
                 const uint16_t* o = off + j * offs_per_slice + code;
-                beg[j] = o[0];
-                len[j] = (uint32_t)o[1] - beg[j];
-                total[j] = __reduce_add_sync(0xFFFFFFFFu, len[j]);
-                over |= total[j] > (uint32_t)kLT_Seg;
+                const uint32_t b = o[0];
+                cum[j + 1] = cum[j] + ((uint32_t)o[1] - b);
+                beg[j] = b - cum[j];                                   // entry of this thread's l-th match = beg[slice(l)] + l
             }
-            if (!over) {
-                const uint32_t lt_mask = (1u << lane) - 1u;
+            // ---- flattened match walk: level l = this thread's l-th match of the whole chunk (all slices) ----
+            // Every thread only touches its own acc column (bank = lane: conflict-free, no atomics, fixed order); walking
+            // the matches of all slices of the chunk as one list keeps lanes busier than a per-slice loop would.
+            const uint32_t mine = cum[kLT_SC];
+            const uint32_t levels = __reduce_max_sync(0xFFFFFFFFu, mine);
+            for (uint32_t l = 0; l < levels; ++l) {
+                if (l < mine) {
+                    int j = 0;
+                    uint32_t e = beg[0];
 #pragma unroll
-                for (int j = 0; j < kLT_SC; ++j) {
-                    uint16_t* seg = wq + j * kLT_Seg;
-                    const uint32_t it = tag | beg[j];
-                    uint32_t base = 0;
-#pragma unroll
-                    for (uint32_t k = 0; k < 3; ++k) {
-                        const bool has = len[j] > k;
-                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, has);
-                        if (has) seg[base + __popc(m & lt_mask)] = (uint16_t)(it + k);
-                        base += __popc(m);
+                    for (int t = 1; t < kLT_SC; ++t) {
+                        const bool ge = l >= cum[t];
+                        j += ge ? 1 : 0;
+                        e = ge ? beg[t] : e;
                     }
-                    for (uint32_t k = 3; base < total[j]; ++k) {               // rare: buckets longer than 3
-                        const bool has = len[j] > k;
-                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, has);
-                        if (has) seg[base + __popc(m & lt_mask)] = (uint16_t)(it + k);
-                        base += __popc(m);
-                    }
+                    uint32_t ew[EW], pv[PW];
+                    load_entry<G>(ent, e + l, ew);
+                    load_pvals<G>(pvals, j, p, pv);
+                    float* ap = acc + (ew[0] & 0xFFFFu) * kLT_PT + p;
+                    *ap = entry_dot<G, 0>(ew, pv, *ap);
                 }
-                __syncwarp();
-                uint32_t t_lo = 0, t_hi = 0;                                    // totals (<= kLT_Seg) packed one byte each
-#pragma unroll
-                for (int j = 0; j < kLT_SC; ++j) {
-                    if (j < 4) t_lo |= total[j] << (8 * j); else t_hi |= total[j] << (8 * (j - 4));
-                }
-                // ---- phase B: consume the segments, one match per lane; slices are ordered by __syncwarp ----
-#pragma unroll 1
-                for (int j = 0; j < kLT_SC; ++j) {
-                    const uint32_t tj = ((j < 4 ? t_lo : t_hi) >> (8 * (j & 3))) & 0xFFu;
-                    const uint16_t* seg = wq + j * kLT_Seg;
-                    // two independent matches per lane and iteration (items i and i + 32 never share a (query, passage) pair)
-                    for (uint32_t i = lane; i < tj; i += 64) {
-                        const bool two = i + 32 < tj;
-                        const uint32_t it0 = seg[i];
-                        const uint32_t it1 = two ? seg[i + 32] : it0;
-                        const int pp0 = (warp << 5) + (int)(it0 >> 10), pp1 = (warp << 5) + (int)(it1 >> 10);
-                        uint32_t ew0[EW], ew1[EW], pv0[PW], pv1[PW];
-                        load_entry<G>(ent, it0 & 0x3FFu, ew0);
-                        load_entry<G>(ent, it1 & 0x3FFu, ew1);
-                        load_pvals<G>(pvals, j, pp0, pv0);
-                        load_pvals<G>(pvals, j, pp1, pv1);
-                        float* ap0 = acc + (ew0[0] & 0xFFFFu) * kLT_PT + pp0;
-                        float* ap1 = acc + (ew1[0] & 0xFFFFu) * kLT_PT + pp1;
-                        const float a0 = *ap0, a1 = *ap1;
-                        const float r0 = entry_dot<G, 0>(ew0, pv0, a0);
-                        const float r1 = entry_dot<G, 0>(ew1, pv1, a1);
-                        *ap0 = r0;
-                        if (two) *ap1 = r1;
-                    }
-                    __syncwarp();
-                }
-            } else {
-                // a queue segment would overflow (degenerate code distribution): every lane walks its own buckets
-#pragma unroll 1
-                for (int j = 0; j < kLT_SC; ++j) {
-                    const uint32_t code = min(((j < 4 ? cw.x : cw.y) >> (8 * (j & 3))) & 0xFFu, (uint32_t)a.rt);
-                    const uint16_t* o = off + j * offs_per_slice + code;
-                    const uint32_t b = o[0], e1 = o[1];
-                    if (b < e1) {
-                        uint32_t pv[PW];
-                        load_pvals<G>(pvals, j, p, pv);
-                        for (uint32_t e = b; e < e1; ++e) {
-                            uint32_t ew[EW];
-                            load_entry<G>(ent, e, ew);
-                            float* ap = acc + (ew[0] & 0xFFFFu) * kLT_PT + p;
-                            *ap = entry_dot<G, 0>(ew, pv, *ap);
-                        }
-                    }
-                }
-                __syncwarp();
             }
+            __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
             if (++s == kLT_Stages) { s = 0; ph ^= 1u; }
         }
