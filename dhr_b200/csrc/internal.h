@@ -109,8 +109,8 @@ struct LexTileGeom {
     int G, code_bytes, n_chunks, rt;
     int pblock_bytes, qoff_bytes, qblock_stride, stage_bytes;
 };
-constexpr int kLexTileRows = 256;        // passages per K1t tile
-constexpr int kLexTileQueries = 64;      // queries per K1t tile (acc[64][256] fp32 = 64 KiB -> two CTAs per SM)
+constexpr int kLexTileRows = 512;        // passages per K1t tile (= consumer threads)
+constexpr int kLexTileQueries = 64;      // queries per K1t tile (acc[64][512] fp32 = 128 KiB, 16 consumer warps per SM)
 constexpr int kLexTileSlices = 4;        // slices per chunk
 LexTileGeom lex_tile_geom(const Geometry& g, int rt);
 bool lex_tile_supported(const Geometry& g, int rt);

@@ -28,10 +28,10 @@ namespace dhr {
 constexpr int kLT_PT = kLexTileRows;    // passages per tile = consumer threads
 constexpr int kLT_QT = kLexTileQueries; // queries per tile
 constexpr int kLT_SC = kLexTileSlices;  // slices per chunk
-constexpr int kLT_Stages = 2;
+constexpr int kLT_Stages = 3;
 constexpr int kLT_Threads = kLT_PT + 32;
 constexpr int kLT_Seg = 48;             // per-warp, per-slice match queue segment (items)
-constexpr int kLT_CtasPerSm = 2;
+constexpr int kLT_CtasPerSm = 1;
 static_assert(kLT_SC == 4 || kLT_SC == 8, "chunk of 4 or 8 slices");
 static_assert(kLT_SC * kLT_QT <= 1024, "queue items carry a 10-bit entry index");
 

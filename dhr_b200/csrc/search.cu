@@ -286,7 +286,7 @@ static int run_batch_dense_tile(dhr_index* h, const QuerySet& qs, int base, int 
 
 // hybrid / lexical index on the tile kernels: per sub-chunk of rows K2 writes the dense scores of the
 // in-flight queries to an L2-resident scratch, K1t adds the lexical part and filters.
-constexpr long long kTileSubRows = 37888;        // 148 K1t tiles of 256 rows (two per CTA with 2 query tiles in flight)
+constexpr long long kTileSubRows = 37888;        // 74 K1t tiles of 512 rows x 4 query tiles = 2 work items per CTA on 148 SMs
 
 static int ensure_tile_workspace(dhr_index* h, const LexTileGeom& t, int n_queries) {
     const size_t n_qtiles = (size_t)(n_queries + kLexTileQueries - 1) / kLexTileQueries + 2;
