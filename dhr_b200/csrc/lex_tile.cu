@@ -1,26 +1,29 @@
-// lex_tile.cu -- K1t: tiled lexical match-and-MAC for a tile of 128 queries, fused with the
-// admission filter.  Throughput-mode counterpart of the row scan K1 (scan_rows.cuh).
+// lex_tile.cu -- K1t: tiled lexical match-and-MAC for a tile of 64 queries x 512 passages, fused with
+// the admission filter.  Throughput-mode counterpart of the row scan K1 (scan_rows.cuh).
 //
-// Replaces, for 128 queries at once, the masked product + row dot of castorini/dhr
+// Replaces, for 64 queries at once, the masked product + row dot of castorini/dhr
 // retrieval/gip_retrieval.py:119-120 restricted to the lexical columns:
 //     lex[q][p] = sum_s [q_idx[s] == p_idx[s]] * sum_g q_val[s,g] * p_val[s,g]
 // without comparing every (query, passage, slice) triple: per query tile and slice the queries are
-// bucketed by their slice index (code) -- an offset table off[slice][code] over a packed entry list
-// {query id, G fp16 values} -- so a passage thread looks up the bucket of ITS code and touches only
-// the queries that really match.  Work is O(matches), not O(Q*N*S).
+// bucketed by their slice index (code) -- a table tab[slice][code] = {byte offset of the first entry,
+// entry count} over a packed entry list {acc byte offset of the query, G fp16 values} -- so a passage
+// thread looks up the bucket of ITS code and touches only the queries that really match.  Work is
+// O(matches), not O(Q*N*S).
 //
-// Per warp and 8-slice chunk: (A) every lane looks up, for each of the 8 slices, the bucket of ITS
-// passage's code; the 8 warp scans that flatten the (passage, entry) matches into per-slice queue
-// segments are independent and interleave; (B) each segment is consumed 32 matches at a time, one
-// per lane, so lanes stay busy however bucket lengths are distributed.
+// Data movement: one producer warp streams, per (passage tile, 4-slice chunk), the tiled corpus block
+// (codes u8 [512][4] | values [4][512][G]) and the query-tile block (table | entries) with TMA bulk
+// copies (cp.async.bulk + mbarrier ring) into shared memory; 512 consumer threads own one passage each
+// and keep acc[64 queries][512 passages] fp32 in shared memory (column p is private to thread p:
+// bank = lane, conflict-free, no atomics, fixed summation order).
 //
-// Data movement: one producer warp streams, per (passage tile, 8-slice chunk), the tiled corpus
-// block (codes u8 [256][8] | values [8][256][G]) and the query-tile block (offsets | entries) with
-// TMA bulk copies (cp.async.bulk + mbarrier ring) into shared memory; 256 consumer threads own one
-// passage each and keep acc[128 queries][256 passages] fp32 in shared memory (column p is private
-// to thread p: conflict-free, no atomics, deterministic summation order).  acc is initialised
-// from the dense scores written by K2 (hybrid index) or zero, and after the last chunk each thread
-// applies the strict threshold tau[q] and appends winners to the candidate lists.
+// Per thread and chunk: (A) four branch-free bucket lookups (one 32-bit table word each); (B) the
+// matches of all four slices are walked as one flattened list, level l = the thread's l-th match.
+// The walk is branch-free inside a level (predicated shared loads/stores) and software-pipelined: the
+// entry and passage-value loads of level l+1 are issued before the accumulate of level l, and the
+// G-term dot is split into two independent FMA chains, so a warp is bound by issue slots and the
+// shared-memory pipe rather than by the latency of one level's dependent chain.
+// acc is initialised from the dense scores written by K2 (hybrid index) or zero, and after the last
+// chunk each thread applies the strict threshold tau[q] and appends winners to the candidate lists.
 #include "internal.h"
 
 namespace dhr {
@@ -30,12 +33,12 @@ constexpr int kLT_QT = kLexTileQueries; // queries per tile
 constexpr int kLT_SC = kLexTileSlices;  // slices per chunk
 constexpr int kLT_Stages = 3;
 constexpr int kLT_Threads = kLT_PT + 32;
-constexpr int kLT_Seg = 48;             // per-warp, per-slice match queue segment (items)
 constexpr int kLT_CtasPerSm = 1;
-static_assert(kLT_SC == 4 || kLT_SC == 8, "chunk of 4 or 8 slices");
-static_assert(kLT_SC * kLT_QT <= 1024, "queue items carry a 10-bit entry index");
+static_assert(kLT_SC == 4, "the flattened walk selects among the 4 slices of a chunk");
 
-__host__ __device__ constexpr int lt_entry_words(int G) { return (G + 2) / 2; }          // {qid, v0..vG-1} as fp16 pairs
+// entry = {acc byte offset of the query (q * PT * 4), G fp16 values, zero pad}; sized so one entry is one or two
+// vector loads (8 / 16 / 16+8 bytes)
+__host__ __device__ constexpr int lt_entry_words(int G) { return G <= 2 ? 2 : (G <= 6 ? 4 : 6); }
 __host__ __device__ constexpr int lt_pval_words(int G) { return (G + 1) / 2; }
 
 
@@ -43,7 +46,7 @@ LexTileGeom lex_tile_geom(const Geometry& g, int rt) {
     LexTileGeom t{};
     t.G = g.G; t.code_bytes = g.code_bytes; t.n_chunks = g.S_pad / kLT_SC; t.rt = rt;
     t.pblock_bytes = kLT_PT * kLT_SC * (1 + 2 * g.G);        // tiled copy always stores 8-bit codes
-    t.qoff_bytes = (int)round_up((int64_t)kLT_SC * (rt + 2) * 2, 16);   // rt buckets + end marker + one duplicate (branch-free clamp)
+    t.qoff_bytes = (int)round_up((int64_t)kLT_SC * (rt + 1) * 4, 16);   // rt buckets + one empty bucket (clamp target) per slice
     t.qblock_stride = t.qoff_bytes + kLT_SC * kLT_QT * lt_entry_words(g.G) * 4;
     t.stage_bytes = (int)round_up(t.pblock_bytes, 128) + (int)round_up(t.qblock_stride, 128);
     return t;
@@ -61,35 +64,41 @@ bool lex_tile_supported(const Geometry& g, int rt) {
     return lex_tile_smem_bytes(lex_tile_geom(g, rt)) + kLT_StaticSmem <= kLT_SmemBudget;
 }
 
-// ---- query-tile preparation: one CTA per (chunk, query tile) builds offsets + entries ------------
+// ---- query-tile preparation: one CTA per (chunk, query tile) builds table + entries -------------
 // Entries of a bucket are ordered by query id, buckets by (slice, code).
 template <typename CodeT>
 __global__ void __launch_bounds__(256)
 lex_tile_prep_kernel(const __half* __restrict__ q_lex16, const CodeT* __restrict__ q_code, int n_queries, int S_pad, int G,
                      int rt, int qoff_bytes, int qblock_stride, uint8_t* __restrict__ qblocks, uint32_t* __restrict__ qblock_bytes) {
-    extern __shared__ uint32_t hist[];             // [SC][rt + 2] counts, then exclusive offsets (last two per slice stay empty)
+    extern __shared__ uint32_t prep_smem[];        // cnt[SC][rt + 1] | start[SC][rt + 1] (start doubles as the placement cursor)
+    __shared__ uint32_t total_s;
     const int chunk = blockIdx.x, qt = blockIdx.y;
     const int n_chunks = gridDim.x;
     const int q0 = qt * kLT_QT;
     const int nq = min(kLT_QT, n_queries - q0);
-    const int tbl = kLT_SC * (rt + 2);
-    for (int i = threadIdx.x; i < tbl; i += blockDim.x) hist[i] = 0;
+    const int per = rt + 1;
+    const int tbl = kLT_SC * per;
+    uint32_t* cnt = prep_smem;
+    uint32_t* start = prep_smem + tbl;
+    const int EW = lt_entry_words(G);
+    for (int i = threadIdx.x; i < tbl; i += blockDim.x) cnt[i] = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < nq * kLT_SC; i += blockDim.x) {
         const int q = i / kLT_SC, j = i % kLT_SC;
         const uint32_t code = q_code[(size_t)(q0 + q) * S_pad + chunk * kLT_SC + j];
-        if (code < (uint32_t)rt) atomicAdd(&hist[j * (rt + 2) + code], 1u);
+        if (code < (uint32_t)rt) atomicAdd(&cnt[j * per + code], 1u);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {                        // exclusive scan over (slice, code); bucket rt of every slice = end marker
+    if (threadIdx.x == 0) {                        // exclusive scan over (slice, code); bucket rt of every slice stays empty
         uint32_t run = 0;
-        for (int i = 0; i < tbl; ++i) { const uint32_t c = hist[i]; hist[i] = run; run += c; }
+        for (int i = 0; i < tbl; ++i) { start[i] = run; run += cnt[i]; }
+        total_s = run;
     }
     __syncthreads();
     uint8_t* blk = qblocks + ((size_t)qt * n_chunks + chunk) * qblock_stride;
-    uint16_t* off = (uint16_t*)blk;
-    for (int i = threadIdx.x; i < tbl; i += blockDim.x) off[i] = (uint16_t)hist[i];
-    const int EW = lt_entry_words(G);
+    uint32_t* tab = (uint32_t*)blk;
+    for (int i = threadIdx.x; i < tbl; i += blockDim.x) tab[i] = (start[i] * (uint32_t)EW * 4u) | (cnt[i] << 16);
+    __syncthreads();
     uint32_t* ent = (uint32_t*)(blk + qoff_bytes);
     if (threadIdx.x < kLT_SC) {                    // placement, sequential in q so that buckets are ordered by query id
         const int j = threadIdx.x;
@@ -97,25 +106,20 @@ lex_tile_prep_kernel(const __half* __restrict__ q_lex16, const CodeT* __restrict
         for (int q = 0; q < nq; ++q) {
             const uint32_t code = q_code[(size_t)(q0 + q) * S_pad + s];
             if (code >= (uint32_t)rt) continue;
-            const uint32_t pos = hist[j * (rt + 2) + code]++;
+            const uint32_t pos = start[j * per + code]++;
             const __half* v = q_lex16 + ((size_t)(q0 + q) * S_pad + s) * G;
             uint32_t* e = ent + (size_t)pos * EW;
-            uint32_t w = (uint32_t)q;
-            for (int g = 0; g < G; ++g) {          // half index g + 1 of the entry
-                const uint32_t hv = __half_as_ushort(v[g]);
-                if ((g + 1) & 1) { w |= hv << 16; e[(g + 1) >> 1] = w; w = 0; }
-                else w = hv;
+            e[0] = (uint32_t)q * (uint32_t)(kLT_PT * 4);
+            for (int w = 1; w < EW; ++w) {         // value g sits in half 2 + g of the entry
+                const int g0 = 2 * (w - 1), g1 = g0 + 1;
+                const uint32_t lo = g0 < G ? __half_as_ushort(v[g0]) : 0u;
+                const uint32_t hi = g1 < G ? __half_as_ushort(v[g1]) : 0u;
+                e[w] = lo | (hi << 16);
             }
-            if (((G + 1) & 1) == 0) { /* last half landed in a high slot: already stored */ }
-            else e[(G + 1) >> 1] = w;              // trailing low half (+ zero pad)
         }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        // total entries = offset of the end marker of the last slice after placement == final hist value there
-        const uint32_t total = hist[(kLT_SC - 1) * (rt + 2) + rt + 1];
-        qblock_bytes[(size_t)qt * n_chunks + chunk] = ((uint32_t)qoff_bytes + total * (uint32_t)EW * 4u + 15u) & ~15u;
-    }
+    if (threadIdx.x == 0)
+        qblock_bytes[(size_t)qt * n_chunks + chunk] = ((uint32_t)qoff_bytes + total_s * (uint32_t)EW * 4u + 15u) & ~15u;
 }
 
 // f32 += f16 * f16 with independent half selection of both operands
@@ -133,11 +137,13 @@ __device__ __forceinline__ float fma_h_sel(uint32_t a, uint32_t b, float c) {
     return d;
 }
 
+// sum over g = g0, g0 + 2, ... < G of entry value g (half 2 + g of the entry) * passage value g: one of the two
+// independent FMA chains of a match (even and odd g)
 template <int G, int g>
-__device__ __forceinline__ float entry_dot(const uint32_t* e, const uint32_t* pv, float t) {
+__device__ __forceinline__ float entry_chain(const uint32_t* e, const uint32_t* pv, float t) {
     if constexpr (g < G) {
-        t = fma_h_sel<((g + 1) & 1) != 0, (g & 1) != 0>(e[(g + 1) >> 1], pv[g >> 1], t);
-        return entry_dot<G, g + 1>(e, pv, t);
+        t = fma_h_sel<(g & 1) != 0, (g & 1) != 0>(e[1 + (g >> 1)], pv[g >> 1], t);
+        return entry_chain<G, g + 2>(e, pv, t);
     } else {
         return t;
     }
@@ -147,7 +153,7 @@ struct LexTileArgs {
     const uint8_t* lext;               // tiled corpus blocks [tile][chunk]
     const uint8_t* qblocks;            // query blocks [qtile][chunk] (stride qblock_stride)
     const uint32_t* qblock_bytes;      // bytes to copy per query block
-    long long row_begin, row_end;      // rows handled by this launch (row_begin multiple of 256)
+    long long row_begin, row_end;      // rows handled by this launch (row_begin multiple of the tile size)
     long long n_rows;
     int n_tiles;                       // tiles in [row_begin, row_end)
     int n_chunks, rt;
@@ -159,35 +165,65 @@ struct LexTileArgs {
     float* tau; uint32_t* cnt; float* cand_score; int32_t* cand_row; int cap;
 };
 
+// ---- predicated shared-memory access (no branches inside a match level) ---------------------------
+// The loads of read-only stage data are plain (non-volatile) asm so the compiler may schedule them freely -- their
+// addresses depend on data read after the stage's mbarrier wait, which orders them; the accumulator read-modify-write
+// is volatile asm and keeps its program order.
+template <int EW>
+__device__ __forceinline__ void lds_entry(uint32_t addr, uint32_t act, uint32_t (&ew)[EW]) {
+    static_assert(EW == 2 || EW == 4 || EW == 6, "entry words");
+    if constexpr (EW == 2)
+        asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q ld.shared.v2.u32 {%0, %1}, [%2];\n\t}"
+            : "=r"(ew[0]), "=r"(ew[1]) : "r"(addr), "r"(act));
+    else if constexpr (EW == 4)
+        asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+            : "=r"(ew[0]), "=r"(ew[1]), "=r"(ew[2]), "=r"(ew[3]) : "r"(addr), "r"(act));
+    else
+        asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %7, 0;\n\t@q ld.shared.v2.u32 {%0, %1}, [%6];\n\t@q ld.shared.v4.u32 {%2, %3, %4, %5}, [%6+8];\n\t}"
+            : "=r"(ew[0]), "=r"(ew[1]), "=r"(ew[2]), "=r"(ew[3]), "=r"(ew[4]), "=r"(ew[5]) : "r"(addr), "r"(act));
+}
+__device__ __forceinline__ uint32_t lds_u32_pred(uint32_t addr, uint32_t act) {
+    uint32_t v;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.shared.u32 %0, [%1];\n\t}" : "=r"(v) : "r"(addr), "r"(act));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16_pred(uint32_t addr, uint32_t act) {
+    uint32_t v;
+    asm("{\n\t.reg .pred q;\n\t.reg .b16 h;\n\tsetp.ne.u32 q, %2, 0;\n\tmov.b16 h, 0;\n\t@q ld.shared.u16 h, [%1];\n\tcvt.u32.u16 %0, h;\n\t}"
+        : "=r"(v) : "r"(addr), "r"(act));
+    return v;
+}
+// passage values of one (slice, passage): G fp16 at `addr` (4-byte aligned when G is even, 2-byte otherwise)
 template <int G>
-__device__ __forceinline__ void load_pvals(const uint32_t* pvals, int j, int pp, uint32_t (&pv)[lt_pval_words(G)]) {
+__device__ __forceinline__ void lds_pvals(uint32_t addr, uint32_t act, uint32_t (&pv)[lt_pval_words(G)]) {
     constexpr int PW = lt_pval_words(G);
     if constexpr (G % 2 == 0) {
-        const uint32_t* src = pvals + ((size_t)j * kLT_PT + pp) * (G / 2);
 #pragma unroll
-        for (int w = 0; w < PW; ++w) pv[w] = src[w];
-    } else {   // odd G: a passage's G halves straddle word boundaries
-        const uint16_t* h16 = (const uint16_t*)pvals + ((size_t)j * kLT_PT + pp) * G;
+        for (int w = 0; w < PW; ++w) pv[w] = lds_u32_pred(addr + 4 * w, act);
+    } else {
 #pragma unroll
         for (int w = 0; w < PW; ++w) {
-            const uint32_t lo = h16[2 * w];
-            const uint32_t hi = (2 * w + 1 < G) ? h16[2 * w + 1] : 0u;
+            const uint32_t lo = lds_u16_pred(addr + 4 * w, act);
+            const uint32_t hi = (2 * w + 1 < G) ? lds_u16_pred(addr + 4 * w + 2, act) : 0u;
             pv[w] = lo | (hi << 16);
         }
     }
 }
+__device__ __forceinline__ float lds_acc_pred(uint32_t addr, uint32_t act) {
+    float v;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.shared.f32 %0, [%1];\n\t}" : "=f"(v) : "r"(addr), "r"(act) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_acc_pred(uint32_t addr, float v, uint32_t act) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.f32 [%0], %1;\n\t}" :: "r"(addr), "f"(v), "r"(act) : "memory");
+}
 
 template <int G>
-__device__ __forceinline__ void load_entry(const uint32_t* ent, uint32_t e, uint32_t (&ew)[lt_entry_words(G)]) {
-    constexpr int EW = lt_entry_words(G);
-    const uint32_t* ep = ent + (size_t)e * EW;
-    if constexpr (EW == 4) { const uint4 v = *(const uint4*)ep; ew[0] = v.x; ew[1] = v.y; ew[2] = v.z; ew[3] = v.w; }
-    else if constexpr (EW == 2) { const uint2 v = *(const uint2*)ep; ew[0] = v.x; ew[1] = v.y; }
-    else {
-#pragma unroll
-        for (int w = 0; w < EW; ++w) ew[w] = ep[w];
-    }
-}
+struct LexLevel {                       // operands of one match level of one thread
+    uint32_t ew[lt_entry_words(G)];
+    uint32_t pv[lt_pval_words(G)];
+    uint32_t act;
+};
 
 template <int G>
 __global__ void __launch_bounds__(kLT_Threads, kLT_CtasPerSm) lex_tile_kernel(const __grid_constant__ LexTileArgs a) {
@@ -197,7 +233,7 @@ __global__ void __launch_bounds__(kLT_Threads, kLT_CtasPerSm) lex_tile_kernel(co
     __shared__ __align__(16) float tau_s[kLT_QT];
 
     constexpr int EW = lt_entry_words(G);
-    constexpr int PW = lt_pval_words(G);
+    constexpr uint32_t ES = EW * 4;                                        // entry bytes
     float* acc = (float*)smem;                                            // [QT][PT]
     uint8_t* stages = smem + (size_t)kLT_QT * kLT_PT * 4;
 
@@ -239,12 +275,14 @@ __global__ void __launch_bounds__(kLT_Threads, kLT_CtasPerSm) lex_tile_kernel(co
 
     // ===== consumers: thread p owns passage p of the tile =====
     const int p = threadIdx.x;
-    const int offs_per_slice = a.rt + 2;
+    const uint32_t per = (uint32_t)a.rt + 1u;
+    const uint32_t acc_p = smem_u32(acc) + (uint32_t)p * 4u;               // shared address of acc[0][p]
+    const uint32_t stages_s = smem_u32(stages);
     int s = 0; uint32_t ph = 0;
     for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q) {
         const long long row = (tile0 + t) * kLT_PT + p;
         const bool row_ok = row >= a.row_begin && row < a.row_end && row < a.n_rows;
-        // acc init: dense scores of (row, q0..q0+127) written by K2 (512 contiguous bytes per row) or zero;
+        // acc init: dense scores of (row, q0..q0+63) written by K2 (256 contiguous bytes per row) or zero;
         // 8 x 128-bit loads are in flight at a time.  Slots beyond nq hold zeros (TMA zero-fills missing queries).
         if (a.scratch && row_ok) {
             const float4* src = (const float4*)(a.scratch + (size_t)(row - a.scratch_row0) * a.scratch_slots + q0);
@@ -266,47 +304,54 @@ __global__ void __launch_bounds__(kLT_Threads, kLT_CtasPerSm) lex_tile_kernel(co
         for (int c = 0; c < a.n_chunks; ++c) {
             mbar_wait(&full_bar[s], ph);
             const uint8_t* st = stages + (size_t)s * a.stage_bytes;
-            const uint32_t* pvals = (const uint32_t*)(st + (size_t)kLT_PT * kLT_SC);
-            const uint16_t* off = (const uint16_t*)(st + a.pblock_smem);
-            const uint32_t* ent = (const uint32_t*)(st + a.pblock_smem + a.qoff_bytes);
-            uint2 cw;                                                             // my slice codes (one byte each)
-            if constexpr (kLT_SC == 8) cw = *(const uint2*)(st + (size_t)p * kLT_SC);
-            else { cw.x = *(const uint32_t*)(st + (size_t)p * kLT_SC); cw.y = 0; }
+            const uint32_t st_s = stages_s + (uint32_t)s * (uint32_t)a.stage_bytes;
+            const uint32_t* tab = (const uint32_t*)(st + a.pblock_smem);
+            const uint32_t cw = *(const uint32_t*)(st + (size_t)p * kLT_SC);       // my four slice codes (one byte each)
 
             // ---- bucket lookups (branch-free) ----
-            // The offset table has rt + 2 entries per slice (the last two equal), so clamping the code to rt yields an
-            // empty bucket for CODE_EMPTY without a branch.
-            uint32_t beg[kLT_SC], cum[kLT_SC + 1];
+            // The table has rt + 1 words per slice (the last one an empty bucket), so clamping the code to rt
+            // resolves CODE_EMPTY without a branch.  ea[j] / pa[j] are the shared addresses a match of slice j reads:
+            // entry of this thread's l-th match = ea[slice(l)] + l * ES.
+            uint32_t ea[kLT_SC], pa[kLT_SC], cum[kLT_SC + 1];
+            const uint32_t ent_s = st_s + (uint32_t)a.pblock_smem + (uint32_t)a.qoff_bytes;
+            const uint32_t pv_s = st_s + (uint32_t)(kLT_PT * kLT_SC) + (uint32_t)p * (uint32_t)(G * 2);
             cum[0] = 0;
 #pragma unroll
             for (int j = 0; j < kLT_SC; ++j) {
-                const uint32_t code = min(((j < 4 ? cw.x : cw.y) >> (8 * (j & 3))) & 0xFFu, (uint32_t)a.rt);
-                const uint16_t* o = off + j * offs_per_slice + code;
-                const uint32_t b = o[0];
-                cum[j + 1] = cum[j] + ((uint32_t)o[1] - b);
-                beg[j] = b - cum[j];                                   // entry of this thread's l-th match = beg[slice(l)] + l
+                const uint32_t code = min((cw >> (8 * j)) & 0xFFu, (uint32_t)a.rt);
+                const uint32_t w = tab[j * per + code];
+                ea[j] = ent_s + (w & 0xFFFFu) - cum[j] * ES;
+                pa[j] = pv_s + (uint32_t)(j * kLT_PT * G * 2);
+                cum[j + 1] = cum[j] + (w >> 16);
             }
-            // ---- flattened match walk: level l = this thread's l-th match of the whole chunk (all slices) ----
-            // Every thread only touches its own acc column (bank = lane: conflict-free, no atomics, fixed order); walking
-            // the matches of all slices of the chunk as one list keeps lanes busier than a per-slice loop would.
             const uint32_t mine = cum[kLT_SC];
             const uint32_t levels = __reduce_max_sync(0xFFFFFFFFu, mine);
-            for (uint32_t l = 0; l < levels; ++l) {
-                if (l < mine) {
-                    int j = 0;
-                    uint32_t e = beg[0];
-#pragma unroll
-                    for (int t = 1; t < kLT_SC; ++t) {
-                        const bool ge = l >= cum[t];
-                        j += ge ? 1 : 0;
-                        e = ge ? beg[t] : e;
-                    }
-                    uint32_t ew[EW], pv[PW];
-                    load_entry<G>(ent, e + l, ew);
-                    load_pvals<G>(pvals, j, p, pv);
-                    float* ap = acc + (ew[0] & 0xFFFFu) * kLT_PT + p;
-                    *ap = entry_dot<G, 0>(ew, pv, *ap);
-                }
+
+            // ---- flattened, software-pipelined match walk ----
+            auto fetch = [&](uint32_t l, LexLevel<G>& o) {
+                const bool g1 = l >= cum[1], g2 = l >= cum[2], g3 = l >= cum[3];
+                const uint32_t e = g3 ? ea[3] : (g2 ? ea[2] : (g1 ? ea[1] : ea[0]));
+                const uint32_t v = g3 ? pa[3] : (g2 ? pa[2] : (g1 ? pa[1] : pa[0]));
+                o.act = l < mine ? 1u : 0u;
+                lds_entry<EW>(e + l * ES, o.act, o.ew);
+                lds_pvals<G>(v, o.act, o.pv);
+            };
+            auto apply = [&](const LexLevel<G>& o) {
+                const uint32_t addr = acc_p + o.ew[0];
+                const float cur = lds_acc_pred(addr, o.act);
+                const float te = entry_chain<G, 0>(o.ew, o.pv, 0.f);
+                const float to = entry_chain<G, 1>(o.ew, o.pv, 0.f);
+                sts_acc_pred(addr, cur + (te + to), o.act);
+            };
+            LexLevel<G> x, y;
+            fetch(0, x);
+#pragma unroll 1
+            for (uint32_t l = 0; l < levels; l += 2) {
+                fetch(l + 1, y);
+                apply(x);
+                if (l + 1 >= levels) break;
+                fetch(l + 2, x);
+                apply(y);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
@@ -345,7 +390,7 @@ int launch_lex_tile_prep(const dhr_index* h, const LexTileGeom& t, const void* q
     const int n_qtiles = (n_queries + kLT_QT - 1) / kLT_QT;
     if (n_qtiles == 0) return DHR_OK;
     dim3 grid((unsigned)t.n_chunks, (unsigned)n_qtiles);
-    const size_t smem = (size_t)kLT_SC * (t.rt + 2) * sizeof(uint32_t);
+    const size_t smem = (size_t)2 * kLT_SC * (t.rt + 1) * sizeof(uint32_t);
     if (g.code_bytes == 1)
         lex_tile_prep_kernel<uint8_t><<<grid, 256, smem, st>>>((const __half*)q_lex16, (const uint8_t*)q_code, n_queries, g.S_pad, g.G,
                                                                t.rt, t.qoff_bytes, t.qblock_stride, qblocks, qblock_bytes);
