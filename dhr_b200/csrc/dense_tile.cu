@@ -9,11 +9,30 @@
 //   - apply the strict admission threshold and append candidates (dense-only index), or
 //   - write the tile to the L2-resident scratch consumed by the lexical kernel K1t (hybrid index).
 // Warp roles: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..5 epilogue.
+//
+// Two variants.  `dense_tile_kernel` (SS: both operands in shared memory, passages = M) measured 82 cycles per
+// M128 x N64 x K16 instruction -- the 4 KiB A-operand read from shared memory per instruction is amortised over only
+// 64 columns.  `dense_tile_ts_kernel` (TS: A operand in TMEM) swaps the roles: the 128 in-flight queries of a CTA are
+// the M dimension and live in tensor memory for the whole launch (row = TMEM lane, fp16 pairs along columns, written
+// once with tcgen05.st), the corpus is the N dimension streamed as 128-passage x 64-column 16 KiB stages through a
+// TMA ring, so an instruction reads only its 4 KiB B slice from shared memory and every corpus byte is reused by twice
+// as many queries.  TS needs C_pad <= 768 (384 TMEM columns of A + 128 accumulator columns = 512).
 #include <cuda.h>
 
 #include "internal.h"
 
 namespace dhr {
+
+// Timeline hooks of the micro-benchmark harness (tools/k2_micro.cu defines DHR_K2_TRACE); compiled out of the library.
+#ifdef DHR_K2_TRACE
+__device__ long long g_k2_trace[8][64];
+__device__ int g_k2_dbg;       // experiment bits (TS kernel): 4 = no epilogue stores, 8 = free-running MMA (no corpus loads, no stage barriers)
+#define K2_TRACE(role, idx) do { if (blockIdx.x == 0 && (idx) < 64) g_k2_trace[role][idx] = clock64(); } while (0)
+#define K2_DBG() g_k2_dbg
+#else
+#define K2_TRACE(role, idx) do { } while (0)
+#define K2_DBG() 0
+#endif
 
 constexpr int kDT_M = 128;             // passages per tile (UMMA M)
 constexpr int kDT_N = 64;              // queries per tile (UMMA N)
@@ -56,6 +75,13 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
+}
+// one lane of a converged warp; the surrounding code stays warp-uniform so tcgen05 / TMA operands live in uniform registers
+// (a divergent `if (lane == 0)` issuer makes ptxas wrap every UTCHMMA in an R2UR waterfall loop: ~140 cycles per instruction)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xFFFFFFFF;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -126,50 +152,57 @@ dense_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const uint32_t tmem_base = tmem_base_smem;
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
+        // ===== TMA producer (whole warp, one elected lane issues) =====
+        if (elect_one()) {
             mbar_arrive_expect_tx(&b_bar, (uint32_t)a.n_kblocks * kDT_BBytes);
             for (int kb = 0; kb < a.n_kblocks; ++kb)
                 tma_load_2d(smem_b + (size_t)kb * kDT_BBytes, &tmap_b, &b_bar, kb * kDT_KB, qt * kDT_N);
-            int s = 0; uint32_t ph = 0;
-            for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q) {
-                const int row0 = (int)(a.tile_row0 + (long long)t * kDT_M);
-                for (int kb = 0; kb < a.n_kblocks; ++kb) {
-                    mbar_wait(&empty_bar[s], ph ^ 1u);
+        }
+        __syncwarp();
+        int s = 0; uint32_t ph = 0;
+        for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q) {
+            const int row0 = (int)(a.tile_row0 + (long long)t * kDT_M);
+            for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&full_bar[s], kDT_ABytes);
                     tma_load_2d(smem_a + (size_t)s * kDT_ABytes, &tmap_a, &full_bar[s], kb * kDT_KB, row0);
-                    if (++s == a.n_stages) { s = 0; ph ^= 1u; }
                 }
+                __syncwarp();
+                if (++s == a.n_stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(kDT_M, kDT_N);
-            mbar_wait(&b_bar, 0);
+        // ===== MMA issuer (whole warp in uniform control flow, one elected lane issues) =====
+        constexpr uint32_t idesc = umma_idesc_f16(kDT_M, kDT_N);
+        const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);
+        mbar_wait(&b_bar, 0);
+        tc_fence_after();
+        int s = 0; uint32_t ph = 0;
+        int i = 0;
+        for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q, ++i) {
+            const int buf = i & 1;
+            mbar_wait(&tempty_bar[buf], (((uint32_t)i >> 1) & 1u) ^ 1u);
             tc_fence_after();
-            int s = 0; uint32_t ph = 0;
-            int i = 0;
-            for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q, ++i) {
-                const int buf = i & 1;
-                mbar_wait(&tempty_bar[buf], (((uint32_t)i >> 1) & 1u) ^ 1u);
+            const uint32_t d_tmem = tmem_u + (uint32_t)buf * kDT_N;
+            for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)buf * kDT_N;
-                for (int kb = 0; kb < a.n_kblocks; ++kb) {
-                    mbar_wait(&full_bar[s], ph);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem_a + (size_t)s * kDT_ABytes);
-                    const uint32_t b_addr = smem_u32(smem_b + (size_t)kb * kDT_BBytes);
+                const uint32_t a_addr = smem_u32(smem_a + (size_t)s * kDT_ABytes);
+                const uint32_t b_addr = smem_u32(smem_b + (size_t)kb * kDT_BBytes);
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < kDT_KB / 16; ++k) {
                         umma_f16(d_tmem, umma_smem_desc(a_addr + k * 32), umma_smem_desc(b_addr + k * 32), idesc,
                                  (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[s]);          // frees the A stage once these MMAs have read it
-                    if (++s == a.n_stages) { s = 0; ph ^= 1u; }
                 }
-                umma_commit(&tfull_bar[buf]);            // accumulator tile complete
+                __syncwarp();
+                if (++s == a.n_stages) { s = 0; ph ^= 1u; }
             }
+            if (elect_one()) umma_commit(&tfull_bar[buf]);   // accumulator tile complete
+            __syncwarp();
         }
     } else {
         // ===== epilogue warps: TMEM lane quarter = warp % 4 =====
@@ -223,6 +256,222 @@ dense_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (warp == 1) tmem_dealloc(tmem_base, 2 * kDT_N);
 }
 
+
+// ---- TS variant: queries in TMEM (M = 128), corpus streamed as the N operand -----------------------------
+constexpr int kTS_M = 128;             // queries per CTA (UMMA M, one TMEM lane each)
+constexpr int kTS_N = 128;             // passages per tile (UMMA N)
+constexpr int kTS_BBytes = kTS_N * kDT_KB * 2;   // 16 KiB per corpus stage
+constexpr int kTS_MaxStages = 12;
+constexpr int kTS_MaxACols = 384;      // TMEM columns holding the query operand (C_pad <= 768)
+constexpr int kTS_Threads = 192;
+
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// thread i of the warp writes its 32 registers to lane (base_lane + i), 32 consecutive columns
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+           "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+           "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+struct DenseTsArgs {
+    long long row_begin, row_end;      // rows of this launch
+    long long tile_row0;               // first row of tile 0 (row_begin rounded down to a 64-row tile from the launch base)
+    long long scratch_row0;            // row of scratch line 0
+    int n_tiles;                       // 64-row tiles in the launch
+    int n_kblocks;                     // ceil(C_pad / 64)
+    int n_stages;
+    int n_qgroups;                     // 128-query groups in flight
+    int n_queries;                     // valid queries in flight (slots)
+    int mode;                          // 0 = filter + append, 1 = write scratch
+    float* scratch;                    // [row - scratch_row0][scratch_slots]  (mode 1)
+    long long scratch_slots;
+    float* tau; uint32_t* cnt; float* cand_score; int32_t* cand_row; int cap;
+};
+
+__global__ void __launch_bounds__(kTS_Threads, 1)
+dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_q, const DenseTsArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[kTS_MaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kTS_MaxStages];
+    __shared__ __align__(8) uint64_t tfull_bar[2];
+    __shared__ __align__(8) uint64_t tempty_bar[2];
+    __shared__ __align__(8) uint64_t q_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) K2_TRACE(0, 0);
+    const int qg = blockIdx.x % a.n_qgroups;
+    const int cta_in_q = blockIdx.x / a.n_qgroups;
+    const int ctas_per_q = gridDim.x / a.n_qgroups;
+    const uint32_t a_cols = (uint32_t)a.n_kblocks * 32u;             // TMEM columns of the query operand
+    uint8_t* ring = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);   // SWIZZLE_128B tiles sit on 1 KiB boundaries
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }   // only [0] is used (one accumulator)
+        mbar_init(&q_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    if (threadIdx.x == 0) K2_TRACE(0, 1);
+
+    // ---- query operand -> TMEM ----
+    // The 128 x C_pad fp16 query block is TMA-loaded into the (still idle) corpus ring as n_kblocks 128B-swizzled
+    // [128 queries][64 columns] tiles of 16 KiB; epilogue thread (quarter, lane) owns query qg * 128 + quarter * 32 + lane,
+    // reads its 128-byte row of every tile (chunk c of row r sits at chunk c ^ (r & 7): conflict-free) and writes it to
+    // its TMEM lane with tcgen05.st.  Queries beyond n_queries and columns beyond C_pad are zero-filled by TMA.
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_arrive_expect_tx(&q_bar, (uint32_t)a.n_kblocks * (uint32_t)(kTS_M * kDT_KB * 2));
+            for (int kb = 0; kb < a.n_kblocks; ++kb)
+                tma_load_2d(ring + (size_t)kb * (kTS_M * kDT_KB * 2), &tmap_q, &q_bar, kb * kDT_KB, qg * kTS_M);
+        }
+        __syncwarp();
+    } else if (warp >= 2) {
+        const int quarter = warp & 3;
+        const int qi = quarter * 32 + lane;
+        mbar_wait(&q_bar, 0);
+        for (int kb = 0; kb < a.n_kblocks; ++kb) {
+            const uint8_t* row = ring + (size_t)kb * (kTS_M * kDT_KB * 2) + (size_t)qi * 128;
+            uint32_t r[32];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                const uint4 x = *(const uint4*)(row + ((v ^ (qi & 7)) << 4));
+                r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+            }
+            tmem_st_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)kb * 32u, r);
+        }
+        tmem_st_wait();
+    }
+    // generic-proxy reads of the ring are complete before the async proxy (TMA) overwrites it with corpus tiles
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x == 0) K2_TRACE(0, 2);
+
+    if (warp == 0) {
+        // ===== TMA producer: corpus tiles (whole warp, one elected lane issues) =====
+        int s = 0; uint32_t ph = 0; int i = 0;
+        for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q, ++i) {
+            if (lane == 0) K2_TRACE(1, i);
+            const int row0 = (int)(a.tile_row0 + (long long)t * kTS_N);
+            for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                if (K2_DBG() & 8) continue;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&full_bar[s], kTS_BBytes);
+                    tma_load_2d(ring + (size_t)s * kTS_BBytes, &tmap_c, &full_bar[s], kb * kDT_KB, row0);
+                }
+                __syncwarp();
+                if (++s == a.n_stages) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (whole warp in uniform control flow, one elected lane issues) =====
+        // One accumulator D[128 queries x 128 passages] (the query operand leaves 128 TMEM columns): an M128 x N128 x K16
+        // instruction costs about the same ~90 cycles as an N64 one (measured per-instruction floor), so the wide tile
+        // halves the tensor time per (query, passage) pair; the price is a short bubble while the epilogue drains D.
+        constexpr uint32_t idesc = umma_idesc_f16(kTS_M, kTS_N);
+        const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);
+        const uint32_t d_tmem = tmem_u + a_cols;
+        int s = 0; uint32_t ph = 0;
+        int i = 0;
+        for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q, ++i) {
+            if (lane == 0) K2_TRACE(2, i);
+            mbar_wait(&tempty_bar[0], ((uint32_t)i & 1u) ^ 1u);
+            tc_fence_after();
+            if (lane == 0) K2_TRACE(3, i);
+            for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                if (!(K2_DBG() & 8)) mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t b_addr = smem_u32(ring + (size_t)s * kTS_BBytes);
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < kDT_KB / 16; ++k)
+                        umma_f16_ts(d_tmem, tmem_u + (uint32_t)kb * 32u + (uint32_t)k * 8u, umma_smem_desc(b_addr + k * 32), idesc,
+                                    (kb | k) != 0 ? 1u : 0u);
+                    if (!(K2_DBG() & 8)) umma_commit(&empty_bar[s]);      // frees the corpus stage once these MMAs have read it
+                }
+                __syncwarp();
+                if (++s == a.n_stages) { s = 0; ph ^= 1u; }
+            }
+            if (elect_one()) umma_commit(&tfull_bar[0]);                  // accumulator tile complete
+            __syncwarp();
+            if (lane == 0) K2_TRACE(4, i);
+        }
+    } else {
+        // ===== epilogue warps: TMEM lane quarter = warp % 4; thread = one query, registers = 128 passages =====
+        const int quarter = warp & 3;
+        const int qi = quarter * 32 + lane;
+        const int slot = qg * kTS_M + qi;
+        const bool q_ok = slot < a.n_queries;
+        const float tau_q = (q_ok && a.mode == 0) ? a.tau[slot] : INFINITY;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a_cols;
+        int i = 0;
+        for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q, ++i) {
+            mbar_wait(&tfull_bar[0], (uint32_t)i & 1u);
+            tc_fence_after();
+            if (threadIdx.x == 64) K2_TRACE(5, i);
+            uint32_t v[kTS_N / 32][32];
+#pragma unroll
+            for (int j = 0; j < kTS_N / 32; ++j) tmem_ld_32x32(taddr + 32u * j, v[j]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[0]);                  // D is free again: the next tile's MMAs may start
+            if (threadIdx.x == 64) K2_TRACE(6, i);
+            const long long row0 = a.tile_row0 + (long long)t * kTS_N;
+            if (K2_DBG() & 4) {
+            } else if (a.mode == 1) {
+                // scratch[row][slot]: for a fixed passage the 32 lanes of a warp write 32 consecutive slots (one 128-byte line)
+                if ((long long)slot < a.scratch_slots) {
+                    float* dst = a.scratch + (size_t)(row0 - a.scratch_row0) * a.scratch_slots + slot;
+#pragma unroll
+                    for (int c = 0; c < kTS_N; ++c) {
+                        const long long row = row0 + c;
+                        if (row >= a.row_begin && row < a.row_end)
+                            dst[(size_t)c * a.scratch_slots] = __uint_as_float(v[c >> 5][c & 31]);
+                    }
+                }
+            } else if (q_ok) {
+#pragma unroll
+                for (int c = 0; c < kTS_N; ++c) {
+                    const long long row = row0 + c;
+                    const float sc = __uint_as_float(v[c >> 5][c & 31]) + 0.0f;
+                    if (sc > tau_q && row >= a.row_begin && row < a.row_end) {
+                        const uint32_t pos = atomicAdd(a.cnt + slot, 1u);
+                        if (pos < (uint32_t)a.cap) {
+                            a.cand_score[(size_t)slot * a.cap + pos] = sc;
+                            a.cand_row[(size_t)slot * a.cap + pos] = (int32_t)row;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (threadIdx.x == 64) K2_TRACE(0, 3);
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) K2_TRACE(0, 4);
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 // ---- host side --------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -269,6 +518,39 @@ bool dense_tile_supported(const Geometry& g, int* n_stages_out) {
     return true;
 }
 
+static bool dense_tile_ts_supported(const Geometry& g) {
+    return g.C_pad > 0 && (g.C_pad + kDT_KB - 1) / kDT_KB * 32 <= kTS_MaxACols;
+}
+
+static int launch_dense_tile_ts(const dhr_index* h, const void* q_dns16, int n_queries, long long tile_row0, long long row_begin,
+                                long long row_end, int mode, float* scratch, long long scratch_slots, const TopkState& t, int cap,
+                                cudaStream_t st) {
+    const Geometry& g = h->g;
+    CUtensorMap tmap_c, tmap_q;
+    DHR_TRY(make_tmap_f16(&tmap_c, h->dns, (uint64_t)h->n_rows, (uint64_t)g.C_pad, (uint64_t)g.C_pad, kTS_N));
+    DHR_TRY(make_tmap_f16(&tmap_q, q_dns16, (uint64_t)n_queries, (uint64_t)g.C_pad, (uint64_t)g.C_pad, kTS_M));
+    DenseTsArgs a{};
+    a.row_begin = row_begin; a.row_end = row_end;
+    a.tile_row0 = tile_row0 + (row_begin - tile_row0) / kTS_N * kTS_N;
+    a.scratch_row0 = tile_row0;
+    a.n_tiles = (int)((row_end - a.tile_row0 + kTS_N - 1) / kTS_N);
+    a.n_kblocks = (g.C_pad + kDT_KB - 1) / kDT_KB;
+    a.n_stages = kTS_MaxStages;
+    a.n_qgroups = (n_queries + kTS_M - 1) / kTS_M;
+    a.n_queries = n_queries;
+    a.mode = mode;
+    a.scratch = scratch; a.scratch_slots = scratch_slots;
+    a.tau = t.tau; a.cnt = t.cnt; a.cand_score = t.cand_score; a.cand_row = t.cand_row; a.cap = cap;
+    const size_t smem = (size_t)a.n_stages * kTS_BBytes + 1024;
+    DHR_CUDA(cudaFuncSetAttribute(dense_tile_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_q = h->num_sms / a.n_qgroups;
+    if (per_q < 1) per_q = 1;
+    if (per_q > a.n_tiles) per_q = a.n_tiles;
+    dense_tile_ts_kernel<<<(unsigned)(per_q * a.n_qgroups), kTS_Threads, smem, st>>>(tmap_c, tmap_q, a);
+    DHR_CUDA(cudaGetLastError());
+    return DHR_OK;
+}
+
 // Launch K2 over rows [row_begin, row_end) (row_begin aligned to 128 from tile_row0) for `n_queries` in-flight queries
 // whose fp16 dense block starts at q_dns16 (row pitch C_pad).
 int launch_dense_tile(const dhr_index* h, const void* q_dns16, int n_queries, long long tile_row0, long long row_begin,
@@ -278,6 +560,8 @@ int launch_dense_tile(const dhr_index* h, const void* q_dns16, int n_queries, lo
     int stages = 0;
     if (!dense_tile_supported(g, &stages)) return DHR_ERR_UNSUPPORTED;
     if (row_end <= row_begin || n_queries <= 0) return DHR_OK;
+    if (h->opt_dense_variant == 1 && dense_tile_ts_supported(g))
+        return launch_dense_tile_ts(h, q_dns16, n_queries, tile_row0, row_begin, row_end, mode, scratch, scratch_slots, t, cap, st);
     CUtensorMap tmap_a, tmap_b;
     DHR_TRY(make_tmap_f16(&tmap_a, h->dns, (uint64_t)h->n_rows, (uint64_t)g.C_pad, (uint64_t)g.C_pad, kDT_M));
     DHR_TRY(make_tmap_f16(&tmap_b, q_dns16, (uint64_t)n_queries, (uint64_t)g.C_pad, (uint64_t)g.C_pad, kDT_N));

@@ -72,6 +72,7 @@ struct dhr_index {
     int opt_query_groups = 8;
     int opt_profile = 0;
     int opt_tile_mode = 1;               // use the tensor-core tile kernels when the shape allows
+    int opt_dense_variant = 1;           // K2: 1 = queries in TMEM (TS) when C_pad <= 768, 0 = both operands in shared memory (SS)
     int num_sms = 148;
     dhr_stats stats{};
     dhr::EventPool events;

@@ -1,0 +1,62 @@
+// k2_micro.cu -- standalone micro-benchmark + timeline of the dense tile kernels K2 (not part of the library).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -DDHR_K2_TRACE -o gpurun_out/k2_micro tools/k2_micro.cu -lcuda
+//   gpurun_out/k2_micro [rows_per_launch=37888] [queries=256] [C=768]
+// Launches K2 (mode 1: scratch writes) over successive sub-chunks of a synthetic dense block and prints the median
+// kernel time per variant plus, for the TS variant, the clock64 timeline of CTA 0.
+#include "../dhr_b200/csrc/dense_tile.cu"
+
+#include <algorithm>
+#include <vector>
+
+namespace dhr {
+void set_cuda_error(cudaError_t e, const char* what, const char*, int line) { fprintf(stderr, "cuda error %d (%s) line %d\n", (int)e, what, line); }
+}
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e_)); return 1; } } while (0)
+
+int main(int argc, char** argv) {
+    const long long sub = argc > 1 ? atoll(argv[1]) : 37888;
+    const int nq = argc > 2 ? atoi(argv[2]) : 256;
+    const int C = argc > 3 ? atoi(argv[3]) : 768;
+    const long long n_rows = sub * 40;
+    dhr_index h;
+    h.g.C = C; h.g.C_pad = (C + 7) / 8 * 8; h.n_rows = n_rows;
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0)); h.num_sms = prop.multiProcessorCount;
+    CK(cudaMalloc(&h.dns, (size_t)n_rows * h.g.C_pad * 2)); CK(cudaMemset(h.dns, 0x3c, (size_t)n_rows * h.g.C_pad * 2));
+    void* q; CK(cudaMalloc(&q, (size_t)nq * h.g.C_pad * 2)); CK(cudaMemset(q, 0x2c, (size_t)nq * h.g.C_pad * 2));
+    float* scratch; CK(cudaMalloc(&scratch, (size_t)sub * 256 * 4));
+    dhr::TopkState t; CK(cudaMalloc(&t.tau, 256 * 4)); CK(cudaMalloc(&t.cnt, 256 * 4));
+    CK(cudaMemset(t.tau, 0x7f, 256 * 4)); CK(cudaMemset(t.cnt, 0, 256 * 4));
+    CK(cudaMalloc(&t.cand_score, (size_t)256 * 16384 * 4)); CK(cudaMalloc(&t.cand_row, (size_t)256 * 16384 * 4));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int dbgs[] = {0, 0, 4, 8, 12};
+    for (int vi = 0; vi < 5; ++vi) {
+        const int variant = vi == 0 ? 0 : 1;
+        const int dbg = dbgs[vi];
+        CK(cudaMemcpyToSymbol(dhr::g_k2_dbg, &dbg, sizeof(int)));
+        h.opt_dense_variant = variant;
+        std::vector<float> ms;
+        for (int i = 0; i < 40; ++i) {
+            const long long r0 = (long long)i * sub;
+            cudaEventRecord(e0);
+            int rc = dhr::launch_dense_tile(&h, q, nq, r0, r0, r0 + sub, 1, scratch, 256, t, 16384, 0);
+            cudaEventRecord(e1);
+            CK(cudaEventSynchronize(e1));
+            if (rc != 0) { fprintf(stderr, "launch rc %d\n", rc); return 1; }
+            float m; cudaEventElapsedTime(&m, e0, e1); ms.push_back(m);
+        }
+        std::sort(ms.begin(), ms.end());
+        const double flops = 2.0 * sub * nq * C;
+        printf("dbg %2d variant %d (%s): median %.1f us  min %.1f us  -> %.0f TFLOP/s, corpus read %.0f GB/s\n", dbg, variant, variant ? "TS" : "SS",
+               ms[20] * 1e3, ms[0] * 1e3, flops / (ms[20] * 1e-3) / 1e12, sub * h.g.C_pad * 2.0 / (ms[20] * 1e-3) / 1e9);
+    }
+    long long tr[8][64];
+    CK(cudaMemcpyFromSymbol(tr, dhr::g_k2_trace, sizeof(tr)));
+    const long long t0 = tr[0][0];
+    printf("TS timeline of CTA 0 (cycles from kernel entry): tmem alloc done %lld, query operand in TMEM %lld, epilogue done %lld, end %lld\n",
+           tr[0][1] - t0, tr[0][2] - t0, tr[0][3] - t0, tr[0][4] - t0);
+    for (int i = 0; i < 10; ++i)
+        printf("  tile %d: producer start %lld | mma: wait-begin %lld acc-free %lld issued %lld | epilogue: acc-ready %lld drained %lld\n", i,
+               tr[1][i] - t0, tr[2][i] - t0, tr[3][i] - t0, tr[4][i] - t0, tr[5][i] - t0, tr[6][i] - t0);
+    return 0;
+}
