@@ -45,6 +45,8 @@ def parse():
     ap.add_argument('--query-block', type=int, default=None)
     ap.add_argument('--query-groups', type=int, default=None)
     ap.add_argument('--scan-variant', type=int, default=None)
+    ap.add_argument('--overlap', type=int, default=None, help='hybrid tile path: K2 on a second stream (1, default) or in line (0)')
+    ap.add_argument('--dense-variant', type=int, default=None, help='K2: 1 = queries in TMEM (default), 0 = both operands in shared memory')
     ap.add_argument('--cpu-rows', type=int, default=400000, help='rows of the bounded CPU-baseline sample')
     ap.add_argument('--cpu-queries', type=int, default=8)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -214,6 +216,10 @@ def main():
         ix.set_option('query_groups', args.query_groups)
     if args.scan_variant is not None:
         ix.set_option('scan_variant', args.scan_variant)
+    if args.overlap is not None:
+        ix.set_option('overlap', args.overlap)
+    if args.dense_variant is not None:
+        ix.set_option('dense_variant', args.dense_variant)
     ix.set_option('profile', 1)
 
     qv_dev, qi_dev = synth.queries_torch(args.workload, n_q, dev)

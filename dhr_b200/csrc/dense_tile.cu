@@ -47,6 +47,9 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tmap, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -264,6 +267,8 @@ constexpr int kTS_BBytes = kTS_N * kDT_KB * 2;   // 16 KiB per corpus stage
 constexpr int kTS_MaxStages = 12;
 constexpr int kTS_MaxACols = 384;      // TMEM columns holding the query operand (C_pad <= 768)
 constexpr int kTS_Threads = 192;
+constexpr int kTS_Prefetch = 2;         // L2 prefetch distance in tiles of one CTA
+static_assert(kTS_N == kDenseTileRows && kDT_KB == kDenseTileCols, "K-blocked dense copy layout");
 
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -288,7 +293,8 @@ struct DenseTsArgs {
     long long row_begin, row_end;      // rows of this launch
     long long tile_row0;               // first row of tile 0 (row_begin rounded down to a 64-row tile from the launch base)
     long long scratch_row0;            // row of scratch line 0
-    int n_tiles;                       // 64-row tiles in the launch
+    int n_tiles;                       // 128-row tiles in the launch
+    int blocked;                       // corpus operand comes from the K-blocked copy
     int n_kblocks;                     // ceil(C_pad / 64)
     int n_stages;
     int n_qgroups;                     // 128-query groups in flight
@@ -375,8 +381,18 @@ dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
                 if (K2_DBG() & 8) continue;
                 mbar_wait(&empty_bar[s], ph ^ 1u);
                 if (elect_one()) {
+                    // the ring holds exactly one corpus tile, so the demand load is issued only one tile-time ahead of its use:
+                    // pull the same k-block of the tile `kTS_Prefetch` iterations further on into L2 now (HBM latency off the
+                    // critical path); the two query groups share tiles, group 0 prefetches
+                    const int tp = t + kTS_Prefetch * ctas_per_q;
+                    if (qg == 0 && tp < a.n_tiles) {
+                        const int rowp = row0 + kTS_Prefetch * ctas_per_q * kTS_N;
+                        if (a.blocked) tma_prefetch_l2_2d(&tmap_c, 0, (rowp / kTS_N * a.n_kblocks + kb) * kTS_N);
+                        else tma_prefetch_l2_2d(&tmap_c, kb * kDT_KB, rowp);
+                    }
                     mbar_arrive_expect_tx(&full_bar[s], kTS_BBytes);
-                    tma_load_2d(ring + (size_t)s * kTS_BBytes, &tmap_c, &full_bar[s], kb * kDT_KB, row0);
+                    if (a.blocked) tma_load_2d(ring + (size_t)s * kTS_BBytes, &tmap_c, &full_bar[s], 0, (row0 / kTS_N * a.n_kblocks + kb) * kTS_N);
+                    else tma_load_2d(ring + (size_t)s * kTS_BBytes, &tmap_c, &full_bar[s], kb * kDT_KB, row0);
                 }
                 __syncwarp();
                 if (++s == a.n_stages) { s = 0; ph ^= 1u; }
@@ -442,23 +458,41 @@ dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
                 // scratch[row][slot]: for a fixed passage the 32 lanes of a warp write 32 consecutive slots (one 128-byte line)
                 if ((long long)slot < a.scratch_slots) {
                     float* dst = a.scratch + (size_t)(row0 - a.scratch_row0) * a.scratch_slots + slot;
+                    if (a.scratch_slots == kMaxInflight && row0 >= a.row_begin && row0 + kTS_N <= a.row_end) {
+                        // whole tile in range, compile-time row pitch: one store instruction per passage
 #pragma unroll
-                    for (int c = 0; c < kTS_N; ++c) {
-                        const long long row = row0 + c;
-                        if (row >= a.row_begin && row < a.row_end)
-                            dst[(size_t)c * a.scratch_slots] = __uint_as_float(v[c >> 5][c & 31]);
+                        for (int c = 0; c < kTS_N; ++c) dst[(size_t)c * kMaxInflight] = __uint_as_float(v[c >> 5][c & 31]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < kTS_N; ++c) {
+                            const long long row = row0 + c;
+                            if (row >= a.row_begin && row < a.row_end)
+                                dst[(size_t)c * a.scratch_slots] = __uint_as_float(v[c >> 5][c & 31]);
+                        }
                     }
                 }
             } else if (q_ok) {
+                // dense-only index: strict admission threshold.  Rows pass rarely once tau is set (~0.1 %), so each group of 8
+                // passages is first reduced to its maximum and scanned only when something can pass; small groups keep the
+                // probability that ANY lane of the warp takes the scan low.
+                const bool full = row0 >= a.row_begin && row0 + kTS_N <= a.row_end;
 #pragma unroll
-                for (int c = 0; c < kTS_N; ++c) {
-                    const long long row = row0 + c;
-                    const float sc = __uint_as_float(v[c >> 5][c & 31]) + 0.0f;
-                    if (sc > tau_q && row >= a.row_begin && row < a.row_end) {
-                        const uint32_t pos = atomicAdd(a.cnt + slot, 1u);
-                        if (pos < (uint32_t)a.cap) {
-                            a.cand_score[(size_t)slot * a.cap + pos] = sc;
-                            a.cand_row[(size_t)slot * a.cap + pos] = (int32_t)row;
+                for (int j = 0; j < kTS_N / 8; ++j) {
+                    float m = __uint_as_float(v[j >> 2][(j & 3) * 8]);
+#pragma unroll
+                    for (int c = 1; c < 8; ++c) m = fmaxf(m, __uint_as_float(v[j >> 2][(j & 3) * 8 + c]));
+                    if (m > tau_q) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const long long row = row0 + 8 * j + c;
+                            const float sc = __uint_as_float(v[j >> 2][(j & 3) * 8 + c]) + 0.0f;
+                            if (sc > tau_q && (full || (row >= a.row_begin && row < a.row_end))) {
+                                const uint32_t pos = atomicAdd(a.cnt + slot, 1u);
+                                if (pos < (uint32_t)a.cap) {
+                                    a.cand_score[(size_t)slot * a.cap + pos] = sc;
+                                    a.cand_row[(size_t)slot * a.cap + pos] = (int32_t)row;
+                                }
+                            }
                         }
                     }
                 }
@@ -518,7 +552,7 @@ bool dense_tile_supported(const Geometry& g, int* n_stages_out) {
     return true;
 }
 
-static bool dense_tile_ts_supported(const Geometry& g) {
+bool dense_tile_ts_supported(const Geometry& g) {
     return g.C_pad > 0 && (g.C_pad + kDT_KB - 1) / kDT_KB * 32 <= kTS_MaxACols;
 }
 
@@ -527,11 +561,18 @@ static int launch_dense_tile_ts(const dhr_index* h, const void* q_dns16, int n_q
                                 cudaStream_t st) {
     const Geometry& g = h->g;
     CUtensorMap tmap_c, tmap_q;
-    DHR_TRY(make_tmap_f16(&tmap_c, h->dns, (uint64_t)h->n_rows, (uint64_t)g.C_pad, (uint64_t)g.C_pad, kTS_N));
+    const int nkb = (g.C_pad + kDT_KB - 1) / kDT_KB;
+    // corpus operand: the K-blocked copy viewed as [blocks * 128 rows][64 cols] (one box = one contiguous 16 KiB block), or the
+    // row-major block when the copy could not be allocated
+    if (h->dnst)
+        DHR_TRY(make_tmap_f16(&tmap_c, h->dnst, (uint64_t)round_up(h->n_rows, kTS_N) * nkb, (uint64_t)kDT_KB, (uint64_t)kDT_KB, kTS_N));
+    else
+        DHR_TRY(make_tmap_f16(&tmap_c, h->dns, (uint64_t)h->n_rows, (uint64_t)g.C_pad, (uint64_t)g.C_pad, kTS_N));
     DHR_TRY(make_tmap_f16(&tmap_q, q_dns16, (uint64_t)n_queries, (uint64_t)g.C_pad, (uint64_t)g.C_pad, kTS_M));
     DenseTsArgs a{};
     a.row_begin = row_begin; a.row_end = row_end;
-    a.tile_row0 = tile_row0 + (row_begin - tile_row0) / kTS_N * kTS_N;
+    a.tile_row0 = row_begin / kTS_N * kTS_N;                     // absolute 128-row tiles (the K-blocked copy is tiled from row 0)
+    a.blocked = h->dnst != nullptr;
     a.scratch_row0 = tile_row0;
     a.n_tiles = (int)((row_end - a.tile_row0 + kTS_N - 1) / kTS_N);
     a.n_kblocks = (g.C_pad + kDT_KB - 1) / kDT_KB;

@@ -158,6 +158,25 @@ __global__ void build_lext_kernel(long long n_rows, long long n_rows_pad, int S_
     for (int g = 0; g < G; ++g) tv[g] = src[g];
 }
 
+// K-blocked copy of the dense block for K2 (TS variant): [tile of 128 rows][k-block][128 rows][64 cols], so that one
+// 16 KiB TMA stage is one contiguous piece of HBM (the row-major block would be read as 128-byte pieces 2*C_pad apart,
+// which measured ~2.2 TB/s).  One thread moves one 16-byte vector; rows >= n_rows and columns >= C_pad are zero.
+__global__ void build_dnst_kernel(long long n_rows, long long n_rows_pad, int C_pad, int n_kblocks, const __half* __restrict__ dns,
+                                  __half* __restrict__ dnst) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long vec_per_row = (long long)n_kblocks * (kDenseTileCols / 8);
+    if (i >= n_rows_pad * vec_per_row) return;
+    const long long r = i / vec_per_row;
+    const int v = (int)(i % vec_per_row);
+    const int kb = v / (kDenseTileCols / 8), cv = v % (kDenseTileCols / 8);
+    const int col = kb * kDenseTileCols + cv * 8;
+    uint4 x = make_uint4(0u, 0u, 0u, 0u);
+    if (r < n_rows && col < C_pad) x = *(const uint4*)(dns + (size_t)r * C_pad + col);
+    const long long tile = r / kDenseTileRows;
+    const int tr = (int)(r % kDenseTileRows);
+    *(uint4*)(dnst + (((size_t)tile * n_kblocks + kb) * kDenseTileRows + tr) * kDenseTileCols + cv * 8) = x;
+}
+
 static int ingest_device(dhr_index* h, long long n, int val_dtype, const void* d_vals, long long vstride, int idx_dtype,
                          const void* d_idx, long long istride) {
     const Geometry& g = h->g;
@@ -339,6 +358,19 @@ int dhr_index_finalize(dhr_index* h) {
             DHR_CUDA(cudaDeviceSynchronize());
         }
     }
+    if (h->g.C_pad > 0 && h->n_rows > 0 && dense_tile_ts_supported(h->g)) {
+        const Geometry& g = h->g;
+        const int nkb = (g.C_pad + kDenseTileCols - 1) / kDenseTileCols;
+        const long long rows_pad = round_up(h->n_rows, kDenseTileRows);
+        h->dnst_bytes = (size_t)rows_pad * nkb * kDenseTileCols * sizeof(__half);
+        if (cudaMalloc(&h->dnst, h->dnst_bytes) != cudaSuccess) { cudaGetLastError(); h->dnst = nullptr; h->dnst_bytes = 0; }   // K2 then reads the row-major block
+        if (h->dnst) {
+            const long long total = rows_pad * nkb * (kDenseTileCols / 8);
+            build_dnst_kernel<<<(unsigned)((total + 255) / 256), 256>>>(h->n_rows, rows_pad, g.C_pad, nkb, h->dns, h->dnst);
+            DHR_CUDA(cudaGetLastError());
+            DHR_CUDA(cudaDeviceSynchronize());
+        }
+    }
     // the ingest staging buffers are not needed any more
     if (h->stage_a) { cudaFree(h->stage_a); h->stage_a = nullptr; h->stage_a_bytes = 0; }
     if (h->stage_b) { cudaFree(h->stage_b); h->stage_b = nullptr; h->stage_b_bytes = 0; }
@@ -363,10 +395,13 @@ int dhr_index_close(dhr_index* h) {
     if (!h) return DHR_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    void* bufs[] = {h->lexv, h->lexi, h->dns, h->lext, h->qblocks, h->qblock_bytes, h->scratch, h->d_flags, h->stage_a, h->stage_b, h->q_lex16, h->q_lex32, h->q_dns16, h->q_dns32,
+    void* bufs[] = {h->lexv, h->lexi, h->dns, h->dnst, h->lext, h->qblocks, h->qblock_bytes, h->scratch, h->d_flags, h->stage_a, h->stage_b, h->q_lex16, h->q_lex32, h->q_dns16, h->q_dns32,
                     h->q_code, h->topk.tau, h->topk.cnt, h->topk.overflow, h->topk.cand_score, h->topk.cand_row,
                     h->d_out_scores, h->d_out_rows, h->d_out_counts};
     for (void* b : bufs) if (b) cudaFree(b);
+    for (int i = 0; i < 2; ++i) { if (h->ev_k2_done[i]) cudaEventDestroy(h->ev_k2_done[i]); if (h->ev_k1_done[i]) cudaEventDestroy(h->ev_k1_done[i]); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     h->events.destroy();
     cudaGetLastError();
     delete h;
@@ -394,6 +429,7 @@ int dhr_index_set_option(dhr_index* h, const char* name, int64_t value) {
     }
     if (!strcmp(name, "query_groups")) { if (value < 1 || value > kMaxScanInflight) return DHR_ERR_INVALID; h->opt_query_groups = (int)value; return DHR_OK; }
     if (!strcmp(name, "tile_mode")) { h->opt_tile_mode = value != 0; return DHR_OK; }
+    if (!strcmp(name, "overlap")) { h->opt_overlap = value != 0; return DHR_OK; }
     if (!strcmp(name, "dense_variant")) { if (value < 0 || value > 1) return DHR_ERR_INVALID; h->opt_dense_variant = (int)value; return DHR_OK; }
     if (!strcmp(name, "profile")) { h->opt_profile = value != 0; return DHR_OK; }
     return DHR_ERR_INVALID;

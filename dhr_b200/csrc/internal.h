@@ -50,6 +50,8 @@ struct dhr_index {
     __half* lexv = nullptr;              // [capacity][D_pad]
     uint8_t* lexi = nullptr;             // [capacity][S_pad] codes (uint8 or uint16)
     __half* dns = nullptr;               // [capacity][C_pad]
+    __half* dnst = nullptr;              // K-blocked copy of the dense block for K2 (TS): [tile of 128 rows][k-block of 64 cols][128][64], built at finalize
+    size_t dnst_bytes = 0;
     uint8_t* lext = nullptr;             // tiled lexical copy for K1t: [tile of 256 rows][8-slice chunk]{codes[256][8] | vals[8][256][G]}
     size_t lext_bytes = 0;
     int max_code = -1;                   // largest slice code stored (known after finalize)
@@ -64,7 +66,9 @@ struct dhr_index {
     // tile-mode workspace
     uint8_t* qblocks = nullptr; size_t qblocks_bytes = 0;
     uint32_t* qblock_bytes = nullptr; size_t qblock_bytes_cap = 0;
-    float* scratch = nullptr; size_t scratch_bytes = 0;
+    float* scratch = nullptr; size_t scratch_bytes = 0;   // two sub-chunk buffers (K2 of sub-chunk i+1 overlaps K1t of sub-chunk i)
+    cudaStream_t aux_stream = nullptr;   // K2 launches of the hybrid tile path
+    cudaEvent_t ev_k2_done[2] = {nullptr, nullptr}, ev_k1_done[2] = {nullptr, nullptr}, ev_fork = nullptr;
     float* d_out_scores = nullptr; int64_t* d_out_rows = nullptr; int32_t* d_out_counts = nullptr; size_t out_capacity = 0;
     // options
     int opt_scan_variant = 1;            // TMA bulk staging (measured faster than direct loads at QB=1 and QB=8)
@@ -72,6 +76,7 @@ struct dhr_index {
     int opt_query_groups = 8;
     int opt_profile = 0;
     int opt_tile_mode = 1;               // use the tensor-core tile kernels when the shape allows
+    int opt_overlap = 1;                 // hybrid tile path: run K2 on a second stream, one sub-chunk ahead of K1t
     int opt_dense_variant = 1;           // K2: 1 = queries in TMEM (TS) when C_pad <= 768, 0 = both operands in shared memory (SS)
     int num_sms = 148;
     dhr_stats stats{};
@@ -122,6 +127,9 @@ int launch_lex_tile(const dhr_index* h, const LexTileGeom& t, const uint8_t* qbl
                     const TopkState& tk, int cap, cudaStream_t st);
 
 bool dense_tile_supported(const Geometry& g, int* n_stages_out);
+bool dense_tile_ts_supported(const Geometry& g);
+constexpr int kDenseTileRows = 128;      // rows per K2 (TS) corpus tile and per block of the K-blocked copy
+constexpr int kDenseTileCols = 64;       // fp16 columns per k-block (128 bytes)
 int launch_dense_tile(const dhr_index* h, const void* q_dns16, int n_queries, long long tile_row0, long long row_begin,
                       long long row_end, int mode, float* scratch, long long scratch_slots, const TopkState& t, int cap,
                       cudaStream_t st);

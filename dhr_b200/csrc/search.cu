@@ -304,12 +304,20 @@ static int ensure_tile_workspace(dhr_index* h, const LexTileGeom& t, int n_queri
         DHR_CUDA(cudaMalloc(&h->qblock_bytes, nb_need));
         h->qblock_bytes_cap = nb_need;
     }
-    const size_t sc_need = h->g.C_pad > 0 ? (size_t)kMaxInflight * kTileSubRows * sizeof(float) : 0;
+    const size_t sc_need = h->g.C_pad > 0 ? (size_t)2 * kMaxInflight * kTileSubRows * sizeof(float) : 0;
     if (sc_need > h->scratch_bytes) {
         if (h->scratch) cudaFree(h->scratch);
         h->scratch = nullptr; h->scratch_bytes = 0;
         DHR_CUDA(cudaMalloc(&h->scratch, sc_need));
         h->scratch_bytes = sc_need;
+    }
+    if (h->g.C_pad > 0 && !h->aux_stream) {
+        DHR_CUDA(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            DHR_CUDA(cudaEventCreateWithFlags(&h->ev_k2_done[i], cudaEventDisableTiming));
+            DHR_CUDA(cudaEventCreateWithFlags(&h->ev_k1_done[i], cudaEventDisableTiming));
+        }
+        DHR_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     }
     return DHR_OK;
 }
@@ -327,17 +335,52 @@ static int run_batch_hybrid_tile(dhr_index* h, const LexTileGeom& lt, const Quer
     const size_t qt0 = (size_t)base / kLexTileQueries;
     const uint8_t* qblocks = h->qblocks + qt0 * lt.n_chunks * (size_t)lt.qblock_stride;
     const uint32_t* qbytes = h->qblock_bytes + qt0 * lt.n_chunks;
+    // K2 runs on the auxiliary stream one sub-chunk ahead of K1t (two scratch buffers): the tensor-core kernel fills the SMs
+    // that the tail of the previous K1t launch leaves idle.  K2 (mode 1) reads only the prepared queries, so it does not
+    // depend on the selects between chunks.
+    const bool dense = g.C_pad > 0;
+    const bool overlap = dense && h->opt_overlap;
+    const size_t sc_half = (size_t)kMaxInflight * kTileSubRows;
+    std::vector<std::pair<long long, long long>> subs;
+    std::vector<size_t> sub_chunk;
+    for (size_t c = 0; c < n_chunks; ++c)
+        for (long long r0 = bounds[c]; r0 < bounds[c + 1]; r0 += kTileSubRows) {
+            subs.emplace_back(r0, std::min(bounds[c + 1], r0 + kTileSubRows));
+            sub_chunk.push_back(c);
+        }
+    cudaStream_t k2s = overlap ? h->aux_stream : st;
+    if (overlap) {
+        DHR_CUDA(cudaEventRecord(h->ev_fork, st));                   // queries prepared, previous batch finished with the scratch
+        DHR_CUDA(cudaStreamWaitEvent(k2s, h->ev_fork, 0));
+    }
+    auto launch_k2 = [&](size_t i) -> int {
+        const int b = (int)(i & 1);
+        if (overlap && i >= 2) DHR_CUDA(cudaStreamWaitEvent(k2s, h->ev_k1_done[b], 0));     // K1t(i-2) has read this buffer
+        DHR_TRY(launch_dense_tile(h, q16, nq, subs[i].first, subs[i].first, subs[i].second, 1, h->scratch + (overlap ? b * sc_half : 0),
+                                  kMaxInflight, t, kCandCap, k2s));
+        if (overlap) DHR_CUDA(cudaEventRecord(h->ev_k2_done[b], k2s));
+        h->stats.n_kernel_launches++;
+        return DHR_OK;
+    };
+    if (dense && overlap && !subs.empty()) DHR_TRY(launch_k2(0));
+    size_t si = 0;
     for (size_t c = 0; c < n_chunks; ++c) {
         cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
         if (h->opt_profile) { e0 = h->events.get(); e1 = h->events.get(); e2 = h->events.get(); cudaEventRecord(e0, st); }
-        for (long long r0 = bounds[c]; r0 < bounds[c + 1]; r0 += kTileSubRows) {
-            const long long r1 = std::min(bounds[c + 1], r0 + kTileSubRows);
-            if (g.C_pad > 0) {
-                DHR_TRY(launch_dense_tile(h, q16, nq, r0, r0, r1, 1, h->scratch, kMaxInflight, t, kCandCap, st));
-                h->stats.n_kernel_launches++;
+        for (; si < subs.size() && sub_chunk[si] == c; ++si) {
+            const int b = (int)(si & 1);
+            const long long r0 = subs[si].first, r1 = subs[si].second;
+            if (dense) {
+                if (overlap) {
+                    if (si + 1 < subs.size()) DHR_TRY(launch_k2(si + 1));
+                    DHR_CUDA(cudaStreamWaitEvent(st, h->ev_k2_done[b], 0));
+                } else {
+                    DHR_TRY(launch_k2(si));
+                }
             }
-            DHR_TRY(launch_lex_tile(h, lt, qblocks, qbytes, nq, r0, r1, g.C_pad > 0 ? h->scratch : nullptr, kMaxInflight, r0, t,
-                                    kCandCap, st));
+            DHR_TRY(launch_lex_tile(h, lt, qblocks, qbytes, nq, r0, r1, dense ? h->scratch + (overlap ? b * sc_half : 0) : nullptr, kMaxInflight,
+                                    r0, t, kCandCap, st));
+            if (overlap) DHR_CUDA(cudaEventRecord(h->ev_k1_done[b], st));
             h->stats.n_kernel_launches++;
             h->stats.n_scan_launches++;
         }

@@ -1,6 +1,6 @@
 // k2_micro.cu -- standalone micro-benchmark + timeline of the dense tile kernels K2 (not part of the library).
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -DDHR_K2_TRACE -o gpurun_out/k2_micro tools/k2_micro.cu -lcuda
-//   gpurun_out/k2_micro [rows_per_launch=37888] [queries=256] [C=768]
+//   k2_micro [rows_per_launch=37888] [queries=256] [C=768] [k_blocked_copy=1]
 // Launches K2 (mode 1: scratch writes) over successive sub-chunks of a synthetic dense block and prints the median
 // kernel time per variant plus, for the TS variant, the clock64 timeline of CTA 0.
 #include "../dhr_b200/csrc/dense_tile.cu"
@@ -18,11 +18,16 @@ int main(int argc, char** argv) {
     const long long sub = argc > 1 ? atoll(argv[1]) : 37888;
     const int nq = argc > 2 ? atoi(argv[2]) : 256;
     const int C = argc > 3 ? atoi(argv[3]) : 768;
+    const bool same_rows = argc > 5 && atoi(argv[5]) != 0;     // relaunch over the same (L2-resident) rows
     const long long n_rows = sub * 40;
     dhr_index h;
     h.g.C = C; h.g.C_pad = (C + 7) / 8 * 8; h.n_rows = n_rows;
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0)); h.num_sms = prop.multiProcessorCount;
     CK(cudaMalloc(&h.dns, (size_t)n_rows * h.g.C_pad * 2)); CK(cudaMemset(h.dns, 0x3c, (size_t)n_rows * h.g.C_pad * 2));
+    if (argc <= 4 || atoi(argv[4]) != 0) {   // K-blocked corpus copy (content irrelevant for timing)
+        const size_t nb = (size_t)((n_rows + 127) / 128 * 128) * ((h.g.C_pad + 63) / 64) * 64 * 2;
+        CK(cudaMalloc(&h.dnst, nb)); CK(cudaMemset(h.dnst, 0x3c, nb));
+    }
     void* q; CK(cudaMalloc(&q, (size_t)nq * h.g.C_pad * 2)); CK(cudaMemset(q, 0x2c, (size_t)nq * h.g.C_pad * 2));
     float* scratch; CK(cudaMalloc(&scratch, (size_t)sub * 256 * 4));
     dhr::TopkState t; CK(cudaMalloc(&t.tau, 256 * 4)); CK(cudaMalloc(&t.cnt, 256 * 4));
@@ -37,7 +42,7 @@ int main(int argc, char** argv) {
         h.opt_dense_variant = variant;
         std::vector<float> ms;
         for (int i = 0; i < 40; ++i) {
-            const long long r0 = (long long)i * sub;
+            const long long r0 = same_rows ? 0 : (long long)i * sub;
             cudaEventRecord(e0);
             int rc = dhr::launch_dense_tile(&h, q, nq, r0, r0, r0 + sub, 1, scratch, 256, t, 16384, 0);
             cudaEventRecord(e1);
@@ -49,6 +54,22 @@ int main(int argc, char** argv) {
         const double flops = 2.0 * sub * nq * C;
         printf("dbg %2d variant %d (%s): median %.1f us  min %.1f us  -> %.0f TFLOP/s, corpus read %.0f GB/s\n", dbg, variant, variant ? "TS" : "SS",
                ms[20] * 1e3, ms[0] * 1e3, flops / (ms[20] * 1e-3) / 1e12, sub * h.g.C_pad * 2.0 / (ms[20] * 1e-3) / 1e9);
+    }
+    // dense-only mode (filter + append, nothing passes tau): one launch over all rows, both variants
+    { const int z = 0; CK(cudaMemcpyToSymbol(dhr::g_k2_dbg, &z, sizeof(int))); }
+    for (int variant = 0; variant < 2; ++variant) {
+        h.opt_dense_variant = variant;
+        float best = 1e9f;
+        for (int i = 0; i < 5; ++i) {
+            cudaEventRecord(e0);
+            int rc = dhr::launch_dense_tile(&h, q, nq, 0, 0, n_rows, 0, nullptr, 0, t, 16384, 0);
+            cudaEventRecord(e1);
+            CK(cudaEventSynchronize(e1));
+            if (rc != 0) { fprintf(stderr, "launch rc %d\n", rc); return 1; }
+            float m; cudaEventElapsedTime(&m, e0, e1); best = std::min(best, m);
+        }
+        printf("mode 0 (filter) variant %d: %lld rows x %d queries in %.1f us -> %.0f TFLOP/s, corpus read %.0f GB/s\n", variant, n_rows, nq,
+               best * 1e3, 2.0 * n_rows * nq * C / (best * 1e-3) / 1e12, n_rows * h.g.C_pad * 2.0 / (best * 1e-3) / 1e9);
     }
     long long tr[8][64];
     CK(cudaMemcpyFromSymbol(tr, dhr::g_k2_trace, sizeof(tr)));
