@@ -132,9 +132,9 @@ __global__ void ingest_dense_kernel(long long n, int D, int C, int C_pad, int va
 }
 
 // Tiled lexical copy for K1t, built once at finalize from the row-major arrays:
-//   [tile of 256 rows][chunk of 8 slices]{ codes u8 [256][8] | vals fp16 [8][256][G] }
-// Codes are always 8-bit here (the tile path requires max code <= 253); CODE_EMPTY/NOMATCH map to 0xFF.
-template <typename CodeT>
+//   [tile of 512 rows][chunk of 4 slices]{ codes TCode [512][4] | vals fp16 [4][512][G] }
+// TCode is uint8 when the largest stored code is <= 253 (CODE_EMPTY/NOMATCH map to 0xFF), else uint16 (0xFFFF).
+template <typename CodeT, typename TCode>
 __global__ void build_lext_kernel(long long n_rows, long long n_rows_pad, int S_pad, int G, const __half* __restrict__ lexv,
                                   const CodeT* __restrict__ lexi, uint8_t* __restrict__ lext) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -143,17 +143,18 @@ __global__ void build_lext_kernel(long long n_rows, long long n_rows_pad, int S_
     const int s = (int)(i % S_pad);
     const long long tile = r / kLexTileRows;
     const int tp = (int)(r % kLexTileRows), chunk = s / kLexTileSlices, tj = s % kLexTileSlices;
-    const size_t pblock = (size_t)kLexTileRows * kLexTileSlices * (1 + 2 * (size_t)G);
+    const size_t pblock = (size_t)kLexTileRows * kLexTileSlices * (sizeof(TCode) + 2 * (size_t)G);
     uint8_t* blk = lext + ((size_t)tile * (S_pad / kLexTileSlices) + chunk) * pblock;
-    uint8_t* tc = blk + (size_t)tp * kLexTileSlices + tj;
-    __half* tv = (__half*)(blk + (size_t)kLexTileRows * kLexTileSlices) + ((size_t)tj * kLexTileRows + tp) * G;
+    TCode* tc = (TCode*)blk + (size_t)tp * kLexTileSlices + tj;
+    __half* tv = (__half*)(blk + (size_t)kLexTileRows * kLexTileSlices * sizeof(TCode)) + ((size_t)tj * kLexTileRows + tp) * G;
+    constexpr uint32_t kTEmpty = sizeof(TCode) == 1 ? 0xFFu : 0xFFFFu;
     if (r >= n_rows) {
-        *tc = 0xFF;
+        *tc = (TCode)kTEmpty;
         for (int g = 0; g < G; ++g) tv[g] = __float2half_rn(0.f);
         return;
     }
     const uint32_t code = lexi[(size_t)r * S_pad + s];
-    *tc = code > 253u ? (uint8_t)0xFF : (uint8_t)code;
+    *tc = code > CodeTraits<TCode>::kMax ? (TCode)kTEmpty : (TCode)code;
     const __half* src = lexv + ((size_t)r * S_pad + s) * G;
     for (int g = 0; g < G; ++g) tv[g] = src[g];
 }
@@ -342,18 +343,21 @@ int dhr_index_finalize(dhr_index* h) {
     if (flags[0]) return DHR_ERR_LOSSY;
     if (flags[1]) return DHR_ERR_IDX_RANGE;
     h->max_code = flags[3] - 1;
-    if (h->g.S_pad > 0 && h->n_rows > 0 && h->max_code <= 253 && lex_tile_supported(h->g, std::max(1, h->max_code + 1))) {
+    if (h->g.S_pad > 0 && h->n_rows > 0 && lex_tile_supported(h->g, std::max(1, h->max_code + 1))) {
         const Geometry& g = h->g;
+        const LexTileGeom lt = lex_tile_geom(g, std::max(1, h->max_code + 1));
         const long long rows_pad = round_up(h->n_rows, kLexTileRows);
-        h->lext_bytes = (size_t)rows_pad * g.S_pad * (1 + 2 * (size_t)g.G);
+        h->lext_bytes = (size_t)rows_pad * g.S_pad * (lt.tcode_bytes + 2 * (size_t)g.G);
         if (cudaMalloc(&h->lext, h->lext_bytes) != cudaSuccess) { cudaGetLastError(); h->lext = nullptr; h->lext_bytes = 0; }   // tile path simply stays off
         if (h->lext) {
             const long long total = rows_pad * g.S_pad;
             const unsigned blocks = (unsigned)((total + 255) / 256);
-            if (g.code_bytes == 1)
-                build_lext_kernel<uint8_t><<<blocks, 256>>>(h->n_rows, rows_pad, g.S_pad, g.G, h->lexv, (const uint8_t*)h->lexi, h->lext);
+            if (lt.wide)
+                build_lext_kernel<uint16_t, uint16_t><<<blocks, 256>>>(h->n_rows, rows_pad, g.S_pad, g.G, h->lexv, (const uint16_t*)h->lexi, h->lext);
+            else if (g.code_bytes == 1)
+                build_lext_kernel<uint8_t, uint8_t><<<blocks, 256>>>(h->n_rows, rows_pad, g.S_pad, g.G, h->lexv, (const uint8_t*)h->lexi, h->lext);
             else
-                build_lext_kernel<uint16_t><<<blocks, 256>>>(h->n_rows, rows_pad, g.S_pad, g.G, h->lexv, (const uint16_t*)h->lexi, h->lext);
+                build_lext_kernel<uint16_t, uint8_t><<<blocks, 256>>>(h->n_rows, rows_pad, g.S_pad, g.G, h->lexv, (const uint16_t*)h->lexi, h->lext);
             DHR_CUDA(cudaGetLastError());
             DHR_CUDA(cudaDeviceSynchronize());
         }

@@ -113,6 +113,7 @@ int launch_rerank(const dhr_index* h, const ScanArgs& a, bool q_f32, const long 
 
 struct LexTileGeom {
     int G, code_bytes, n_chunks, rt;
+    int wide, tcode_bytes, n_stages;     // bucket-lookup layout (lex_tile.cu), code width of the tiled copy, smem ring depth
     int pblock_bytes, qoff_bytes, qblock_stride, stage_bytes;
 };
 constexpr int kLexTileRows = 512;        // passages per K1t tile (= consumer threads)

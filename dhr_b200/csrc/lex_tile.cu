@@ -31,7 +31,7 @@ namespace dhr {
 constexpr int kLT_PT = kLexTileRows;    // passages per tile = consumer threads
 constexpr int kLT_QT = kLexTileQueries; // queries per tile
 constexpr int kLT_SC = kLexTileSlices;  // slices per chunk
-constexpr int kLT_Stages = 3;
+constexpr int kLT_MaxStages = 6;      // ring depth: as many stages as fit next to acc (small-G shapes have small stages and need depth)
 constexpr int kLT_Threads = kLT_PT + 32;
 constexpr int kLT_CtasPerSm = 1;
 static_assert(kLT_SC == 4, "the flattened walk selects among the 4 slices of a chunk");
@@ -42,25 +42,40 @@ __host__ __device__ constexpr int lt_entry_words(int G) { return G <= 2 ? 2 : (G
 __host__ __device__ constexpr int lt_pval_words(int G) { return (G + 1) / 2; }
 
 
-LexTileGeom lex_tile_geom(const Geometry& g, int rt) {
-    LexTileGeom t{};
-    t.G = g.G; t.code_bytes = g.code_bytes; t.n_chunks = g.S_pad / kLT_SC; t.rt = rt;
-    t.pblock_bytes = kLT_PT * kLT_SC * (1 + 2 * g.G);        // tiled copy always stores 8-bit codes
-    t.qoff_bytes = (int)round_up((int64_t)kLT_SC * (rt + 1) * 4, 16);   // rt buckets + one empty bucket (clamp target) per slice
-    t.qblock_stride = t.qoff_bytes + kLT_SC * kLT_QT * lt_entry_words(g.G) * 4;
-    t.stage_bytes = (int)round_up(t.pblock_bytes, 128) + (int)round_up(t.qblock_stride, 128);
-    return t;
-}
-
-size_t lex_tile_smem_bytes(const LexTileGeom& t) {
-    return (size_t)kLT_QT * kLT_PT * 4 + (size_t)kLT_Stages * t.stage_bytes + 128;
-}
+// Two bucket-lookup layouts, chosen by the index range rt (= largest stored code + 1):
+//  * narrow (rt <= 254, e.g. DeLADE's 39 strides, uniCOIL/SPLADE int8): 8-bit codes in the tiled copy, direct table
+//    tab[slice][code] of rt + 1 words;
+//  * wide (rt up to 65534, e.g. densified BM25 with idx < 3466): 16-bit codes, and per slice the short list of DISTINCT
+//    query codes of the tile {n, (code, table word) x n} that every passage thread compares against (warp-uniform loop;
+//    a BM25 query tile has ~2 non-empty queries per slice).
+constexpr int kLT_WideSliceBytes = 16 + kLT_QT * 8;
 
 constexpr size_t kLT_StaticSmem = kLT_QT * 4 + 2048;
 constexpr size_t kLT_SmemBudget = (size_t)(227 * 1024) / kLT_CtasPerSm - 1024;   // per CTA (1 KiB reserved per CTA by the driver)
 
+LexTileGeom lex_tile_geom(const Geometry& g, int rt) {
+    LexTileGeom t{};
+    t.G = g.G; t.code_bytes = g.code_bytes; t.n_chunks = g.S_pad / kLT_SC; t.rt = rt;
+    t.wide = rt > 254 ? 1 : 0;
+    t.tcode_bytes = t.wide ? 2 : 1;
+    t.pblock_bytes = kLT_PT * kLT_SC * (t.tcode_bytes + 2 * g.G);
+    t.qoff_bytes = t.wide ? kLT_SC * kLT_WideSliceBytes
+                          : (int)round_up((int64_t)kLT_SC * (rt + 1) * 4, 16);   // rt buckets + one empty bucket (clamp target) per slice
+    t.qblock_stride = t.qoff_bytes + kLT_SC * kLT_QT * lt_entry_words(g.G) * 4;
+    t.stage_bytes = (int)round_up(t.pblock_bytes, 128) + (int)round_up(t.qblock_stride, 128);
+    const size_t fixed = (size_t)kLT_QT * kLT_PT * 4 + 128 + kLT_StaticSmem;
+    t.n_stages = kLT_MaxStages;
+    while (t.n_stages > 2 && fixed + (size_t)t.n_stages * t.stage_bytes > kLT_SmemBudget) --t.n_stages;
+    return t;
+}
+
+size_t lex_tile_smem_bytes(const LexTileGeom& t) {
+    return (size_t)kLT_QT * kLT_PT * 4 + (size_t)t.n_stages * t.stage_bytes + 128;
+}
+
 bool lex_tile_supported(const Geometry& g, int rt) {
-    if (g.S_pad <= 0 || g.S_pad % kLT_SC != 0 || rt < 1 || rt > 254 || g.G > 8) return false;
+    if (g.S_pad <= 0 || g.S_pad % kLT_SC != 0 || rt < 1 || rt > 65534 || g.G > 8) return false;
+    if (rt > 254 && g.code_bytes != 2) return false;
     return lex_tile_smem_bytes(lex_tile_geom(g, rt)) + kLT_StaticSmem <= kLT_SmemBudget;
 }
 
@@ -122,6 +137,72 @@ lex_tile_prep_kernel(const __half* __restrict__ q_lex16, const CodeT* __restrict
         qblock_bytes[(size_t)qt * n_chunks + chunk] = ((uint32_t)qoff_bytes + total_s * (uint32_t)EW * 4u + 15u) & ~15u;
 }
 
+// wide layout: one warp per (chunk, query tile); lane j < 4 builds slice j sequentially (64 queries, a handful of codes)
+template <typename CodeT>
+__global__ void __launch_bounds__(32)
+lex_tile_prep_wide_kernel(const __half* __restrict__ q_lex16, const CodeT* __restrict__ q_code, int n_queries, int S_pad, int G,
+                          int qoff_bytes, int qblock_stride, uint8_t* __restrict__ qblocks, uint32_t* __restrict__ qblock_bytes) {
+    __shared__ uint32_t dcode[kLT_SC][kLT_QT], dcnt[kLT_SC][kLT_QT], dpos[kLT_SC][kLT_QT];
+    __shared__ uint32_t nd[kLT_SC], tot[kLT_SC];
+    const int chunk = blockIdx.x, qt = blockIdx.y;
+    const int n_chunks = gridDim.x;
+    const int q0 = qt * kLT_QT;
+    const int nq = min(kLT_QT, n_queries - q0);
+    const int EW = lt_entry_words(G);
+    const int j = threadIdx.x;
+    uint8_t* blk = qblocks + ((size_t)qt * n_chunks + chunk) * qblock_stride;
+    if (j < kLT_SC) {
+        const int s = chunk * kLT_SC + j;
+        uint32_t n = 0, total = 0;
+        for (int q = 0; q < nq; ++q) {                 // distinct codes of the slice, in order of first appearance
+            const uint32_t code = q_code[(size_t)(q0 + q) * S_pad + s];
+            if (code > CodeTraits<uint16_t>::kMax) continue;
+            uint32_t i = 0;
+            while (i < n && dcode[j][i] != code) ++i;
+            if (i == n) { dcode[j][n] = code; dcnt[j][n] = 0; ++n; }
+            ++dcnt[j][i]; ++total;
+        }
+        nd[j] = n; tot[j] = total;
+    }
+    __syncwarp();
+    if (j < kLT_SC) {
+        const int s = chunk * kLT_SC + j;
+        uint32_t base = 0;
+        for (int jj = 0; jj < j; ++jj) base += tot[jj];
+        uint32_t* hdr = (uint32_t*)(blk + (size_t)j * kLT_WideSliceBytes);
+        hdr[0] = nd[j];
+        uint32_t run = base;
+        for (uint32_t i = 0; i < nd[j]; ++i) {
+            hdr[4 + 2 * i] = dcode[j][i];
+            hdr[4 + 2 * i + 1] = (run * (uint32_t)EW * 4u) | (dcnt[j][i] << 16);
+            dpos[j][i] = run; run += dcnt[j][i];
+        }
+        uint32_t* ent = (uint32_t*)(blk + qoff_bytes);
+        for (int q = 0; q < nq; ++q) {                 // placement in query order: buckets stay ordered by query id
+            const uint32_t code = q_code[(size_t)(q0 + q) * S_pad + s];
+            if (code > CodeTraits<uint16_t>::kMax) continue;
+            uint32_t i = 0;
+            while (dcode[j][i] != code) ++i;
+            const uint32_t pos = dpos[j][i]++;
+            const __half* v = q_lex16 + ((size_t)(q0 + q) * S_pad + s) * G;
+            uint32_t* e = ent + (size_t)pos * EW;
+            e[0] = (uint32_t)q * (uint32_t)(kLT_PT * 4);
+            for (int w = 1; w < EW; ++w) {
+                const int g0 = 2 * (w - 1), g1 = g0 + 1;
+                const uint32_t lo = g0 < G ? __half_as_ushort(v[g0]) : 0u;
+                const uint32_t hi = g1 < G ? __half_as_ushort(v[g1]) : 0u;
+                e[w] = lo | (hi << 16);
+            }
+        }
+    }
+    __syncwarp();
+    if (j == 0) {
+        uint32_t total = 0;
+        for (int jj = 0; jj < kLT_SC; ++jj) total += tot[jj];
+        qblock_bytes[(size_t)qt * n_chunks + chunk] = ((uint32_t)qoff_bytes + total * (uint32_t)EW * 4u + 15u) & ~15u;
+    }
+}
+
 // f32 += f16 * f16 with independent half selection of both operands
 template <bool AHI, bool BHI>
 __device__ __forceinline__ float fma_h_sel(uint32_t a, uint32_t b, float c) {
@@ -156,7 +237,7 @@ struct LexTileArgs {
     long long row_begin, row_end;      // rows handled by this launch (row_begin multiple of the tile size)
     long long n_rows;
     int n_tiles;                       // tiles in [row_begin, row_end)
-    int n_chunks, rt;
+    int n_chunks, rt, n_stages;
     int pblock_bytes, qoff_bytes, qblock_stride, stage_bytes, pblock_smem;
     int n_qtiles;                      // query tiles in flight
     int n_queries;                     // valid in-flight queries (slots)
@@ -179,7 +260,8 @@ __device__ __forceinline__ void lds_entry(uint32_t addr, uint32_t act, uint32_t 
         asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
             : "=r"(ew[0]), "=r"(ew[1]), "=r"(ew[2]), "=r"(ew[3]) : "r"(addr), "r"(act));
     else
-        asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %7, 0;\n\t@q ld.shared.v2.u32 {%0, %1}, [%6];\n\t@q ld.shared.v4.u32 {%2, %3, %4, %5}, [%6+8];\n\t}"
+        asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %7, 0;\n\t@q ld.shared.v2.u32 {%0, %1}, [%6];\n\t@q ld.shared.v2.u32 {%2, %3}, [%6+8];\n\t"
+            "@q ld.shared.v2.u32 {%4, %5}, [%6+16];\n\t}"      // 24-byte entries are only 8-byte aligned
             : "=r"(ew[0]), "=r"(ew[1]), "=r"(ew[2]), "=r"(ew[3]), "=r"(ew[4]), "=r"(ew[5]) : "r"(addr), "r"(act));
 }
 __device__ __forceinline__ uint32_t lds_u32_pred(uint32_t addr, uint32_t act) {
@@ -225,11 +307,11 @@ struct LexLevel {                       // operands of one match level of one th
     uint32_t act;
 };
 
-template <int G>
+template <int G, bool WIDE>
 __global__ void __launch_bounds__(kLT_Threads, kLT_CtasPerSm) lex_tile_kernel(const __grid_constant__ LexTileArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t full_bar[kLT_Stages];
-    __shared__ __align__(8) uint64_t empty_bar[kLT_Stages];
+    __shared__ __align__(8) uint64_t full_bar[kLT_MaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kLT_MaxStages];
     __shared__ __align__(16) float tau_s[kLT_QT];
 
     constexpr int EW = lt_entry_words(G);
@@ -245,7 +327,7 @@ __global__ void __launch_bounds__(kLT_Threads, kLT_CtasPerSm) lex_tile_kernel(co
     const int nq = min(kLT_QT, a.n_queries - q0);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kLT_Stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kLT_PT / 32); }
+        for (int s = 0; s < a.n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kLT_PT / 32); }
         mbar_fence_init();
     }
     if (threadIdx.x < kLT_QT) tau_s[threadIdx.x] = threadIdx.x < nq ? a.tau[q0 + threadIdx.x] : INFINITY;
@@ -266,7 +348,7 @@ __global__ void __launch_bounds__(kLT_Threads, kLT_CtasPerSm) lex_tile_kernel(co
                     mbar_arrive_expect_tx(&full_bar[s], (uint32_t)a.pblock_bytes + qb);
                     bulk_g2s(dst, ptile + (size_t)c * a.pblock_bytes, (uint32_t)a.pblock_bytes, &full_bar[s]);
                     bulk_g2s(dst + a.pblock_smem, a.qblocks + ((size_t)qt * a.n_chunks + c) * a.qblock_stride, qb, &full_bar[s]);
-                    if (++s == kLT_Stages) { s = 0; ph ^= 1u; }
+                    if (++s == a.n_stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -305,24 +387,44 @@ __global__ void __launch_bounds__(kLT_Threads, kLT_CtasPerSm) lex_tile_kernel(co
             mbar_wait(&full_bar[s], ph);
             const uint8_t* st = stages + (size_t)s * a.stage_bytes;
             const uint32_t st_s = stages_s + (uint32_t)s * (uint32_t)a.stage_bytes;
-            const uint32_t* tab = (const uint32_t*)(st + a.pblock_smem);
-            const uint32_t cw = *(const uint32_t*)(st + (size_t)p * kLT_SC);       // my four slice codes (one byte each)
-
             // ---- bucket lookups (branch-free) ----
-            // The table has rt + 1 words per slice (the last one an empty bucket), so clamping the code to rt
-            // resolves CODE_EMPTY without a branch.  ea[j] / pa[j] are the shared addresses a match of slice j reads:
-            // entry of this thread's l-th match = ea[slice(l)] + l * ES.
+            // narrow: the table has rt + 1 words per slice (the last one an empty bucket), so clamping the code to rt
+            // resolves CODE_EMPTY without a branch.  wide: compare against the slice's distinct query codes (warp-uniform loop).
+            // ea[j] / pa[j] are the shared addresses a match of slice j reads: entry of this thread's l-th match =
+            // ea[slice(l)] + l * ES.
             uint32_t ea[kLT_SC], pa[kLT_SC], cum[kLT_SC + 1];
             const uint32_t ent_s = st_s + (uint32_t)a.pblock_smem + (uint32_t)a.qoff_bytes;
-            const uint32_t pv_s = st_s + (uint32_t)(kLT_PT * kLT_SC) + (uint32_t)p * (uint32_t)(G * 2);
+            const uint32_t pv_s = st_s + (uint32_t)(kLT_PT * kLT_SC * (WIDE ? 2 : 1)) + (uint32_t)p * (uint32_t)(G * 2);
+            uint32_t tw[kLT_SC];
+            if constexpr (WIDE) {
+                const uint2 cw = *(const uint2*)(st + (size_t)p * (kLT_SC * 2));        // my four slice codes (16 bits each)
+#pragma unroll
+                for (int j = 0; j < kLT_SC; ++j) {
+                    const uint32_t code = ((j < 2 ? cw.x : cw.y) >> (16 * (j & 1))) & 0xFFFFu;
+                    const uint32_t* hdr = (const uint32_t*)(st + a.pblock_smem + j * kLT_WideSliceBytes);
+                    const uint32_t n = hdr[0];
+                    uint32_t w = 0;
+                    for (uint32_t i = 0; i < n; ++i) {
+                        const uint2 pr = *(const uint2*)(hdr + 4 + 2 * i);
+                        w = pr.x == code ? pr.y : w;
+                    }
+                    tw[j] = w;
+                }
+            } else {
+                const uint32_t* tab = (const uint32_t*)(st + a.pblock_smem);
+                const uint32_t cw = *(const uint32_t*)(st + (size_t)p * kLT_SC);       // my four slice codes (one byte each)
+#pragma unroll
+                for (int j = 0; j < kLT_SC; ++j) {
+                    const uint32_t code = min((cw >> (8 * j)) & 0xFFu, (uint32_t)a.rt);
+                    tw[j] = tab[j * per + code];
+                }
+            }
             cum[0] = 0;
 #pragma unroll
             for (int j = 0; j < kLT_SC; ++j) {
-                const uint32_t code = min((cw >> (8 * j)) & 0xFFu, (uint32_t)a.rt);
-                const uint32_t w = tab[j * per + code];
-                ea[j] = ent_s + (w & 0xFFFFu) - cum[j] * ES;
+                ea[j] = ent_s + (tw[j] & 0xFFFFu) - cum[j] * ES;
                 pa[j] = pv_s + (uint32_t)(j * kLT_PT * G * 2);
-                cum[j + 1] = cum[j] + (w >> 16);
+                cum[j + 1] = cum[j] + (tw[j] >> 16);
             }
             const uint32_t mine = cum[kLT_SC];
             const uint32_t levels = __reduce_max_sync(0xFFFFFFFFu, mine);
@@ -355,7 +457,7 @@ __global__ void __launch_bounds__(kLT_Threads, kLT_CtasPerSm) lex_tile_kernel(co
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
-            if (++s == kLT_Stages) { s = 0; ph ^= 1u; }
+            if (++s == a.n_stages) { s = 0; ph ^= 1u; }
         }
         // admission filter
         if (row_ok) {
@@ -390,6 +492,13 @@ int launch_lex_tile_prep(const dhr_index* h, const LexTileGeom& t, const void* q
     const int n_qtiles = (n_queries + kLT_QT - 1) / kLT_QT;
     if (n_qtiles == 0) return DHR_OK;
     dim3 grid((unsigned)t.n_chunks, (unsigned)n_qtiles);
+    if (t.wide) {
+        if (g.code_bytes != 2) return DHR_ERR_UNSUPPORTED;
+        lex_tile_prep_wide_kernel<uint16_t><<<grid, 32, 0, st>>>((const __half*)q_lex16, (const uint16_t*)q_code, n_queries, g.S_pad, g.G,
+                                                                 t.qoff_bytes, t.qblock_stride, qblocks, qblock_bytes);
+        DHR_CUDA(cudaGetLastError());
+        return DHR_OK;
+    }
     const size_t smem = (size_t)2 * kLT_SC * (t.rt + 1) * sizeof(uint32_t);
     if (g.code_bytes == 1)
         lex_tile_prep_kernel<uint8_t><<<grid, 256, smem, st>>>((const __half*)q_lex16, (const uint8_t*)q_code, n_queries, g.S_pad, g.G,
@@ -401,9 +510,9 @@ int launch_lex_tile_prep(const dhr_index* h, const LexTileGeom& t, const void* q
     return DHR_OK;
 }
 
-template <int G>
+template <int G, bool WIDE>
 static int launch_lex_tile_t(const dhr_index* h, const LexTileArgs& a, size_t smem, cudaStream_t st) {
-    auto kern = lex_tile_kernel<G>;
+    auto kern = lex_tile_kernel<G, WIDE>;
     DHR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_q = h->num_sms * kLT_CtasPerSm / a.n_qtiles;
     if (per_q < 1) per_q = 1;
@@ -413,16 +522,17 @@ static int launch_lex_tile_t(const dhr_index* h, const LexTileArgs& a, size_t sm
     return DHR_OK;
 }
 
+template <bool WIDE>
 static int launch_lex_tile_g(const dhr_index* h, const LexTileArgs& a, size_t smem, cudaStream_t st) {
     switch (h->g.G) {
-        case 1: return launch_lex_tile_t<1>(h, a, smem, st);
-        case 2: return launch_lex_tile_t<2>(h, a, smem, st);
-        case 3: return launch_lex_tile_t<3>(h, a, smem, st);
-        case 4: return launch_lex_tile_t<4>(h, a, smem, st);
-        case 5: return launch_lex_tile_t<5>(h, a, smem, st);
-        case 6: return launch_lex_tile_t<6>(h, a, smem, st);
-        case 7: return launch_lex_tile_t<7>(h, a, smem, st);
-        case 8: return launch_lex_tile_t<8>(h, a, smem, st);
+        case 1: return launch_lex_tile_t<1, WIDE>(h, a, smem, st);
+        case 2: return launch_lex_tile_t<2, WIDE>(h, a, smem, st);
+        case 3: return launch_lex_tile_t<3, WIDE>(h, a, smem, st);
+        case 4: return launch_lex_tile_t<4, WIDE>(h, a, smem, st);
+        case 5: return launch_lex_tile_t<5, WIDE>(h, a, smem, st);
+        case 6: return launch_lex_tile_t<6, WIDE>(h, a, smem, st);
+        case 7: return launch_lex_tile_t<7, WIDE>(h, a, smem, st);
+        case 8: return launch_lex_tile_t<8, WIDE>(h, a, smem, st);
         default: return DHR_ERR_UNSUPPORTED;
     }
 }
@@ -435,7 +545,7 @@ int launch_lex_tile(const dhr_index* h, const LexTileGeom& t, const uint8_t* qbl
     a.lext = h->lext; a.qblocks = qblocks; a.qblock_bytes = qblock_bytes;
     a.row_begin = row_begin; a.row_end = row_end; a.n_rows = h->n_rows;
     a.n_tiles = (int)((row_end - row_begin / kLT_PT * kLT_PT + kLT_PT - 1) / kLT_PT);
-    a.n_chunks = t.n_chunks; a.rt = t.rt;
+    a.n_chunks = t.n_chunks; a.rt = t.rt; a.n_stages = t.n_stages;
     a.pblock_bytes = t.pblock_bytes; a.qoff_bytes = t.qoff_bytes; a.qblock_stride = t.qblock_stride;
     a.stage_bytes = t.stage_bytes; a.pblock_smem = (int)round_up(t.pblock_bytes, 128);
     a.n_qtiles = (n_queries + kLT_QT - 1) / kLT_QT;
@@ -443,7 +553,7 @@ int launch_lex_tile(const dhr_index* h, const LexTileGeom& t, const uint8_t* qbl
     a.scratch = scratch; a.scratch_slots = scratch_slots; a.scratch_row0 = scratch_row0;
     a.tau = tk.tau; a.cnt = tk.cnt; a.cand_score = tk.cand_score; a.cand_row = tk.cand_row; a.cap = cap;
     if (!h->lext) return DHR_ERR_STATE;
-    return launch_lex_tile_g(h, a, lex_tile_smem_bytes(t), st);
+    return t.wide ? launch_lex_tile_g<true>(h, a, lex_tile_smem_bytes(t), st) : launch_lex_tile_g<false>(h, a, lex_tile_smem_bytes(t), st);
 }
 
 }  // namespace dhr

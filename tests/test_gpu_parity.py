@@ -324,7 +324,10 @@ def test_dense_tile_grid_bit_exact_and_ties():
 
 @pytest.mark.parametrize('shape', [(128, 6, 768, 39, np.uint16), (768, 1, 128, 39, np.uint8), (64, 3, 0, 200, np.uint16),
                                    (40, 1, 32, 39, np.int8), (24, 8, 40, 39, np.uint16), (16, 5, 8, 39, np.int32),
-                                   (16, 7, 100, 39, np.uint8), (48, 2, 16, 100, np.int16), (24, 4, 24, 39, np.uint8)])
+                                   (16, 7, 100, 39, np.uint8), (48, 2, 16, 100, np.int16), (24, 4, 24, 39, np.uint8),
+                                   # index range > 254: 16-bit codes in the tiled copy, distinct-code lookup ("wide" layout)
+                                   (64, 3, 0, 3466, np.uint16), (32, 6, 64, 300, np.int16), (128, 1, 0, 1000, np.int16),
+                                   (20, 2, 24, 40000, np.int32), (16, 5, 16, 500, np.uint16)])
 def test_tile_path_many_queries(shape):
     """Tile kernels with several query tiles in flight (300 queries -> 3 tiles of 128, two super-batches)."""
     S, G, Cd, R, cdt = shape
@@ -340,3 +343,34 @@ def test_tile_path_many_queries(shape):
     sel = np.r_[0:8, 120:136, 250:260, 292:300]
     sub['q_vals'], sub['q_idx'] = case['q_vals'][sel], case['q_idx'][sel]
     assert_matches_oracle(sub, s[sel], r[sel], c[sel], k)
+
+
+@pytest.mark.parametrize('shape', [(256, 3, 3466), (768, 1, 3466)])
+def test_tile_path_bm25_like(shape):
+    """Densified-BM25 shape (BASELINE config 3): 5 % of the corpus slices set, <= 8 query slices set with small-integer
+    term frequencies (exact ties), idx up to 3465 -> wide tile layout; exact arithmetic -> bit-exact against the oracle."""
+    S, G, R = shape
+    rng = np.random.default_rng(77 + S)
+    n, nq, k = 40000, 70, 100
+    cv = np.zeros((n, S, G), np.float32)
+    ci = np.zeros((n, S), np.int64)
+    on = rng.random((n, S)) < 0.05
+    cv[on] = rng.integers(32, 512, size=(int(on.sum()), G)).astype(np.float32) / 64.0
+    ci[on] = rng.integers(0, R, size=int(on.sum()))
+    qv = np.zeros((nq, S, G), np.float32)
+    qi = np.zeros((nq, S), np.int64)
+    for q in range(nq):
+        sl = rng.choice(S, size=rng.integers(1, 9), replace=False)
+        qv[q, sl] = rng.integers(1, 4, size=(len(sl), G)).astype(np.float32)
+        # reuse indices that occur in the corpus so that matches exist
+        qi[q, sl] = ci[rng.integers(0, n, size=len(sl)), sl]
+    case = dict(S=S, G=G, C=0, c_vals=cv.reshape(n, S * G).astype(np.float16), c_idx=ci.astype(np.uint16),
+                q_vals=qv.reshape(nq, S * G), q_idx=qi.astype(np.int16))
+    with GipIndex.from_arrays(case['c_vals'], case['c_idx'], n_slices=S, group=G) as ix:
+        configure(ix, 'tile')
+        s, r, c = ix.search(case['q_vals'], case['q_idx'], k)
+        assert ix.stats()['scan_variant'] == 3, 'tile path not taken'
+        configure(ix, 'scan1', 8)
+        s2, r2, c2 = ix.search(case['q_vals'], case['q_idx'], k)
+    assert_matches_oracle(case, s, r, c, k, exact=True)
+    assert np.array_equal(s, s2) and np.array_equal(r, r2)
