@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'build')
 LIB = os.path.join(HERE, 'lib', 'libdhr_b200.so')
-SOURCES = ['index.cu', 'search.cu', 'scan_dispatch.cu', 'topk.cu', 'dense_tile.cu', 'lex_tile.cu', 'densify.cu']
+SOURCES = ['index.cu', 'search.cu', 'scan_dispatch.cu', 'topk.cu', 'dense_tile.cu', 'lex_tile.cu', 'densify.cu', 'trec.cu']
 GROUPS = [1, 2, 3, 4, 5, 6, 7, 8]          # scan_inst.cu is compiled once per G (values per slice)
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 

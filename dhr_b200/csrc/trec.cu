@@ -1,0 +1,148 @@
+// trec.cu -- host-side TREC run writer: replaces the Python string formatting of
+// castorini/dhr retrieval/gip_retrieval.py:329-342 (7 M lines at MS MARCO dev scale).
+//
+//   "{qid} Q0 {docid} {rank+1} {score} {run_name}\n"
+// * rows whose docid equals the query id are skipped and ranks are NOT renumbered (:339-341);
+// * {score} is Python's repr() of the float that `.tolist()` made from the fp32 score (:158-159), i.e. the
+//   shortest round-trip decimal of the double with repr's fixed/exponent rule -- py_float_repr below.
+// Queries are formatted by a pool of threads into per-thread buffers and written in query order.
+#include <charconv>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/dhr_b200.h"
+
+namespace {
+
+// CPython float_repr_style 'short', format code 'r' (Python/pystrtod.c format_float_short): shortest digits that
+// round-trip; exponent form when decpt > 16 or decpt < -3; at least two exponent digits; ".0" added to integers.
+size_t py_float_repr(double x, char* out) {
+    if (std::isnan(x)) { memcpy(out, "nan", 3); return 3; }
+    if (std::isinf(x)) { if (x < 0) { memcpy(out, "-inf", 4); return 4; } memcpy(out, "inf", 3); return 3; }
+    char sci[64];
+    auto r = std::to_chars(sci, sci + sizeof(sci), x, std::chars_format::scientific);   // [-]d[.ddd]e[+-]XX, shortest
+    *r.ptr = 0;
+    const char* p = sci;
+    char* o = out;
+    if (*p == '-') { *o++ = '-'; ++p; }
+    char digits[32]; int nd = 0;
+    while (*p && *p != 'e') { if (*p != '.') digits[nd++] = *p; ++p; }
+    const int exp10 = atoi(p + 1);
+    const int decpt = exp10 + 1;                       // value = 0.d1d2... x 10^decpt
+    if (decpt > 16 || decpt < -3) {
+        *o++ = digits[0];
+        if (nd > 1) { *o++ = '.'; memcpy(o, digits + 1, nd - 1); o += nd - 1; }
+        *o++ = 'e';
+        int e = decpt - 1;
+        *o++ = e < 0 ? '-' : '+';
+        if (e < 0) e = -e;
+        char eb[8]; int ne = 0;
+        do { eb[ne++] = (char)('0' + e % 10); e /= 10; } while (e);
+        if (ne < 2) eb[ne++] = '0';
+        while (ne) *o++ = eb[--ne];
+    } else if (decpt <= 0) {
+        *o++ = '0'; *o++ = '.';
+        for (int i = 0; i < -decpt; ++i) *o++ = '0';
+        memcpy(o, digits, nd); o += nd;
+    } else if (decpt >= nd) {
+        memcpy(o, digits, nd); o += nd;
+        for (int i = nd; i < decpt; ++i) *o++ = '0';
+        *o++ = '.'; *o++ = '0';
+    } else {
+        memcpy(o, digits, decpt); o += decpt;
+        *o++ = '.';
+        memcpy(o, digits + decpt, nd - decpt); o += nd - decpt;
+    }
+    return (size_t)(o - out);
+}
+
+struct IdTable {                       // ids as int64 values or as strings packed in one buffer with [n + 1] offsets
+    const int64_t* ints; const char* str; const int64_t* off;
+    size_t put(int64_t i, char* out) const {
+        if (ints) { auto r = std::to_chars(out, out + 24, ints[i]); return (size_t)(r.ptr - out); }
+        const size_t n = (size_t)(off[i + 1] - off[i]);
+        memcpy(out, str + off[i], n);
+        return n;
+    }
+    size_t max_len(int64_t i) const { return ints ? 24 : (size_t)(off[i + 1] - off[i]); }
+};
+
+bool ids_equal(const IdTable& a, int64_t i, const IdTable& b, int64_t j) {
+    if (a.ints && b.ints) return a.ints[i] == b.ints[j];
+    char ba[32], bb[32];
+    const char* pa; const char* pb; size_t na, nb;
+    if (a.ints) { na = a.put(i, ba); pa = ba; } else { pa = a.str + a.off[i]; na = (size_t)(a.off[i + 1] - a.off[i]); }
+    if (b.ints) { nb = b.put(j, bb); pb = bb; } else { pb = b.str + b.off[j]; nb = (size_t)(b.off[j + 1] - b.off[j]); }
+    return na == nb && memcmp(pa, pb, na) == 0;
+}
+
+}  // namespace
+
+extern "C" int dhr_write_trec(const char* path, int append, int n_queries, int k, const int32_t* counts, const int64_t* rows,
+                              const float* scores, const int64_t* qid_int, const char* qid_str, const int64_t* qid_off,
+                              int64_t n_docids, const int64_t* docid_int, const char* docid_str, const int64_t* docid_off,
+                              int skip_equal, const char* run_name, int n_threads, int64_t* lines_written) {
+    if (!path || n_queries < 0 || k < 0 || !rows || !scores || !run_name) return DHR_ERR_INVALID;
+    if ((!qid_int && !(qid_str && qid_off)) || (!docid_int && !(docid_str && docid_off))) return DHR_ERR_INVALID;
+    const IdTable qt{qid_int, qid_str, qid_off}, dt{docid_int, docid_str, docid_off};
+    const size_t run_len = strlen(run_name);
+    if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+    if (n_threads <= 0) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    if (n_threads > n_queries) n_threads = n_queries > 0 ? n_queries : 1;
+    std::vector<std::string> bufs((size_t)n_threads);
+    std::vector<int64_t> lines((size_t)n_threads, 0);
+    std::vector<int> bad((size_t)n_threads, 0);
+    auto work = [&](int t) {
+        const int q0 = (int)((int64_t)n_queries * t / n_threads), q1 = (int)((int64_t)n_queries * (t + 1) / n_threads);
+        std::string& b = bufs[(size_t)t];
+        b.reserve((size_t)(q1 - q0) * (size_t)k * 48);
+        char line[1024];
+        for (int q = q0; q < q1; ++q) {
+            const int n = counts ? counts[q] : k;
+            char qbuf[512];
+            if (qt.max_len(q) > sizeof(qbuf)) { bad[(size_t)t] = 1; return; }
+            const size_t ql = qt.put(q, qbuf);
+            for (int r = 0; r < n && r < k; ++r) {
+                const int64_t row = rows[(size_t)q * k + r];
+                if (row < 0) continue;                                   // padding (k > rows in the shard)
+                if (row >= n_docids || dt.max_len(row) > 400) { bad[(size_t)t] = 1; return; }
+                if (skip_equal && ids_equal(dt, row, qt, q)) continue;   // gip_retrieval.py:340
+                char* o = line;
+                memcpy(o, qbuf, ql); o += ql;
+                memcpy(o, " Q0 ", 4); o += 4;
+                o += dt.put(row, o);
+                *o++ = ' ';
+                o = std::to_chars(o, o + 12, r + 1).ptr;
+                *o++ = ' ';
+                o += py_float_repr((double)scores[(size_t)q * k + r], o);
+                *o++ = ' ';
+                if (run_len > 256) { bad[(size_t)t] = 1; return; }
+                memcpy(o, run_name, run_len); o += run_len;
+                *o++ = '\n';
+                b.append(line, (size_t)(o - line));
+                ++lines[(size_t)t];
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    for (int t = 0; t < n_threads; ++t) if (bad[(size_t)t]) return DHR_ERR_INVALID;
+    FILE* f = fopen(path, append ? "ab" : "wb");
+    if (!f) return DHR_ERR_INVALID;
+    int64_t total = 0;
+    bool ok = true;
+    for (int t = 0; t < n_threads; ++t) {
+        if (!bufs[(size_t)t].empty() && fwrite(bufs[(size_t)t].data(), 1, bufs[(size_t)t].size(), f) != bufs[(size_t)t].size()) ok = false;
+        total += lines[(size_t)t];
+    }
+    if (fclose(f) != 0) ok = false;
+    if (lines_written) *lines_written = total;
+    return ok ? DHR_OK : DHR_ERR_INVALID;
+}

@@ -15,12 +15,14 @@ Differences, all deliberate:
 from __future__ import annotations
 
 import argparse
+import ctypes
 import os
 import pickle
 import time
 
 import numpy as np
 
+from . import _cabi
 from .index import GipIndex
 
 try:
@@ -162,8 +164,60 @@ def shard_bounds(n_docs, total_shrad, shrad):
     return lo, hi
 
 
+def _id_table(ids):
+    """ids (list / array of ints or of strs) -> (kind, int64 array | None, packed utf-8 bytes | None, offsets | None)."""
+    if isinstance(ids, np.ndarray) and ids.dtype.kind in 'iu':
+        return 'int', np.ascontiguousarray(ids, dtype=np.int64), None, None
+    ids = list(ids)
+    if all(isinstance(x, (int, np.integer)) and not isinstance(x, (bool, np.bool_)) for x in ids):
+        try:
+            return 'int', np.asarray(ids, dtype=np.int64), None, None
+        except OverflowError:
+            return None, None, None, None
+    if all(isinstance(x, str) for x in ids):
+        enc = [x.encode('utf-8') for x in ids]
+        off = np.zeros(len(enc) + 1, np.int64)
+        np.cumsum([len(b) for b in enc], out=off[1:])
+        return 'str', None, b''.join(enc), off
+    return None, None, None, None
+
+
+def write_trec_arrays(path, qids, scores, rows, counts, docids, run_name, append=False, n_threads=0):
+    """TREC run from [Q,k] arrays through the C++ writer (dhr_write_trec, csrc/trec.cu); rows index `docids`
+    (shard-local), negative rows are padding.  Returns the number of lines written, or None when the id types are not
+    plain ints / strs (the caller then formats in Python)."""
+    qk, qi, qs, qo = _id_table(qids)
+    dk, di, ds, do = _id_table(docids)
+    if qk is None or dk is None:
+        return None
+    scores = np.ascontiguousarray(scores, dtype=np.float32)
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    nq, k = rows.shape
+    cnt = None if counts is None else np.ascontiguousarray(counts, dtype=np.int32)
+    ptr = lambda a: None if a is None else a.ctypes.data
+    n_lines = ctypes.c_int64(0)
+    _cabi.check(_cabi.lib().dhr_write_trec(
+        os.fsencode(path), 1 if append else 0, nq, k, ptr(cnt), ptr(rows), ptr(scores), ptr(qi), qs, ptr(qo),
+        len(docids), ptr(di), ds, ptr(do), 1 if qk == dk else 0, str(run_name).encode('utf-8'), int(n_threads),
+        ctypes.byref(n_lines)), 'dhr_write_trec')
+    return n_lines.value
+
+
 def write_trec(path, results, scores, docids, run_name):
-    """gip_retrieval.py:329-342: rows whose docid equals the query id are skipped, ranks are NOT renumbered."""
+    """gip_retrieval.py:329-342: rows whose docid equals the query id are skipped, ranks are NOT renumbered.
+    The per-line formatting runs in C++ (same text, including Python's float repr); exotic id types fall back to the
+    reference's Python loop."""
+    qids = list(results.keys())
+    kmax = max((len(results[q]) for q in qids), default=0)
+    if qids and kmax > 0:
+        rows = np.full((len(qids), kmax), -1, np.int64)
+        sc = np.zeros((len(qids), kmax), np.float32)
+        for i, q in enumerate(qids):
+            n = len(results[q])
+            rows[i, :n] = results[q]
+            sc[i, :n] = scores[q]
+        if write_trec_arrays(path, qids, sc, rows, None, docids, run_name) is not None:
+            return
     with open(path, 'w') as fout:
         for query_id in results:
             result, score = results[query_id], scores[query_id]

@@ -148,6 +148,19 @@ int dhr_densify(int device, int batch, int vocab, int dims, int remove_dims, int
                 int64_t reps_row_stride, void* out_vals_f16, int64_t out_val_row_stride, uint8_t* out_idx,
                 int64_t out_idx_row_stride, void* stream);
 
+/* ---- next row: TREC run writer on the host -----------------------------------
+ * Replaces the Python formatting loop of retrieval/gip_retrieval.py:329-342: for query q and rank r writes
+ *   "{qid} Q0 {docid} {r+1} {score} {run_name}\n"
+ * with {score} = Python's repr() of the fp32 score widened to double (what `.tolist()` + str.format produce).
+ * rows [Q,k] index the docid table (LOCAL rows of the shard; < 0 = padding, skipped); counts [Q] may be NULL (= k).
+ * Ids are either int64 arrays or strings packed in one buffer with [n + 1] byte offsets (exactly one form per table).
+ * skip_equal != 0 drops lines whose docid equals the query id without renumbering the ranks (:340).
+ * HOST pointers only; n_threads <= 0 uses all cores.  The file is created (append = 0) or appended to. */
+int dhr_write_trec(const char* path, int append, int n_queries, int k, const int32_t* counts, const int64_t* rows,
+                   const float* scores, const int64_t* qid_int, const char* qid_str, const int64_t* qid_off,
+                   int64_t n_docids, const int64_t* docid_int, const char* docid_str, const int64_t* docid_off,
+                   int skip_equal, const char* run_name, int n_threads, int64_t* lines_written);
+
 #ifdef __cplusplus
 }
 #endif

@@ -155,3 +155,44 @@ def test_merge_splits_matches_reference_semantics(tmp_path):
     with open(out, 'rb') as f:
         v, i, ids = pickle.load(f)
     assert np.array_equal(v, g['c_vals']) and np.array_equal(i, g['c_idx']) and ids == [str(x) for x in g['docids']]
+
+
+def _py_write_trec(path, results, scores, docids, run_name):
+    """the reference's formatting loop (gip_retrieval.py:329-342), kept here as the expected text"""
+    with open(path, 'w') as fout:
+        for query_id in results:
+            for rank, docidx in enumerate(results[query_id]):
+                if docids[docidx] != query_id:
+                    fout.write('{} Q0 {} {} {} {}\n'.format(query_id, docids[docidx], rank + 1, scores[query_id][rank], run_name))
+
+
+@pytest.mark.parametrize('ids', ['int', 'str', 'mixed'])
+def test_trec_writer_matches_python_formatting(tmp_path, ids):
+    """C++ TREC writer (csrc/trec.cu): byte-identical to the reference's Python loop, including float repr, the
+    docid == qid skip rule without renumbering, and ragged per-query lengths."""
+    from dhr_b200.gip_retrieval import write_trec
+    rng = np.random.default_rng(5)
+    n_docs, nq, k = 500, 37, 60
+    special = np.array([0.0, -0.0, 1.0, 100.0, 1e-5, 9.999999e-5, 1e-4, 123456.789, 1e16, 9.9e15, 3.4028235e38, 1.17549435e-38,
+                        1e-45, 0.1, 0.3, 16777216.0, 2.5e-7, -7.25, 65504.0, 1e7], np.float32)
+    if ids == 'int':
+        docids = list(range(1000, 1000 + n_docs)); qids = [int(x) for x in rng.choice(np.arange(900, 1600), nq, replace=False)]
+    elif ids == 'str':
+        docids = ['D%d' % i for i in range(n_docs)]; qids = ['D%d' % i for i in rng.choice(n_docs * 2, nq, replace=False)]
+    else:
+        docids = list(range(n_docs)); qids = [str(i) for i in range(nq)]        # int docids vs str qids never compare equal
+    results, scores = {}, {}
+    for q in qids:
+        n = int(rng.integers(1, k + 1))
+        rows = rng.choice(n_docs, n, replace=False)
+        if ids != 'mixed' and q in docids and rng.random() < 0.8:
+            rows[rng.integers(0, n)] = docids.index(q)                             # force the skip rule
+        sc = np.sort(np.concatenate([rng.standard_normal(n).astype(np.float32) * np.float32(10.0 ** rng.integers(-6, 7)), special]))[::-1][:n]
+        results[q] = rows.tolist()
+        scores[q] = sc.astype(np.float32).tolist()
+    a, b = str(tmp_path / 'a.trec'), str(tmp_path / 'b.trec')
+    write_trec(a, results, scores, docids, 'h2oloo')
+    _py_write_trec(b, results, scores, docids, 'h2oloo')
+    ta, tb = open(a).read(), open(b).read()
+    assert ta == tb
+    assert len(ta) > 0
