@@ -398,26 +398,17 @@ __global__ void __launch_bounds__(kLT_Threads, kLT_CtasPerSm) lex_tile_kernel(co
             uint32_t tw[kLT_SC];
             if constexpr (WIDE) {
                 const uint2 cw = *(const uint2*)(st + (size_t)p * (kLT_SC * 2));        // my four slice codes (16 bits each)
-                // the four slices' lists are walked together (one warp-uniform loop to the longest list) so that their
-                // dependent shared-memory loads overlap
-                uint32_t code[kLT_SC], n[kLT_SC];
-                const uint32_t* hdr = (const uint32_t*)(st + a.pblock_smem);
-                uint32_t nmax = 0;
 #pragma unroll
                 for (int j = 0; j < kLT_SC; ++j) {
-                    code[j] = ((j < 2 ? cw.x : cw.y) >> (16 * (j & 1))) & 0xFFFFu;
-                    n[j] = hdr[j * (kLT_WideSliceBytes / 4)];
-                    nmax = max(nmax, n[j]);
-                    tw[j] = 0;
-                }
-                for (uint32_t i = 0; i < nmax; ++i) {
-#pragma unroll
-                    for (int j = 0; j < kLT_SC; ++j) {
-                        // lists are read up to nmax: words past a slice's own count may hold stale pairs of another tile, so the
-                        // count guards the match (the loads stay inside the slice's 16 + 64 * 8 byte area)
-                        const uint2 pr = *(const uint2*)(hdr + j * (kLT_WideSliceBytes / 4) + 4 + 2 * i);
-                        tw[j] = (i < n[j] && pr.x == code[j]) ? pr.y : tw[j];
+                    const uint32_t code = ((j < 2 ? cw.x : cw.y) >> (16 * (j & 1))) & 0xFFFFu;
+                    const uint32_t* hdr = (const uint32_t*)(st + a.pblock_smem + j * kLT_WideSliceBytes);
+                    const uint32_t n = hdr[0];
+                    uint32_t w = 0;
+                    for (uint32_t i = 0; i < n; ++i) {
+                        const uint2 pr = *(const uint2*)(hdr + 4 + 2 * i);
+                        w = pr.x == code ? pr.y : w;
                     }
+                    tw[j] = w;
                 }
             } else {
                 const uint32_t* tab = (const uint32_t*)(st + a.pblock_smem);
