@@ -3,6 +3,8 @@
 // Replaces torch.topk / torch.argsort of gip_retrieval.py:75,123 and the per-query
 // argsort of retrieval/merge.result.py:39.  Order is total: (score desc, row asc), encoded in
 // one 64-bit key so a single descending bitonic sort in shared memory yields the answer.
+#include <algorithm>
+
 #include "internal.h"
 
 namespace dhr {
@@ -27,27 +29,125 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, int 
     __syncthreads();
 }
 
-// One CTA per in-flight query slot.  Sorts the candidates appended so far, keeps the best k in
-// slots [0, k), publishes the new strict admission threshold tau (the k-th best score: rows
-// scanned later have larger row ids, so a later row with score == tau loses the tie) and, on
-// the final pass, writes the result row.
+// One CTA per in-flight query slot.  Keeps the best k of the candidates appended so far in slots [0, k) (sorted),
+// publishes the new strict admission threshold tau (the k-th best score: rows scanned later have larger row ids, so a
+// later row with score == tau loses the tie) and, on the final pass, writes the result row.
+//
+// Selection before sorting: the n <= 16384 candidate keys stay in registers (16 per thread); an MSB-first radix select
+// (8 passes of 8 bits; per-warp private histograms: candidate scores share their high bytes, so a CTA-wide
+// histogram would serialise all warps on one bin) finds the k-th largest key -- keys are unique because
+// they embed the row -- then only the k keys >= it are compacted into shared memory and bitonic-sorted.  A chunk
+// admits ~7k rows next to the k kept ones, so this sorts 1024 keys instead of 8192-16384, and the small footprint
+// (8 * pow2(k) bytes) lets two CTAs share an SM.
+constexpr int kSelectKeysPerThread = kCandCap / kSelectThreads;
+static_assert(kCandCap % kSelectThreads == 0, "candidate keys are distributed evenly over the select CTA");
+
 __global__ void __launch_bounds__(kSelectThreads, 1)
 topk_select_kernel(TopkState t, int k, int cap, int final_pass, long long row_offset, float* out_scores,
                    long long* out_rows, int* out_counts, int out_base) {
-    extern __shared__ __align__(16) unsigned long long keys[];
+    extern __shared__ __align__(16) unsigned long long keys[];          // [m] selected keys, m = pow2 >= min(n, k)
+    __shared__ uint32_t whist[kSelectThreads / 32][256];              // one histogram per warp
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t wtot[kSelectThreads / 32];
+    __shared__ uint32_t sh_digit, sh_need;
     const int slot = blockIdx.x;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t raw = t.cnt[slot];
     const int n = (int)min(raw, (uint32_t)cap);
     if (raw > (uint32_t)cap && tid == 0) t.overflow[slot] = 1u;
-    int m = 2;
-    while (m < n) m <<= 1;
     float* cs = t.cand_score + (size_t)slot * cap;
     int32_t* cr = t.cand_row + (size_t)slot * cap;
-    for (int i = tid; i < m; i += kSelectThreads)
-        keys[i] = i < n ? make_key(cs[i], (uint32_t)cr[i]) : 0ull;
-    bitonic_sort_desc(keys, m, tid, kSelectThreads);
+    unsigned long long r[kSelectKeysPerThread];
+#pragma unroll
+    for (int j = 0; j < kSelectKeysPerThread; ++j) {
+        const int i = tid + j * kSelectThreads;
+        r[j] = i < n ? make_key(cs[i], (uint32_t)cr[i]) : 0ull;
+    }
     const int keep = min(n, k);
+    unsigned long long kth = 0ull;                                       // n <= k: everything is kept
+    if (n > k) {
+        unsigned long long prefix = 0ull;
+        uint32_t need = (uint32_t)k;                                     // rank (from the top) inside the current prefix group
+        for (int shift = 56; shift >= 0; shift -= 8) {
+#pragma unroll
+            for (int b = 0; b < 8; ++b) whist[warp][lane * 8 + b] = 0u;
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < kSelectKeysPerThread; ++j) {
+                const int i = tid + j * kSelectThreads;
+                const bool active = i < n && (shift == 56 || (r[j] >> (shift + 8)) == prefix);
+                const uint32_t digit = (uint32_t)(r[j] >> shift) & 0xFFu;
+                if (active) atomicAdd(&whist[warp][digit], 1u);       // conflicts stay inside the warp (MATCH.ANY grouping measured slower)
+            }
+            __syncthreads();
+            if (tid < 256) {
+                uint32_t sum = 0;
+#pragma unroll 8
+                for (int w = 0; w < kSelectThreads / 32; ++w) sum += whist[w][tid];
+                hist[tid] = sum;
+            }
+            __syncthreads();
+            if (warp == 0) {                                             // digit of the need-th key, counting from bin 255 down
+                uint32_t c[8], sum = 0;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) { c[b] = hist[lane * 8 + b]; sum += c[b]; }
+                uint32_t suf = sum;                                      // inclusive suffix sum over lanes
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const uint32_t v = __shfl_down_sync(0xFFFFFFFFu, suf, off);
+                    if (lane + off < 32) suf += v;
+                }
+                const uint32_t above = suf - sum;
+                if (above < need && suf >= need) {
+                    uint32_t rem = need - above;
+                    int d = 0;
+#pragma unroll
+                    for (int b = 7; b >= 0; --b) {
+                        if (rem != 0u) {
+                            if (c[b] >= rem) { d = lane * 8 + b; sh_need = rem; rem = 0u; }
+                            else rem -= c[b];
+                        }
+                    }
+                    sh_digit = (uint32_t)d;
+                }
+            }
+            __syncthreads();
+            prefix = (prefix << 8) | (unsigned long long)sh_digit;
+            need = sh_need;
+        }
+        kth = prefix;
+    }
+    // compaction of the kept keys, then a small sort
+    int m = 2;
+    while (m < keep) m <<= 1;
+    for (int i = tid; i < m; i += kSelectThreads) keys[i] = 0ull;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int j = 0; j < kSelectKeysPerThread; ++j) mine += (tid + j * kSelectThreads < n && r[j] >= kth) ? 1u : 0u;
+    uint32_t incl = mine;                                                // block-wide exclusive scan (no atomics)
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (lane >= off) incl += v;
+    }
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t wv = wtot[lane];
+        uint32_t wi = wv;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, wi, off);
+            if (lane >= off) wi += v;
+        }
+        wtot[lane] = wi - wv;
+    }
+    __syncthreads();
+    uint32_t pos = wtot[warp] + incl - mine;
+#pragma unroll
+    for (int j = 0; j < kSelectKeysPerThread; ++j)
+        if (tid + j * kSelectThreads < n && r[j] >= kth) keys[pos++] = r[j];
+    bitonic_sort_desc(keys, m, tid, kSelectThreads);
     for (int i = tid; i < keep; i += kSelectThreads) {
         const unsigned long long key = keys[i];
         cs[i] = key_score(key);
@@ -77,11 +177,14 @@ topk_select_kernel(TopkState t, int k, int cap, int final_pass, long long row_of
 int launch_select(const TopkState& t, int n_slots, int k, int cap, bool final_pass, int64_t row_offset,
                   float* out_scores, int64_t* out_rows, int32_t* out_counts, int out_base, cudaStream_t st) {
     if (n_slots <= 0) return DHR_OK;
-    static bool attr_set = false;
-    const size_t smem = (size_t)cap * sizeof(unsigned long long);
-    if (!attr_set) {
+    if (cap > kCandCap) return DHR_ERR_INVALID;
+    int m = 2;
+    while (m < std::min(k, cap)) m <<= 1;
+    const size_t smem = (size_t)m * sizeof(unsigned long long);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
         DHR_CUDA(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_smem = smem;
     }
     topk_select_kernel<<<n_slots, kSelectThreads, smem, st>>>(t, k, cap, final_pass ? 1 : 0, (long long)row_offset,
                                                               out_scores, (long long*)out_rows, out_counts, out_base);
