@@ -405,7 +405,10 @@ int dhr_index_close(dhr_index* h) {
     for (void* b : bufs) if (b) cudaFree(b);
     for (int i = 0; i < 2; ++i) { if (h->ev_k2_done[i]) cudaEventDestroy(h->ev_k2_done[i]); if (h->ev_k1_done[i]) cudaEventDestroy(h->ev_k1_done[i]); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_sel) cudaEventDestroy(h->ev_sel);
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+    if (h->aux2_stream) cudaStreamDestroy(h->aux2_stream);
     h->events.destroy();
     cudaGetLastError();
     delete h;

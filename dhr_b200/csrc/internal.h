@@ -68,7 +68,8 @@ struct dhr_index {
     uint32_t* qblock_bytes = nullptr; size_t qblock_bytes_cap = 0;
     float* scratch = nullptr; size_t scratch_bytes = 0;   // two sub-chunk buffers (K2 of sub-chunk i+1 overlaps K1t of sub-chunk i)
     cudaStream_t aux_stream = nullptr;   // K2 launches of the hybrid tile path
-    cudaEvent_t ev_k2_done[2] = {nullptr, nullptr}, ev_k1_done[2] = {nullptr, nullptr}, ev_fork = nullptr;
+    cudaStream_t aux2_stream = nullptr;  // every second K1t launch of a chunk (launches of one chunk are independent)
+    cudaEvent_t ev_k2_done[2] = {nullptr, nullptr}, ev_k1_done[2] = {nullptr, nullptr}, ev_fork = nullptr, ev_join = nullptr, ev_sel = nullptr;
     float* d_out_scores = nullptr; int64_t* d_out_rows = nullptr; int32_t* d_out_counts = nullptr; size_t out_capacity = 0;
     // options
     int opt_scan_variant = 1;            // TMA bulk staging (measured faster than direct loads at QB=1 and QB=8)

@@ -311,8 +311,11 @@ static int ensure_tile_workspace(dhr_index* h, const LexTileGeom& t, int n_queri
         DHR_CUDA(cudaMalloc(&h->scratch, sc_need));
         h->scratch_bytes = sc_need;
     }
-    if (h->g.C_pad > 0 && !h->aux_stream) {
+    if (!h->aux_stream) {
         DHR_CUDA(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+        DHR_CUDA(cudaStreamCreateWithFlags(&h->aux2_stream, cudaStreamNonBlocking));
+        DHR_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        DHR_CUDA(cudaEventCreateWithFlags(&h->ev_sel, cudaEventDisableTiming));
         for (int i = 0; i < 2; ++i) {
             DHR_CUDA(cudaEventCreateWithFlags(&h->ev_k2_done[i], cudaEventDisableTiming));
             DHR_CUDA(cudaEventCreateWithFlags(&h->ev_k1_done[i], cudaEventDisableTiming));
@@ -335,11 +338,14 @@ static int run_batch_hybrid_tile(dhr_index* h, const LexTileGeom& lt, const Quer
     const size_t qt0 = (size_t)base / kLexTileQueries;
     const uint8_t* qblocks = h->qblocks + qt0 * lt.n_chunks * (size_t)lt.qblock_stride;
     const uint32_t* qbytes = h->qblock_bytes + qt0 * lt.n_chunks;
-    // K2 runs on the auxiliary stream one sub-chunk ahead of K1t (two scratch buffers): the tensor-core kernel fills the SMs
-    // that the tail of the previous K1t launch leaves idle.  K2 (mode 1) reads only the prepared queries, so it does not
-    // depend on the selects between chunks.
+    // Stream plan.  K2 runs on an auxiliary stream one sub-chunk ahead of K1t (two scratch buffers); K2 (mode 1) reads only
+    // the prepared queries, so it does not depend on the selects between chunks.  The K1t launches of one chunk are
+    // independent of each other (they append to the candidate lists with atomics and read a tau that only the select
+    // between chunks changes), so they alternate between the caller's stream and a second auxiliary stream: the CTAs of
+    // the next launch fill the SMs that the tail of the previous one leaves idle.  The select of a chunk joins both.
     const bool dense = g.C_pad > 0;
-    const bool overlap = dense && h->opt_overlap;
+    const bool overlap = h->opt_overlap != 0;
+    const bool k2_overlap = dense && overlap;
     const size_t sc_half = (size_t)kMaxInflight * kTileSubRows;
     std::vector<std::pair<long long, long long>> subs;
     std::vector<size_t> sub_chunk;
@@ -348,41 +354,51 @@ static int run_batch_hybrid_tile(dhr_index* h, const LexTileGeom& lt, const Quer
             subs.emplace_back(r0, std::min(bounds[c + 1], r0 + kTileSubRows));
             sub_chunk.push_back(c);
         }
-    cudaStream_t k2s = overlap ? h->aux_stream : st;
+    cudaStream_t k2s = k2_overlap ? h->aux_stream : st;
+    cudaStream_t k1s[2] = {st, overlap ? h->aux2_stream : st};
     if (overlap) {
-        DHR_CUDA(cudaEventRecord(h->ev_fork, st));                   // queries prepared, previous batch finished with the scratch
-        DHR_CUDA(cudaStreamWaitEvent(k2s, h->ev_fork, 0));
+        DHR_CUDA(cudaEventRecord(h->ev_fork, st));                   // queries prepared, slots initialised, previous batch done
+        if (k2_overlap) DHR_CUDA(cudaStreamWaitEvent(k2s, h->ev_fork, 0));
+        DHR_CUDA(cudaStreamWaitEvent(k1s[1], h->ev_fork, 0));
     }
     auto launch_k2 = [&](size_t i) -> int {
         const int b = (int)(i & 1);
-        if (overlap && i >= 2) DHR_CUDA(cudaStreamWaitEvent(k2s, h->ev_k1_done[b], 0));     // K1t(i-2) has read this buffer
-        DHR_TRY(launch_dense_tile(h, q16, nq, subs[i].first, subs[i].first, subs[i].second, 1, h->scratch + (overlap ? b * sc_half : 0),
+        if (k2_overlap && i >= 2) DHR_CUDA(cudaStreamWaitEvent(k2s, h->ev_k1_done[b], 0));     // K1t(i-2) has read this buffer
+        DHR_TRY(launch_dense_tile(h, q16, nq, subs[i].first, subs[i].first, subs[i].second, 1, h->scratch + (k2_overlap ? b * sc_half : 0),
                                   kMaxInflight, t, kCandCap, k2s));
-        if (overlap) DHR_CUDA(cudaEventRecord(h->ev_k2_done[b], k2s));
+        if (k2_overlap) DHR_CUDA(cudaEventRecord(h->ev_k2_done[b], k2s));
         h->stats.n_kernel_launches++;
         return DHR_OK;
     };
-    if (dense && overlap && !subs.empty()) DHR_TRY(launch_k2(0));
+    if (k2_overlap && !subs.empty()) DHR_TRY(launch_k2(0));
     size_t si = 0;
     for (size_t c = 0; c < n_chunks; ++c) {
         cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
         if (h->opt_profile) { e0 = h->events.get(); e1 = h->events.get(); e2 = h->events.get(); cudaEventRecord(e0, st); }
+        bool used_aux2 = false;
         for (; si < subs.size() && sub_chunk[si] == c; ++si) {
             const int b = (int)(si & 1);
+            cudaStream_t ks = k1s[b];
             const long long r0 = subs[si].first, r1 = subs[si].second;
             if (dense) {
-                if (overlap) {
+                if (k2_overlap) {
                     if (si + 1 < subs.size()) DHR_TRY(launch_k2(si + 1));
-                    DHR_CUDA(cudaStreamWaitEvent(st, h->ev_k2_done[b], 0));
+                    DHR_CUDA(cudaStreamWaitEvent(ks, h->ev_k2_done[b], 0));
                 } else {
                     DHR_TRY(launch_k2(si));
+                    if (ks != st) { DHR_CUDA(cudaEventRecord(h->ev_k2_done[b], st)); DHR_CUDA(cudaStreamWaitEvent(ks, h->ev_k2_done[b], 0)); }
                 }
             }
-            DHR_TRY(launch_lex_tile(h, lt, qblocks, qbytes, nq, r0, r1, dense ? h->scratch + (overlap ? b * sc_half : 0) : nullptr, kMaxInflight,
-                                    r0, t, kCandCap, st));
-            if (overlap) DHR_CUDA(cudaEventRecord(h->ev_k1_done[b], st));
+            DHR_TRY(launch_lex_tile(h, lt, qblocks, qbytes, nq, r0, r1, dense ? h->scratch + (k2_overlap ? b * sc_half : 0) : nullptr, kMaxInflight,
+                                    r0, t, kCandCap, ks));
+            if (overlap) DHR_CUDA(cudaEventRecord(h->ev_k1_done[b], ks));
+            if (ks != st) used_aux2 = true;
             h->stats.n_kernel_launches++;
             h->stats.n_scan_launches++;
+        }
+        if (used_aux2) {                                             // the select needs every K1t launch of the chunk
+            DHR_CUDA(cudaEventRecord(h->ev_join, k1s[1]));
+            DHR_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
         }
         if (h->opt_profile) cudaEventRecord(e1, st);
         DHR_TRY(launch_select(t, nq, k, kCandCap, c + 1 == n_chunks, h->row_offset, d_scores, d_rows, d_counts, base, st));
@@ -391,6 +407,10 @@ static int run_batch_hybrid_tile(dhr_index* h, const LexTileGeom& lt, const Quer
         h->stats.n_kernel_launches++;
         h->stats.corpus_passes += (double)(bounds[c + 1] - bounds[c]) * ((nq + kLexTileQueries - 1) / kLexTileQueries) /
                                   (double)std::max<int64_t>(1, h->n_rows);
+        if (overlap && c + 1 < n_chunks) {                           // the next chunk's K1t launches read the new tau
+            DHR_CUDA(cudaEventRecord(h->ev_sel, st));
+            DHR_CUDA(cudaStreamWaitEvent(k1s[1], h->ev_sel, 0));
+        }
     }
     if (n_chunks == 0) {
         DHR_TRY(launch_select(t, nq, k, kCandCap, true, h->row_offset, d_scores, d_rows, d_counts, base, st));
