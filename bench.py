@@ -46,6 +46,7 @@ def parse():
     ap.add_argument('--query-groups', type=int, default=None)
     ap.add_argument('--scan-variant', type=int, default=None)
     ap.add_argument('--overlap', type=int, default=None, help='hybrid tile path: K2 on a second stream (1, default) or in line (0)')
+    ap.add_argument('--dense-multicast', type=int, default=None, help='K2: cluster of two query groups sharing corpus tiles by TMA multicast (1, default) or not (0)')
     ap.add_argument('--dense-variant', type=int, default=None, help='K2: 1 = queries in TMEM (default), 0 = both operands in shared memory')
     ap.add_argument('--cpu-rows', type=int, default=400000, help='rows of the bounded CPU-baseline sample')
     ap.add_argument('--cpu-queries', type=int, default=24)
@@ -222,6 +223,8 @@ def main():
         ix.set_option('overlap', args.overlap)
     if args.dense_variant is not None:
         ix.set_option('dense_variant', args.dense_variant)
+    if args.dense_multicast is not None:
+        ix.set_option('dense_multicast', args.dense_multicast)
     ix.set_option('profile', 1)
 
     qv_dev, qi_dev = synth.queries_torch(args.workload, n_q, dev)

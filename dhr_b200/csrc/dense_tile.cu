@@ -47,6 +47,19 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// the same load delivered to the same shared-memory offset (and signalled on the same mbarrier offset) of every CTA in cta_mask
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tmap, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
 }
@@ -295,6 +308,7 @@ struct DenseTsArgs {
     long long scratch_row0;            // row of scratch line 0
     int n_tiles;                       // 128-row tiles in the launch
     int blocked;                       // corpus operand comes from the K-blocked copy
+    int cluster;                       // 1: launched as clusters of two CTAs (the two query groups) sharing corpus tiles by TMA multicast
     int n_kblocks;                     // ceil(C_pad / 64)
     int n_stages;
     int n_qgroups;                     // 128-query groups in flight
@@ -307,6 +321,10 @@ struct DenseTsArgs {
 
 __global__ void __launch_bounds__(kTS_Threads, 1)
 dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_q, const DenseTsArgs a) {
+    // a.cluster: the two query groups of a batch form a cluster of two CTAs that walk the same corpus tiles in lockstep; each
+    // CTA loads half of every stage (64 passages) and multicasts it into both rings, so a corpus byte crosses L2->SM once for
+    // 256 queries and the pair cannot drift apart (a drifting pair reads HBM twice).  Stage-empty barriers then count both
+    // CTAs' MMA commits.
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar[kTS_MaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kTS_MaxStages];
@@ -324,7 +342,7 @@ dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
     uint8_t* ring = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);   // SWIZZLE_128B tiles sit on 1 KiB boundaries
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < a.n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < a.n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], a.cluster ? 2 : 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }   // only [0] is used (one accumulator)
         mbar_init(&q_bar, 1);
         mbar_fence_init();
@@ -367,9 +385,11 @@ dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
     // generic-proxy reads of the ring are complete before the async proxy (TMA) overwrites it with corpus tiles
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
-    __syncthreads();
+    if (a.cluster) cluster_sync_all();          // the peer may multicast into this ring / arrive on these barriers from here on
+    else __syncthreads();
     tc_fence_after();
     if (threadIdx.x == 0) K2_TRACE(0, 2);
+    const uint32_t crank = a.cluster ? cluster_ctarank() : 0u;
 
     if (warp == 0) {
         // ===== TMA producer: corpus tiles (whole warp, one elected lane issues) =====
@@ -390,8 +410,13 @@ dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
                         if (a.blocked) tma_prefetch_l2_2d(&tmap_c, 0, (rowp / kTS_N * a.n_kblocks + kb) * kTS_N);
                         else tma_prefetch_l2_2d(&tmap_c, kb * kDT_KB, rowp);
                     }
-                    mbar_arrive_expect_tx(&full_bar[s], kTS_BBytes);
-                    if (a.blocked) tma_load_2d(ring + (size_t)s * kTS_BBytes, &tmap_c, &full_bar[s], 0, (row0 / kTS_N * a.n_kblocks + kb) * kTS_N);
+                    mbar_arrive_expect_tx(&full_bar[s], kTS_BBytes);              // both halves (own + peer's multicast)
+                    if (a.cluster) {
+                        const int half = (int)crank * (kTS_N / 2);
+                        uint8_t* dst = ring + (size_t)s * kTS_BBytes + (size_t)crank * (kTS_BBytes / 2);
+                        if (a.blocked) tma_load_2d_multicast(dst, &tmap_c, &full_bar[s], 0, (row0 / kTS_N * a.n_kblocks + kb) * kTS_N + half, 3);
+                        else tma_load_2d_multicast(dst, &tmap_c, &full_bar[s], kb * kDT_KB, row0 + half, 3);
+                    } else if (a.blocked) tma_load_2d(ring + (size_t)s * kTS_BBytes, &tmap_c, &full_bar[s], 0, (row0 / kTS_N * a.n_kblocks + kb) * kTS_N);
                     else tma_load_2d(ring + (size_t)s * kTS_BBytes, &tmap_c, &full_bar[s], kb * kDT_KB, row0);
                 }
                 __syncwarp();
@@ -422,7 +447,10 @@ dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
                     for (int k = 0; k < kDT_KB / 16; ++k)
                         umma_f16_ts(d_tmem, tmem_u + (uint32_t)kb * 32u + (uint32_t)k * 8u, umma_smem_desc(b_addr + k * 32), idesc,
                                     (kb | k) != 0 ? 1u : 0u);
-                    if (!(K2_DBG() & 8)) umma_commit(&empty_bar[s]);      // frees the corpus stage once these MMAs have read it
+                    if (!(K2_DBG() & 8)) {                                // frees the corpus stage once these MMAs have read it
+                        if (a.cluster) umma_commit_multicast(&empty_bar[s], 3);
+                        else umma_commit(&empty_bar[s]);
+                    }
                 }
                 __syncwarp();
                 if (++s == a.n_stages) { s = 0; ph ^= 1u; }
@@ -501,7 +529,8 @@ dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
     }
     if (threadIdx.x == 64) K2_TRACE(0, 3);
     tc_fence_before();
-    __syncthreads();
+    if (a.cluster) cluster_sync_all();          // no CTA of the pair exits while the other may still signal its barriers
+    else __syncthreads();
     if (threadIdx.x == 0) K2_TRACE(0, 4);
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
@@ -562,12 +591,8 @@ static int launch_dense_tile_ts(const dhr_index* h, const void* q_dns16, int n_q
     const Geometry& g = h->g;
     CUtensorMap tmap_c, tmap_q;
     const int nkb = (g.C_pad + kDT_KB - 1) / kDT_KB;
-    // corpus operand: the K-blocked copy viewed as [blocks * 128 rows][64 cols] (one box = one contiguous 16 KiB block), or the
-    // row-major block when the copy could not be allocated
-    if (h->dnst)
-        DHR_TRY(make_tmap_f16(&tmap_c, h->dnst, (uint64_t)round_up(h->n_rows, kTS_N) * nkb, (uint64_t)kDT_KB, (uint64_t)kDT_KB, kTS_N));
-    else
-        DHR_TRY(make_tmap_f16(&tmap_c, h->dns, (uint64_t)h->n_rows, (uint64_t)g.C_pad, (uint64_t)g.C_pad, kTS_N));
+    // corpus operand (built below): the K-blocked copy viewed as [blocks * 128 rows][64 cols] (one box = one contiguous piece
+    // of HBM), or the row-major block when the copy could not be allocated
     DHR_TRY(make_tmap_f16(&tmap_q, q_dns16, (uint64_t)n_queries, (uint64_t)g.C_pad, (uint64_t)g.C_pad, kTS_M));
     DenseTsArgs a{};
     a.row_begin = row_begin; a.row_end = row_end;
@@ -587,8 +612,38 @@ static int launch_dense_tile_ts(const dhr_index* h, const void* q_dns16, int n_q
     int per_q = h->num_sms / a.n_qgroups;
     if (per_q < 1) per_q = 1;
     if (per_q > a.n_tiles) per_q = a.n_tiles;
-    dense_tile_ts_kernel<<<(unsigned)(per_q * a.n_qgroups), kTS_Threads, smem, st>>>(tmap_c, tmap_q, a);
-    DHR_CUDA(cudaGetLastError());
+    // Dense-only searches (long launches, HBM-fed) gain 12 %; in the hybrid path K2 runs beside the tail of K1t on whatever SMs
+    // free up, and a cluster needs both SMs of a pair at once (measured 1.5 % slower), so scratch mode stays unicast unless
+    // asked for (dense_multicast = 2).
+    a.cluster = (a.n_qgroups == 2 && ((h->opt_dense_multicast == 1 && mode == 0) || h->opt_dense_multicast == 2)) ? 1 : 0;
+    // with multicast the corpus map delivers half a stage (64 passages) per load
+    const int box_rows = a.cluster ? kTS_N / 2 : kTS_N;
+    if (h->dnst)
+        DHR_TRY(make_tmap_f16(&tmap_c, h->dnst, (uint64_t)round_up(h->n_rows, kTS_N) * nkb, (uint64_t)kDT_KB, (uint64_t)kDT_KB, box_rows));
+    else
+        DHR_TRY(make_tmap_f16(&tmap_c, h->dns, (uint64_t)h->n_rows, (uint64_t)g.C_pad, (uint64_t)g.C_pad, box_rows));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(per_q * a.n_qgroups));
+    cfg.blockDim = dim3(kTS_Threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (a.cluster) {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        static int max_clusters = -1;                                  // pairs the device can keep resident (same for every launch)
+        if (max_clusters < 0) {
+            cudaLaunchConfig_t probe = cfg;
+            probe.gridDim = dim3((unsigned)(h->num_sms / 2 * 2));
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, dense_tile_ts_kernel, &probe) != cudaSuccess || n < 1) { cudaGetLastError(); n = 0; }
+            max_clusters = n;
+        }
+        if (max_clusters < 1) return DHR_ERR_UNSUPPORTED;
+        if (per_q > max_clusters) { per_q = max_clusters; cfg.gridDim = dim3((unsigned)(per_q * 2)); }
+    }
+    DHR_CUDA(cudaLaunchKernelEx(&cfg, dense_tile_ts_kernel, tmap_c, tmap_q, a));
     return DHR_OK;
 }
 

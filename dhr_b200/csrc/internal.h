@@ -78,6 +78,7 @@ struct dhr_index {
     int opt_profile = 0;
     int opt_tile_mode = 1;               // use the tensor-core tile kernels when the shape allows
     int opt_overlap = 1;                 // hybrid tile path: run K2 on a second stream, one sub-chunk ahead of K1t
+    int opt_dense_multicast = 1;         // K2 (TS): the two query groups of a batch share corpus tiles as a cluster of two CTAs (0 off, 1 dense-only searches, 2 always)
     int opt_dense_variant = 1;           // K2: 1 = queries in TMEM (TS) when C_pad <= 768, 0 = both operands in shared memory (SS)
     int num_sms = 148;
     dhr_stats stats{};

@@ -374,3 +374,26 @@ def test_tile_path_bm25_like(shape):
         s2, r2, c2 = ix.search(case['q_vals'], case['q_idx'], k)
     assert_matches_oracle(case, s, r, c, k, exact=True)
     assert np.array_equal(s, s2) and np.array_equal(r, r2)
+
+
+def test_tile_path_options_agree():
+    """K2 variants (queries in TMEM / both operands in shared memory) and the stream plan (overlapped / in line) are
+    implementation choices: on exact-arithmetic inputs every combination returns the identical answer."""
+    case = make_case(31, 90000, 200, 32, 6, 96, 39, np.uint16, np.uint16, grid=True)
+    k = 64
+    outs = []
+    with GipIndex.from_arrays(case['c_vals'], case['c_idx'], n_slices=32, group=6) as ix:
+        configure(ix, 'tile')
+        for dv in (1, 0):
+            for ov in (1, 0):
+                ix.set_option('dense_variant', dv)
+                ix.set_option('overlap', ov)
+                ix.set_option('dense_multicast', 2 if ov else 0)       # cluster-of-two multicast also in scratch mode
+                outs.append(ix.search(case['q_vals'], case['q_idx'], k))
+                assert ix.stats()['scan_variant'] == 3, 'tile path not taken'
+    sub = dict(case)
+    sel = np.r_[0:6, 100:106, 194:200]
+    sub['q_vals'], sub['q_idx'] = case['q_vals'][sel], case['q_idx'][sel]
+    assert_matches_oracle(sub, outs[0][0][sel], outs[0][1][sel], outs[0][2][sel], k, exact=True)
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])

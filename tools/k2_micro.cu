@@ -34,12 +34,14 @@ int main(int argc, char** argv) {
     CK(cudaMemset(t.tau, 0x7f, 256 * 4)); CK(cudaMemset(t.cnt, 0, 256 * 4));
     CK(cudaMalloc(&t.cand_score, (size_t)256 * 16384 * 4)); CK(cudaMalloc(&t.cand_row, (size_t)256 * 16384 * 4));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    const int dbgs[] = {0, 0, 4, 8, 12};
+    const int dbgs[] = {0, 0, 0, 4, 12};
+    const int mcast[] = {1, 0, 1, 1, 1};
     for (int vi = 0; vi < 5; ++vi) {
         const int variant = vi == 0 ? 0 : 1;
         const int dbg = dbgs[vi];
         CK(cudaMemcpyToSymbol(dhr::g_k2_dbg, &dbg, sizeof(int)));
         h.opt_dense_variant = variant;
+        h.opt_dense_multicast = mcast[vi] * 2;
         std::vector<float> ms;
         for (int i = 0; i < 40; ++i) {
             const long long r0 = same_rows ? 0 : (long long)i * sub;
@@ -52,13 +54,14 @@ int main(int argc, char** argv) {
         }
         std::sort(ms.begin(), ms.end());
         const double flops = 2.0 * sub * nq * C;
-        printf("dbg %2d variant %d (%s): median %.1f us  min %.1f us  -> %.0f TFLOP/s, corpus read %.0f GB/s\n", dbg, variant, variant ? "TS" : "SS",
+        printf("dbg %2d multicast %d variant %d (%s): median %.1f us  min %.1f us  -> %.0f TFLOP/s, corpus read %.0f GB/s\n", dbg, mcast[vi], variant, variant ? "TS" : "SS",
                ms[20] * 1e3, ms[0] * 1e3, flops / (ms[20] * 1e-3) / 1e12, sub * h.g.C_pad * 2.0 / (ms[20] * 1e-3) / 1e9);
     }
     // dense-only mode (filter + append, nothing passes tau): one launch over all rows, both variants
     { const int z = 0; CK(cudaMemcpyToSymbol(dhr::g_k2_dbg, &z, sizeof(int))); }
-    for (int variant = 0; variant < 2; ++variant) {
-        h.opt_dense_variant = variant;
+    for (int variant = 1; variant < 3; ++variant) {
+        h.opt_dense_variant = 1;
+        h.opt_dense_multicast = variant - 1;
         float best = 1e9f;
         for (int i = 0; i < 5; ++i) {
             cudaEventRecord(e0);
@@ -68,7 +71,7 @@ int main(int argc, char** argv) {
             if (rc != 0) { fprintf(stderr, "launch rc %d\n", rc); return 1; }
             float m; cudaEventElapsedTime(&m, e0, e1); best = std::min(best, m);
         }
-        printf("mode 0 (filter) variant %d: %lld rows x %d queries in %.1f us -> %.0f TFLOP/s, corpus read %.0f GB/s\n", variant, n_rows, nq,
+        printf("mode 0 (filter) TS multicast %d: %lld rows x %d queries in %.1f us -> %.0f TFLOP/s, corpus read %.0f GB/s\n", variant - 1, n_rows, nq,
                best * 1e3, 2.0 * n_rows * nq * C / (best * 1e-3) / 1e12, n_rows * h.g.C_pad * 2.0 / (best * 1e-3) / 1e9);
     }
     long long tr[8][64];
