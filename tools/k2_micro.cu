@@ -1,6 +1,6 @@
 // k2_micro.cu -- standalone micro-benchmark + timeline of the dense tile kernels K2 (not part of the library).
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -DDHR_K2_TRACE -o gpurun_out/k2_micro tools/k2_micro.cu -lcuda
-//   k2_micro [rows_per_launch=37888] [queries=256] [C=768] [k_blocked_copy=1]
+//   k2_micro [rows_per_launch=37888] [queries=256] [C=768] [k_blocked_copy=1] [same_rows=0] [random_data=0]
 // Launches K2 (mode 1: scratch writes) over successive sub-chunks of a synthetic dense block and prints the median
 // kernel time per variant plus, for the TS variant, the clock64 timeline of CTA 0.
 #include "../dhr_b200/csrc/dense_tile.cu"
@@ -10,6 +10,13 @@
 
 namespace dhr {
 void set_cuda_error(cudaError_t e, const char* what, const char*, int line) { fprintf(stderr, "cuda error %d (%s) line %d\n", (int)e, what, line); }
+}
+
+__global__ void fill_random_halves(__half* p, size_t n, unsigned seed, float scale) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned x = (unsigned)i * 2654435761u ^ seed; x ^= x >> 15; x *= 2246822519u; x ^= x >> 13; x *= 3266489917u; x ^= x >> 16;
+        p[i] = __float2half_rn(((float)(x & 0xFFFF) / 32768.0f - 1.0f) * scale);
+    }
 }
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e_)); return 1; } } while (0)
@@ -29,6 +36,12 @@ int main(int argc, char** argv) {
         CK(cudaMalloc(&h.dnst, nb)); CK(cudaMemset(h.dnst, 0x3c, nb));
     }
     void* q; CK(cudaMalloc(&q, (size_t)nq * h.g.C_pad * 2)); CK(cudaMemset(q, 0x2c, (size_t)nq * h.g.C_pad * 2));
+    if (argc > 6 && atoi(argv[6]) != 0) {      // random operands instead of constants (data-dependent power / timing)
+        fill_random_halves<<<1184, 256>>>((__half*)q, (size_t)nq * h.g.C_pad, 1u, 0.05f);
+        fill_random_halves<<<1184, 256>>>(h.dns, (size_t)n_rows * h.g.C_pad, 2u, 0.05f);
+        if (h.dnst) fill_random_halves<<<1184, 256>>>(h.dnst, (size_t)((n_rows + 127) / 128 * 128) * ((h.g.C_pad + 63) / 64) * 64, 3u, 0.05f);
+        CK(cudaDeviceSynchronize());
+    }
     float* scratch; CK(cudaMalloc(&scratch, (size_t)sub * 256 * 4));
     dhr::TopkState t; CK(cudaMalloc(&t.tau, 256 * 4)); CK(cudaMalloc(&t.cnt, 256 * 4));
     CK(cudaMemset(t.tau, 0x7f, 256 * 4)); CK(cudaMemset(t.cnt, 0, 256 * 4));
