@@ -195,6 +195,7 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # NCCL's version banner must not share stdout with the JSON line
         dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
