@@ -195,7 +195,11 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # NCCL's version banner must not share stdout with the JSON line
+        # NCCL prints its version banner on fd 1 at the first collective; stdout must carry the JSON line only, so fd 1 points
+        # to stderr until the result is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
@@ -362,6 +366,11 @@ def main():
                 'value': v, 'unit': 'queries/s', 'cores': threads, 'kind': 'port',
                 'sample': '%d queries x %d rows (%.1f s), torch-op port of gip_retrieval.py:110-126, scaled linearly to %d rows' % (
                     args.cpu_queries, rows, dt, n_total)}
+        if world > 1:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)                  # C stdio may still buffer the banner
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     ix.close()
     if world > 1:
