@@ -52,7 +52,7 @@ struct dhr_index {
     __half* dns = nullptr;               // [capacity][C_pad]
     __half* dnst = nullptr;              // K-blocked copy of the dense block for K2 (TS): [tile of 128 rows][k-block of 64 cols][128][64], built at finalize
     size_t dnst_bytes = 0;
-    uint8_t* lext = nullptr;             // tiled lexical copy for K1t: [tile of 256 rows][8-slice chunk]{codes[256][8] | vals[8][256][G]}
+    uint8_t* lext = nullptr;             // tiled lexical copy for K1t: [tile of 512 rows][4-slice chunk]{codes u8|u16 [512][4] | vals [4][512][G]}
     size_t lext_bytes = 0;
     int max_code = -1;                   // largest slice code stored (known after finalize)
     int* d_flags = nullptr;              // [4] device-side validation flags (lossy, idx range, query needs fp32, spare)

@@ -329,7 +329,7 @@ def test_dense_tile_grid_bit_exact_and_ties():
                                    (64, 3, 0, 3466, np.uint16), (32, 6, 64, 300, np.int16), (128, 1, 0, 1000, np.int16),
                                    (20, 2, 24, 40000, np.int32), (16, 5, 16, 500, np.uint16)])
 def test_tile_path_many_queries(shape):
-    """Tile kernels with several query tiles in flight (300 queries -> 3 tiles of 128, two super-batches)."""
+    """Tile kernels with several query tiles in flight (300 queries -> 5 tiles of 64, two super-batches of 256)."""
     S, G, Cd, R, cdt = shape
     case = make_case(900 + S + G, 60000, 300, S, G, Cd, R, cdt, cdt)
     k = 100
