@@ -25,7 +25,7 @@ EXPORTS = [
     'dhr_version', 'dhr_strerror', 'dhr_last_cuda_error', 'dhr_device_count',
     'dhr_index_create', 'dhr_index_append', 'dhr_index_finalize', 'dhr_index_open', 'dhr_index_close',
     'dhr_index_rows', 'dhr_index_row_bytes', 'dhr_index_set_option', 'dhr_index_get_stats',
-    'dhr_search', 'dhr_rerank', 'dhr_topk_merge', 'dhr_densify', 'dhr_write_trec',
+    'dhr_search', 'dhr_rerank', 'dhr_topk_merge', 'dhr_densify', 'dhr_write_trec', 'dhr_merge_trec',
 ]
 
 
@@ -85,6 +85,7 @@ def lib():
     L.dhr_topk_merge.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp]
     L.dhr_densify.argtypes = [i32, i32, i32, i32, i32, i32, vp, i64, vp, i64, vp, i64, vp]
     L.dhr_write_trec.argtypes = [c.c_char_p, i32, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, i32, c.c_char_p, i32, c.POINTER(i64)]
+    L.dhr_merge_trec.argtypes = [i32, c.POINTER(c.c_char_p), c.c_char_p, i32, c.c_char_p, i32, c.POINTER(i64)]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is c.c_int and name not in ('dhr_version',):

@@ -6,12 +6,15 @@
 // * {score} is Python's repr() of the float that `.tolist()` made from the fp32 score (:158-159), i.e. the
 //   shortest round-trip decimal of the double with repr's fixed/exponent rule -- py_float_repr below.
 // Queries are formatted by a pool of threads into per-thread buffers and written in query order.
+#include <algorithm>
 #include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <string_view>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/dhr_b200.h"
@@ -135,6 +138,133 @@ extern "C" int dhr_write_trec(const char* path, int append, int n_queries, int k
     for (auto& th : pool) th.join();
     for (int t = 0; t < n_threads; ++t) if (bad[(size_t)t]) return DHR_ERR_INVALID;
     FILE* f = fopen(path, append ? "ab" : "wb");
+    if (!f) return DHR_ERR_INVALID;
+    int64_t total = 0;
+    bool ok = true;
+    for (int t = 0; t < n_threads; ++t) {
+        if (!bufs[(size_t)t].empty() && fwrite(bufs[(size_t)t].data(), 1, bufs[(size_t)t].size(), f) != bufs[(size_t)t].size()) ok = false;
+        total += lines[(size_t)t];
+    }
+    if (fclose(f) != 0) ok = false;
+    if (lines_written) *lines_written = total;
+    return ok ? DHR_OK : DHR_ERR_INVALID;
+}
+
+
+// ---- shard merge on the host ------------------------------------------------------------------
+// Replaces retrieval/merge.result.py:20-43: concatenate the shards' (docid, score) per query id in file order, keep the
+// top-k by score, rewrite the ranks.  The reference sorts with `argsort()[::-1]`, which leaves the order of equal scores
+// to numpy's unstable sort; here ties are ordered by position in the concatenated lists (shard, then the shard's own
+// rank), i.e. the single-shard order.  Scores are re-printed as Python would print float(text).
+namespace {
+
+struct TrecItem { const char* docid; uint32_t docid_len; uint32_t pos; double score; };
+struct TrecGroup { std::string_view qid; std::vector<TrecItem> items; };
+
+bool read_file(const char* path, std::string& out) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    const long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    out.resize(n > 0 ? (size_t)n : 0);
+    const bool ok = n <= 0 || fread(&out[0], 1, (size_t)n, f) == (size_t)n;
+    fclose(f);
+    return ok;
+}
+
+}  // namespace
+
+extern "C" int dhr_merge_trec(int n_paths, const char* const* paths, const char* out_path, int topk, const char* run_name,
+                              int n_threads, int64_t* lines_written) {
+    if (n_paths < 0 || (n_paths > 0 && !paths) || !out_path || topk < 0 || !run_name) return DHR_ERR_INVALID;
+    std::vector<std::string> files((size_t)n_paths);
+    for (int i = 0; i < n_paths; ++i)
+        if (!paths[i] || !read_file(paths[i], files[(size_t)i])) return DHR_ERR_INVALID;
+    std::vector<TrecGroup> groups;                                   // in order of first appearance (dict order of the reference)
+    std::unordered_map<std::string_view, size_t> index;
+    for (const std::string& text : files) {
+        const char* p = text.data();
+        const char* end = p + text.size();
+        while (p < end) {
+            const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
+            if (!eol) eol = end;
+            const char* le = eol;
+            while (le > p && (le[-1] == '\r' || le[-1] == ' ' || le[-1] == '\t')) --le;     // line.strip()
+            const char* lb = p;
+            while (lb < le && (*lb == ' ' || *lb == '\t')) ++lb;
+            if (lb < le) {
+                const char* fld[7]; int nf = 0;                        // split(' '): exactly six fields
+                fld[nf++] = lb;
+                for (const char* c = lb; c < le && nf < 7; ++c) if (*c == ' ') fld[nf++] = c + 1;
+                if (nf != 6) return DHR_ERR_INVALID;
+                const std::string_view qid(fld[0], (size_t)(fld[1] - 1 - fld[0]));
+                TrecItem it;
+                it.docid = fld[2]; it.docid_len = (uint32_t)(fld[3] - 1 - fld[2]);
+                const char* sb = fld[4]; const char* se = fld[5] - 1;
+                if (sb < se && *sb == '+') ++sb;
+                auto r = std::from_chars(sb, se, it.score);
+                if (r.ec != std::errc() || r.ptr != se) {               // inf / nan spellings of Python
+                    const std::string_view sv(sb, (size_t)(se - sb));
+                    if (sv == "inf" || sv == "Infinity") it.score = INFINITY;
+                    else if (sv == "-inf" || sv == "-Infinity") it.score = -INFINITY;
+                    else if (sv == "nan") it.score = NAN;
+                    else return DHR_ERR_INVALID;
+                }
+                auto f = index.find(qid);
+                size_t gi;
+                if (f == index.end()) { gi = groups.size(); groups.push_back(TrecGroup{qid, {}}); index.emplace(qid, gi); }
+                else gi = f->second;
+                it.pos = (uint32_t)groups[gi].items.size();
+                groups[gi].items.push_back(it);
+            }
+            p = eol < end ? eol + 1 : end;
+        }
+    }
+    const int nq = (int)groups.size();
+    const size_t run_len = strlen(run_name);
+    if (run_len > 256) return DHR_ERR_INVALID;
+    if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+    if (n_threads <= 0) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    if (n_threads > nq) n_threads = nq > 0 ? nq : 1;
+    std::vector<std::string> bufs((size_t)n_threads);
+    std::vector<int64_t> lines((size_t)n_threads, 0);
+    std::vector<int> bad((size_t)n_threads, 0);
+    auto work = [&](int t) {
+        const int q0 = (int)((int64_t)nq * t / n_threads), q1 = (int)((int64_t)nq * (t + 1) / n_threads);
+        std::string& b = bufs[(size_t)t];
+        char line[1200];
+        for (int q = q0; q < q1; ++q) {
+            std::vector<TrecItem>& v = groups[(size_t)q].items;
+            const size_t keep = std::min<size_t>((size_t)topk, v.size());
+            auto before = [](const TrecItem& a, const TrecItem& c) { return a.score > c.score || (a.score == c.score && a.pos < c.pos); };
+            std::partial_sort(v.begin(), v.begin() + (long)keep, v.end(), before);
+            const std::string_view qid = groups[(size_t)q].qid;
+            for (size_t r = 0; r < keep; ++r) {
+                if (qid.size() + v[r].docid_len + run_len + 80 > sizeof(line)) { bad[(size_t)t] = 1; return; }
+                char* o = line;
+                memcpy(o, qid.data(), qid.size()); o += qid.size();
+                memcpy(o, " Q0 ", 4); o += 4;
+                memcpy(o, v[r].docid, v[r].docid_len); o += v[r].docid_len;
+                *o++ = ' ';
+                o = std::to_chars(o, o + 12, (int)r + 1).ptr;
+                *o++ = ' ';
+                o += py_float_repr(v[r].score, o);
+                *o++ = ' ';
+                memcpy(o, run_name, run_len); o += run_len;
+                *o++ = '\n';
+                b.append(line, (size_t)(o - line));
+                ++lines[(size_t)t];
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work, t);
+    if (nq > 0) work(0);
+    for (auto& th : pool) th.join();
+    for (int t = 0; t < n_threads; ++t) if (bad[(size_t)t]) return DHR_ERR_INVALID;
+    FILE* f = fopen(out_path, "wb");
     if (!f) return DHR_ERR_INVALID;
     int64_t total = 0;
     bool ok = true;

@@ -1,34 +1,40 @@
 """Mirror of castorini/dhr ``retrieval/merge.result.py`` (:14-43): merge per-shard TREC files into result.trec.
 
 Same flags (--total_shrad, --topk, --run_name).  The reference reads ``result{:02d}.trec`` although
-``gip_retrieval.py:332`` writes ``result{}.trec``; both spellings are accepted here.  The per-query selection runs on
-the GPU through ``dhr_topk_merge`` and orders ties by (score desc, position in the concatenated shard lists asc), i.e.
-by shard then by the shard's own rank -- which equals the single-shard order because every shard lists ties by row."""
+``gip_retrieval.py:332`` writes ``result{}.trec``; both spellings are accepted here.  Parsing, the per-query selection
+and the formatting run on the host in C++ (``dhr_merge_trec``, csrc/trec.cu); ties are ordered by (score desc, position
+in the concatenated shard lists asc), i.e. by shard then by the shard's own rank -- which equals the single-shard order
+because every shard lists ties by row (the reference's ``argsort()[::-1]`` leaves the order of equal scores to numpy's
+unstable sort)."""
 from __future__ import annotations
 
 import argparse
+import ctypes
 import os
-from collections import OrderedDict
 
-import numpy as np
-
-from .index import topk_merge
+from . import _cabi
 
 
-def read_shards(total_shrad, directory='.'):
-    per_q = OrderedDict()
+def shard_paths(total_shrad, directory='.'):
+    paths = []
     for shrad in range(total_shrad):
         for name in ('result{:02d}.trec'.format(shrad), 'result{}.trec'.format(shrad)):
             path = os.path.join(directory, name)
             if os.path.exists(path):
+                paths.append(path)
                 break
         else:
             raise FileNotFoundError('no result file for shard %d in %s' % (shrad, directory))
-        with open(path) as f:
-            for line in f:
-                query_id, _, docid, _rank, score, _ = line.strip().split(' ')
-                per_q.setdefault(query_id, []).append((shrad, docid, score))
-    return per_q
+    return paths
+
+
+def merge_trec(paths, out_path, topk, run_name, n_threads=0):
+    """merge the TREC files `paths` (shard order) into `out_path`; returns the number of lines written"""
+    arr = (ctypes.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+    n_lines = ctypes.c_int64(0)
+    _cabi.check(_cabi.lib().dhr_merge_trec(len(paths), arr, os.fsencode(out_path), int(topk), str(run_name).encode('utf-8'),
+                                           int(n_threads), ctypes.byref(n_lines)), 'dhr_merge_trec')
+    return n_lines.value
 
 
 def main(argv=None):
@@ -36,33 +42,10 @@ def main(argv=None):
     parser.add_argument("--total_shrad", type=int, default=1)
     parser.add_argument("--topk", type=int, default=1000)
     parser.add_argument("--run_name", default='dhr')
-    parser.add_argument("--device", type=int, default=0)
     args = parser.parse_args(argv)
-    per_q = read_shards(args.total_shrad)
-    qids = list(per_q.keys())
-    width = max((len(v) for v in per_q.values()), default=0)
-    if width == 0:
-        open('result.trec', 'w').close()
-        return
-    # one "part" holding, per query, all shards' candidates in file order; position encodes the tie order
-    scores = np.full((1, len(qids), width), -np.inf, np.float32)
-    rows = np.full((1, len(qids), width), -1, np.int64)
-    for i, q in enumerate(qids):
-        n = len(per_q[q])
-        scores[0, i, :n] = [float(s) for _, _, s in per_q[q]]
-        rows[0, i, :n] = np.arange(n)
+    paths = shard_paths(args.total_shrad)
     print('write results ...')
-    ms, mr = topk_merge(scores, rows, device=args.device)
-    with open('result.trec', 'w') as fout:
-        for i, q in enumerate(qids):
-            out = []
-            for rank in range(min(args.topk, width)):
-                pos = int(mr[i, rank])
-                if pos < 0:
-                    break
-                _, docid, score_text = per_q[q][pos]
-                out.append('{} Q0 {} {} {} {}\n'.format(q, docid, rank + 1, float(score_text), args.run_name))
-            fout.write(''.join(out))
+    merge_trec(paths, 'result.trec', args.topk, args.run_name)
 
 
 if __name__ == "__main__":

@@ -161,6 +161,13 @@ int dhr_write_trec(const char* path, int append, int n_queries, int k, const int
                    int64_t n_docids, const int64_t* docid_int, const char* docid_str, const int64_t* docid_off,
                    int skip_equal, const char* run_name, int n_threads, int64_t* lines_written);
 
+/* Shard merge on the host, replacing retrieval/merge.result.py:20-43: reads the shards' TREC files in the given order,
+ * groups lines by query id (order of first appearance), keeps the top `topk` per query by (score desc, position in the
+ * concatenated shard lists asc) and writes out_path with ranks renumbered from 1 and scores printed as Python prints
+ * float(text).  Lines must have the six space-separated fields gip_retrieval.py:341 writes. */
+int dhr_merge_trec(int n_paths, const char* const* paths, const char* out_path, int topk, const char* run_name,
+                   int n_threads, int64_t* lines_written);
+
 #ifdef __cplusplus
 }
 #endif

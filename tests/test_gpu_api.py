@@ -151,31 +151,3 @@ def test_gpu_densify_op_matches_reference():
     assert torch.all(vals[:, 768:] == 0)
     with pytest.raises(ValueError):
         densify(x, dims=7)
-
-
-def test_merge_result_cli(tmp_path, monkeypatch):
-    """3 shard files written by the CLI merge into the single-shard result (tie groups as sets)."""
-    from dhr_b200 import merge_result
-    g = load_golden('main_trec_grid')
-    monkeypatch.chdir(tmp_path)
-    for sh in range(3):
-        with open('result%d.trec' % sh, 'w') as f:
-            f.write(str(g['trec_shard%d' % sh]))
-    merge_result.main(['--total_shrad', '3', '--topk', str(int(g['topk'])), '--run_name', 'golden'])
-    ours = open('result.trec').read().splitlines()
-    # expected: per query, the best topk of the union by score; compare (qid, rank, score) sequences with an oracle merge
-    exp = {}
-    for sh in range(3):
-        for l in str(g['trec_shard%d' % sh]).splitlines():
-            f = l.split(' ')
-            exp.setdefault(f[0], []).append((float(f[4]), f[2]))
-    k = int(g['topk'])
-    got = {}
-    for l in ours:
-        f = l.split(' ')
-        got.setdefault(f[0], []).append((float(f[4]), f[2], int(f[3])))
-    for q, items in exp.items():
-        want = sorted((s for s, _ in items), reverse=True)[:k]
-        assert [s for s, _, _ in got[q]] == want
-        assert [r for _, _, r in got[q]] == list(range(1, len(want) + 1))
-        assert all((s, d) in items for s, d, _ in got[q])

@@ -196,3 +196,69 @@ def test_trec_writer_matches_python_formatting(tmp_path, ids):
     ta, tb = open(a).read(), open(b).read()
     assert ta == tb
     assert len(ta) > 0
+
+
+def test_merge_result_cli(tmp_path, monkeypatch):
+    """3 shard files written by the CLI merge into the single-shard result (tie groups as sets)."""
+    from dhr_b200 import merge_result
+    g = load_golden('main_trec_grid')
+    monkeypatch.chdir(tmp_path)
+    for sh in range(3):
+        with open('result%d.trec' % sh, 'w') as f:
+            f.write(str(g['trec_shard%d' % sh]))
+    merge_result.main(['--total_shrad', '3', '--topk', str(int(g['topk'])), '--run_name', 'golden'])
+    ours = open('result.trec').read().splitlines()
+    # expected: per query, the best topk of the union by score; compare (qid, rank, score) sequences with an oracle merge
+    exp = {}
+    for sh in range(3):
+        for l in str(g['trec_shard%d' % sh]).splitlines():
+            f = l.split(' ')
+            exp.setdefault(f[0], []).append((float(f[4]), f[2]))
+    k = int(g['topk'])
+    got = {}
+    for l in ours:
+        f = l.split(' ')
+        got.setdefault(f[0], []).append((float(f[4]), f[2], int(f[3])))
+    for q, items in exp.items():
+        want = sorted((s for s, _ in items), reverse=True)[:k]
+        assert [s for s, _, _ in got[q]] == want
+        assert [r for _, _, r in got[q]] == list(range(1, len(want) + 1))
+        assert all((s, d) in items for s, d, _ in got[q])
+
+
+def test_merge_trec_matches_python_rule(tmp_path):
+    """C++ shard merge (csrc/trec.cu): same text as a Python statement of the rule -- per query the union of the shards'
+    lines, (score desc, position asc), ranks from 1, scores printed as Python prints float(text) -- including ties, ragged
+    shards, queries missing from a shard and exponent-form scores."""
+    from dhr_b200.merge_result import merge_trec
+    rng = np.random.default_rng(11)
+    qids = ['q%d' % i for i in range(23)]
+    paths = []
+    per_q = {}
+    for sh in range(4):
+        p = str(tmp_path / ('result%d.trec' % sh))
+        paths.append(p)
+        with open(p, 'w') as f:
+            for q in qids:
+                if rng.random() < 0.15:
+                    continue                                             # this shard has nothing for the query
+                n = int(rng.integers(1, 40))
+                sc = np.sort(np.round(rng.standard_normal(n).astype(np.float32) * np.float32(10.0 ** rng.integers(-6, 5)), 3))[::-1]
+                sc[rng.random(n) < 0.3] = np.float32(1.5)                # ties across and inside shards
+                sc = np.sort(sc)[::-1]
+                for r in range(n):
+                    doc = 'D%d_%d' % (sh, int(rng.integers(0, 10 ** 6)))
+                    text = repr(float(sc[r]))
+                    f.write('%s Q0 %s %d %s shard\n' % (q, doc, r + 1, text))
+                    per_q.setdefault(q, []).append((float(text), doc))
+    out = str(tmp_path / 'merged.trec')
+    k = 25
+    n_lines = merge_trec(paths, out, k, 'dhr')
+    exp = []
+    for q, items in per_q.items():                                       # dict order = order of first appearance
+        order = sorted(range(len(items)), key=lambda i: (-items[i][0], i))[:k]
+        for rank, i in enumerate(order):
+            exp.append('{} Q0 {} {} {} {}\n'.format(q, items[i][1], rank + 1, items[i][0], 'dhr'))
+    got = open(out).read()
+    assert got == ''.join(exp)
+    assert n_lines == len(exp)
