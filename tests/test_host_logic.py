@@ -262,3 +262,30 @@ def test_merge_trec_matches_python_rule(tmp_path):
     got = open(out).read()
     assert got == ''.join(exp)
     assert n_lines == len(exp)
+
+
+def test_k1t_postings_spec_matches_oracle():
+    """tools/k1t_postings_spec.py (the layout + walk the next K1t is specified by): code-sorted postings inside a tile,
+    query-driven walk == the exact lexical scores, on exact-arithmetic inputs incl. empty slices and a ragged last tile."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('k1t_postings_spec', os.path.join(ROOT, 'tools', 'k1t_postings_spec.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    from helpers import make_case
+    from oracle import c_oracle
+    S, G, R = 16, 3, 12
+    case = make_case(3, 700, 9, S, G, 0, R, np.uint8, np.uint8, c_density=0.6, q_density=0.7, grid=True)
+    tiles = mod.build_postings(case['c_vals'], case['c_idx'], S, G, R, tile_rows=512)
+    assert [t['rows'] for t in tiles] == [512, 188]
+    got = np.concatenate([mod.walk_tile(t, case['q_vals'], case['q_idx'], S, G, R)[0] for t in tiles], axis=1)
+    for q in range(case['q_vals'].shape[0]):
+        ex = c_oracle.scores(case['c_vals'], case['c_idx'], case['q_vals'][q].astype(np.float32), case['q_idx'][q], S, G)
+        assert np.array_equal(got[q].astype(np.float64), ex)
+    # every stored item is a non-empty slice and lists are sorted by (code, passage)
+    t0 = tiles[0]
+    assert np.all(np.any(t0['val'] != 0, axis=1))
+    for s in range(S):
+        for c in range(R):
+            p = t0['pid'][t0['off'][s, c]:t0['off'][s, c + 1]]
+            assert np.all(np.diff(p.astype(np.int64)) > 0)
+            assert np.all(case['c_idx'][p, s] == c)
