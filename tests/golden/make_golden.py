@@ -234,9 +234,39 @@ def densify_golden():
     print('wrote densify_op.npz')
 
 
+def wide_golden():
+    """Index ranges beyond 8 bits (densified BM25 / DeepImpact: idx < 3466, densify_corpus.py:31-32): the CUDA tile path
+    switches to 16-bit codes there.  Indices are drawn from a pool of 60 values spread over [0, 3466) so that queries and
+    passages do collide at this small N.  Own rng: the fixtures written by main() stay byte-identical."""
+    torch.set_num_threads(1)
+    rng = np.random.default_rng(20261017)
+    pool = np.sort(rng.choice(3466, size=60, replace=False))
+
+    def remap(case):
+        for key in ('c_idx', 'q_idx'):
+            idx = case[key]
+            nz = np.any(case[key[0] + '_vals'][:, :case['S'] * case['G']].reshape(idx.shape[0], case['S'], case['G']) != 0, axis=2)
+            new = pool[idx.astype(np.int64) % 60]
+            new[~nz] = 0                                               # empty slice: value 0 and idx 0
+            case[key] = new.astype(idx.dtype)
+        return case
+
+    # reference-true densified BM25: G = 1, int16 idx on both sides
+    c = remap(make_case(rng, 4000, 8, 64, 1, 0, 60, np.int16, np.int16, 0.30, 0.25, grid=True))
+    rows, sc = run_gip(c, brute_force=True, topk=80)
+    save('bm25_wide_i16_grid', c, topk=80, ref_rows=rows, ref_scores=sc)
+    # BASELINE config 3 literal, scaled down: 3 values per slice, uint16 idx
+    c = remap(make_case(rng, 3000, 6, 32, 3, 0, 60, np.uint16, np.uint16, 0.30, 0.30, grid=True))
+    rows, sc = run_gip(c, brute_force=True, topk=60)
+    save('grouped_g3_wide_u16_grid', c, topk=60, ref_rows=rows, ref_scores=sc)
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'densify':
         densify_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'wide':
+        wide_golden()
     else:
         main()
         densify_golden()
+        wide_golden()

@@ -35,7 +35,8 @@ def _golden_queries(g):
     return g['q_vals'].astype(np.float32)
 
 
-GRID = ['delade_g1_u8_grid', 'bm25_i16_grid', 'unicoil_i8_i16_grid', 'grouped_g6_u16_grid', 'grouped_g3_u16_grid',
+GRID = ['delade_g1_u8_grid', 'bm25_i16_grid', 'unicoil_i8_i16_grid', 'grouped_g6_u16_grid', 'grouped_g3_u16_grid', 'bm25_wide_i16_grid',
+        'grouped_g3_wide_u16_grid',
         'delade_lamda_grid']
 
 
