@@ -1,6 +1,6 @@
 // k1t_v7_proto.cu -- self-checking prototype of the planned K1t v7 walk ("postings within the tile", DESIGN.md section 7,
-// executable spec: tools/k1t_postings_spec.py).  NOT part of the library and not yet run on a GPU: written in the round-1
-// build container (no device) so that the next round starts from one command:
+// executable spec: tools/k1t_postings_spec.py).  NOT part of the library.  First (and so far only) run on a B200:
+// bit-exact, 106 us per launch (profiles/r1_k1t_v7_proto.txt).  One command:
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o /tmp/k1t_v7 tools/k1t_v7_proto.cu && /tmp/k1t_v7
 //
