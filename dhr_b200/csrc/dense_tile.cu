@@ -616,12 +616,6 @@ static int launch_dense_tile_ts(const dhr_index* h, const void* q_dns16, int n_q
     // free up, and a cluster needs both SMs of a pair at once (measured 1.5 % slower), so scratch mode stays unicast unless
     // asked for (dense_multicast = 2).
     a.cluster = (a.n_qgroups == 2 && ((h->opt_dense_multicast == 1 && mode == 0) || h->opt_dense_multicast == 2)) ? 1 : 0;
-    // with multicast the corpus map delivers half a stage (64 passages) per load
-    const int box_rows = a.cluster ? kTS_N / 2 : kTS_N;
-    if (h->dnst)
-        DHR_TRY(make_tmap_f16(&tmap_c, h->dnst, (uint64_t)round_up(h->n_rows, kTS_N) * nkb, (uint64_t)kDT_KB, (uint64_t)kDT_KB, box_rows));
-    else
-        DHR_TRY(make_tmap_f16(&tmap_c, h->dns, (uint64_t)h->n_rows, (uint64_t)g.C_pad, (uint64_t)g.C_pad, box_rows));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(per_q * a.n_qgroups));
     cfg.blockDim = dim3(kTS_Threads);
@@ -640,9 +634,20 @@ static int launch_dense_tile_ts(const dhr_index* h, const void* q_dns16, int n_q
             if (cudaOccupancyMaxActiveClusters(&n, dense_tile_ts_kernel, &probe) != cudaSuccess || n < 1) { cudaGetLastError(); n = 0; }
             max_clusters = n;
         }
-        if (max_clusters < 1) return DHR_ERR_UNSUPPORTED;
-        if (per_q > max_clusters) { per_q = max_clusters; cfg.gridDim = dim3((unsigned)(per_q * 2)); }
+        if (max_clusters < 1) {                                        // no cluster launch on this device / partition: unicast
+            a.cluster = 0;
+            cfg.attrs = nullptr; cfg.numAttrs = 0;
+        } else if (per_q > max_clusters) {
+            per_q = max_clusters;
+            cfg.gridDim = dim3((unsigned)(per_q * 2));
+        }
     }
+    // with multicast the corpus map delivers half a stage (64 passages) per load
+    const int box_rows = a.cluster ? kTS_N / 2 : kTS_N;
+    if (h->dnst)
+        DHR_TRY(make_tmap_f16(&tmap_c, h->dnst, (uint64_t)round_up(h->n_rows, kTS_N) * nkb, (uint64_t)kDT_KB, (uint64_t)kDT_KB, box_rows));
+    else
+        DHR_TRY(make_tmap_f16(&tmap_c, h->dns, (uint64_t)h->n_rows, (uint64_t)g.C_pad, (uint64_t)g.C_pad, box_rows));
     DHR_CUDA(cudaLaunchKernelEx(&cfg, dense_tile_ts_kernel, tmap_c, tmap_q, a));
     return DHR_OK;
 }
