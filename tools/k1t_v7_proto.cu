@@ -72,6 +72,7 @@ struct Args {
     const uint8_t* qblocks;                                                              // [qtile][chunk] of QBLOCK bytes
     float* out;                                                                          // [qtile][tile][QT][PT]
     int n_tiles, n_chunks, n_qtiles, rt, hdr_bytes, stage_bytes, pblock_smem;
+    int store;                                                                           // 0: skip the accumulator store (walk time only)
 };
 constexpr int QBLOCK = SC * QT * 16;
 
@@ -160,9 +161,11 @@ __global__ void __launch_bounds__(THREADS, 1) k1t_v7_kernel(const __grid_constan
             if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
         consumer_barrier();                                      // rows go back to the passage threads
-        float* o = a.out + (((size_t)qt * a.n_tiles + t) * QT) * PT + p;
+        if (a.store) {
+            float* o = a.out + (((size_t)qt * a.n_tiles + t) * QT) * PT + p;
 #pragma unroll 8
-        for (int q = 0; q < QT; ++q) o[(size_t)q * PT] = acc[q * PT + p];
+            for (int q = 0; q < QT; ++q) o[(size_t)q * PT] = acc[q * PT + p];
+        }
         consumer_barrier();
     }
 }
@@ -269,17 +272,21 @@ int main(int argc, char** argv) {
     if (per_q > n_tiles) per_q = n_tiles;
     const unsigned grid = (unsigned)(per_q * n_qtiles);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    std::vector<float> ms;
-    for (int i = 0; i < 21; ++i) {
-        cudaEventRecord(e0);
-        k1t_v7_kernel<<<grid, THREADS, smem>>>(a);
-        cudaEventRecord(e1);
-        CK(cudaEventSynchronize(e1));
-        CK(cudaGetLastError());
-        float m; cudaEventElapsedTime(&m, e0, e1); ms.push_back(m);
+    for (int store = 0; store < 2; ++store) {                   // walk only first, then with the accumulator store (checked below)
+        a.store = store;
+        std::vector<float> ms;
+        for (int i = 0; i < 21; ++i) {
+            cudaEventRecord(e0);
+            k1t_v7_kernel<<<grid, THREADS, smem>>>(a);
+            cudaEventRecord(e1);
+            CK(cudaEventSynchronize(e1));
+            CK(cudaGetLastError());
+            float m; cudaEventElapsedTime(&m, e0, e1); ms.push_back(m);
+        }
+        std::sort(ms.begin(), ms.end());
+        printf("k1t_v7_kernel (%s): %d rows x %d queries, median %.1f us, min %.1f us per launch (grid %u)\n",
+               store ? "with accumulator store" : "walk only", rows, n_queries, ms[10] * 1e3, ms[0] * 1e3, grid);
     }
-    std::sort(ms.begin(), ms.end());
-    printf("k1t_v7_kernel: %d rows x %d queries, median %.1f us, min %.1f us per launch (grid %u)\n", rows, n_queries, ms[10] * 1e3, ms[0] * 1e3, grid);
     // ---- check against the host (same fp32 operation order: slices ascending, te/to chains, acc + (te + to)) ----
     std::vector<float> out(out_elems);
     CK(cudaMemcpy(out.data(), d_out, out_elems * 4, cudaMemcpyDeviceToHost));
