@@ -88,6 +88,22 @@ def occupancy_model(lens, lists_per_warp=4):
     return used / max(1, issued), used
 
 
+def v6_occupancy(c_idx_tile, nonempty_tile, q_idx, q_nonempty, S, slices_per_chunk):
+    """Lane occupancy of the current kernel (thread = passage, a warp steps to the largest per-thread match count of the
+    chunk): matches / (32 * sum over (warp, chunk) of the warp maximum)."""
+    rows = c_idx_tile.shape[0]
+    used = issued = 0
+    for c0 in range(0, S, slices_per_chunk):
+        cnt = np.zeros(rows, np.int64)
+        for s in range(c0, c0 + slices_per_chunk):
+            m = (c_idx_tile[:, s][:, None] == q_idx[:, s][None, :]) & nonempty_tile[:, s][:, None] & q_nonempty[:, s][None, :]
+            cnt += m.sum(axis=1)
+        used += int(cnt.sum())
+        for w in range(0, rows, 32):
+            issued += 32 * int(cnt[w:w + 32].max())
+    return used / max(1, issued)
+
+
 def main():
     from dhr_b200 import synth
     from oracle import c_oracle
@@ -116,6 +132,12 @@ def main():
         nz = lens[lens > 0]
         print('tile %d: %d matches, %d non-empty lists, mean list %.2f, max %d' % (t, int(lens.sum()), len(nz), nz.mean(), nz.max()))
     print('max |score - oracle| over the checked queries: %.2e' % worst)
+    ne = np.any(cv[:, :S * G].reshape(-1, S, G) != 0, axis=2)
+    qne = np.any(qv[:, :S * G].reshape(-1, S, G) != 0, axis=2)
+    for sc in (4, 8, 16):
+        o = np.mean([v6_occupancy(ci[t * tile_rows:(t + 1) * tile_rows].astype(np.int64), ne[t * tile_rows:(t + 1) * tile_rows],
+                                  qi.astype(np.int64), qne, S, sc) for t in range(n_tiles)])
+        print('current kernel (thread = passage), %2d slices per flattened walk: lane occupancy %.1f %%' % (sc, 100 * o))
     for lw in (1, 2, 4, 8):
         sel = [o for o in occ if o[0] == lw]
         print('lists per warp %d: lane occupancy %.1f %%' % (lw, 100 * np.mean([o[1] for o in sel])))
