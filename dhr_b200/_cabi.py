@@ -18,6 +18,7 @@ IDX_NONE, IDX_U8, IDX_I8, IDX_I16, IDX_U16, IDX_I32, IDX_I64 = range(7)
 VAL_F16, VAL_F32 = 0, 1
 SEARCH_UNMASKED = 1
 INDEX_NARROW_CODES = 1
+INDEX_KEEP_ROWMAJOR = 2
 MAX_K = 12288
 MAX_GROUP = 8
 
@@ -26,6 +27,8 @@ EXPORTS = [
     'dhr_index_create', 'dhr_index_append', 'dhr_index_finalize', 'dhr_index_open', 'dhr_index_close',
     'dhr_index_rows', 'dhr_index_row_bytes', 'dhr_index_set_option', 'dhr_index_get_stats',
     'dhr_search', 'dhr_rerank', 'dhr_topk_merge', 'dhr_densify', 'dhr_write_trec', 'dhr_merge_trec',
+    'dhr_search_keys', 'dhr_search_batches', 'dhr_search_wait_batch', 'dhr_search_complete', 'dhr_merge_keys',
+    'dhr_index_device_bytes',
 ]
 
 
@@ -34,9 +37,9 @@ class DhrStats(ctypes.Structure):
         ('n_queries', ctypes.c_int32), ('query_block', ctypes.c_int32), ('query_groups', ctypes.c_int32),
         ('scan_variant', ctypes.c_int32), ('n_scan_launches', ctypes.c_int32), ('n_select_launches', ctypes.c_int32),
         ('n_prep_launches', ctypes.c_int32), ('n_fallback_queries', ctypes.c_int32),
-        ('n_kernel_launches', ctypes.c_int32), ('reserved0', ctypes.c_int32),
+        ('n_kernel_launches', ctypes.c_int32), ('rowmajor_rebuilds', ctypes.c_int32),
         ('scan_ms', ctypes.c_double), ('select_ms', ctypes.c_double), ('total_ms', ctypes.c_double),
-        ('corpus_passes', ctypes.c_double), ('bytes_per_pass', ctypes.c_double),
+        ('corpus_passes', ctypes.c_double), ('bytes_per_pass', ctypes.c_double), ('dense_flops', ctypes.c_double),
     ]
 
     def as_dict(self):
@@ -81,6 +84,12 @@ def lib():
     L.dhr_index_set_option.argtypes = [vp, c.c_char_p, i64]
     L.dhr_index_get_stats.argtypes = [vp, c.POINTER(DhrStats)]
     L.dhr_search.argtypes = [vp, i32, i32, vp, i64, i32, vp, i64, f32, i32, c.c_uint, vp, vp, vp, vp]
+    L.dhr_search_keys.argtypes = [vp, i32, i32, vp, i64, i32, vp, i64, f32, i32, c.c_uint, vp, vp]
+    L.dhr_search_batches.argtypes = [vp, c.POINTER(i32), c.POINTER(i32)]
+    L.dhr_search_wait_batch.argtypes = [vp, i32, vp]
+    L.dhr_search_complete.argtypes = [vp, c.POINTER(i32), vp]
+    L.dhr_merge_keys.argtypes = [i32, i32, i32, i32, vp, i64, vp, vp, vp, vp]
+    L.dhr_index_device_bytes.argtypes = [vp, c.POINTER(i64)]
     L.dhr_rerank.argtypes = [vp, i32, i32, vp, i64, i32, vp, i64, f32, vp, i32, i32, vp, vp, vp, vp]
     L.dhr_topk_merge.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp]
     L.dhr_densify.argtypes = [i32, i32, i32, i32, i32, i32, vp, i64, vp, i64, vp, i64, vp]

@@ -178,6 +178,89 @@ __global__ void build_dnst_kernel(long long n_rows, long long n_rows_pad, int C_
     *(uint4*)(dnst + (((size_t)tile * n_kblocks + kb) * kDenseTileRows + tr) * kDenseTileCols + cv * 8) = x;
 }
 
+// inverse of build_lext_kernel / build_dnst_kernel: rebuild the row-major arrays from the tiled copies (option "rowmajor")
+template <typename CodeT, typename TCode>
+__global__ void unbuild_lext_kernel(long long n_rows, int S_pad, int G, const uint8_t* __restrict__ lext, __half* __restrict__ lexv,
+                                    CodeT* __restrict__ lexi) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows * S_pad) return;
+    const long long r = i / S_pad;
+    const int s = (int)(i % S_pad);
+    const long long tile = r / kLexTileRows;
+    const int tp = (int)(r % kLexTileRows), chunk = s / kLexTileSlices, tj = s % kLexTileSlices;
+    const size_t pblock = (size_t)kLexTileRows * kLexTileSlices * (sizeof(TCode) + 2 * (size_t)G);
+    const uint8_t* blk = lext + ((size_t)tile * (S_pad / kLexTileSlices) + chunk) * pblock;
+    const TCode tc = ((const TCode*)blk)[(size_t)tp * kLexTileSlices + tj];
+    const __half* tv = (const __half*)(blk + (size_t)kLexTileRows * kLexTileSlices * sizeof(TCode)) + ((size_t)tj * kLexTileRows + tp) * G;
+    constexpr uint32_t kTEmpty = sizeof(TCode) == 1 ? 0xFFu : 0xFFFFu;
+    lexi[(size_t)r * S_pad + s] = (uint32_t)tc == kTEmpty ? (CodeT)CodeTraits<CodeT>::kEmpty : (CodeT)tc;
+    __half* dst = lexv + ((size_t)r * S_pad + s) * G;
+    for (int g = 0; g < G; ++g) dst[g] = tv[g];
+}
+
+__global__ void unbuild_dnst_kernel(long long n_rows, int C_pad, int n_kblocks, const __half* __restrict__ dnst, __half* __restrict__ dns) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long vec_per_row = C_pad / 8;
+    if (i >= n_rows * vec_per_row) return;
+    const long long r = i / vec_per_row;
+    const int col = (int)(i % vec_per_row) * 8;
+    const int kb = col / kDenseTileCols, cv = (col % kDenseTileCols) / 8;
+    const long long tile = r / kDenseTileRows;
+    const int tr = (int)(r % kDenseTileRows);
+    *(uint4*)(dns + (size_t)r * C_pad + col) =
+        *(const uint4*)(dnst + (((size_t)tile * n_kblocks + kb) * kDenseTileRows + tr) * kDenseTileCols + cv * 8);
+}
+
+static bool tiled_copies_complete(const dhr_index* h) {
+    const Geometry& g = h->g;
+    return (g.D_pad == 0 || h->lext) && (g.C_pad == 0 || h->dnst);
+}
+
+static int drop_rowmajor_unchecked(dhr_index* h);
+int drop_rowmajor(dhr_index* h) {
+    if (!h->finalized) return DHR_OK;
+    return drop_rowmajor_unchecked(h);
+}
+static int drop_rowmajor_unchecked(dhr_index* h) {
+    if (!tiled_copies_complete(h) || h->n_rows == 0) return DHR_OK;   // nothing to rebuild from: keep them
+    DHR_CUDA(cudaSetDevice(h->device));
+    DHR_CUDA(cudaDeviceSynchronize());
+    if (h->lexv) { cudaFree(h->lexv); h->lexv = nullptr; }
+    if (h->lexi) { cudaFree(h->lexi); h->lexi = nullptr; }
+    if (h->dns) { cudaFree(h->dns); h->dns = nullptr; }
+    return DHR_OK;
+}
+
+int ensure_rowmajor(dhr_index* h) {
+    const Geometry& g = h->g;
+    const bool have = (g.D_pad == 0 || (h->lexv && h->lexi)) && (g.C_pad == 0 || h->dns);
+    if (have) return DHR_OK;
+    if (!tiled_copies_complete(h)) return DHR_ERR_STATE;
+    DHR_CUDA(cudaSetDevice(h->device));
+    const size_t rows = (size_t)(h->capacity > 0 ? h->capacity : 1);
+    if (g.D_pad > 0 && !h->lexv) {
+        DHR_CUDA(cudaMalloc(&h->lexv, rows * g.D_pad * 2));
+        DHR_CUDA(cudaMalloc(&h->lexi, rows * g.S_pad * g.code_bytes));
+        const long long total = h->n_rows * g.S_pad;
+        const unsigned blocks = (unsigned)((total + 255) / 256);
+        const bool wide = std::max(1, h->max_code + 1) > 254;
+        if (wide) unbuild_lext_kernel<uint16_t, uint16_t><<<blocks, 256>>>(h->n_rows, g.S_pad, g.G, h->lext, h->lexv, (uint16_t*)h->lexi);
+        else if (g.code_bytes == 1) unbuild_lext_kernel<uint8_t, uint8_t><<<blocks, 256>>>(h->n_rows, g.S_pad, g.G, h->lext, h->lexv, (uint8_t*)h->lexi);
+        else unbuild_lext_kernel<uint16_t, uint8_t><<<blocks, 256>>>(h->n_rows, g.S_pad, g.G, h->lext, h->lexv, (uint16_t*)h->lexi);
+        DHR_CUDA(cudaGetLastError());
+    }
+    if (g.C_pad > 0 && !h->dns) {
+        DHR_CUDA(cudaMalloc(&h->dns, rows * g.C_pad * 2));
+        const int nkb = (g.C_pad + kDenseTileCols - 1) / kDenseTileCols;
+        const long long total = h->n_rows * (g.C_pad / 8);
+        unbuild_dnst_kernel<<<(unsigned)((total + 255) / 256), 256>>>(h->n_rows, g.C_pad, nkb, h->dnst, h->dns);
+        DHR_CUDA(cudaGetLastError());
+    }
+    DHR_CUDA(cudaDeviceSynchronize());
+    h->stats.rowmajor_rebuilds++;
+    return DHR_OK;
+}
+
 static int ingest_device(dhr_index* h, long long n, int val_dtype, const void* d_vals, long long vstride, int idx_dtype,
                          const void* d_idx, long long istride) {
     const Geometry& g = h->g;
@@ -260,6 +343,7 @@ int dhr_index_create(dhr_index** out, int device, int64_t cap_rows, int n_slices
     g.D_pad = g.S_pad * group;
     g.C_pad = (int)round_up(n_dense, 8);
     const bool narrow = (flags & DHR_INDEX_NARROW_CODES) != 0;
+    h->keep_rowmajor = (flags & DHR_INDEX_KEEP_ROWMAJOR) != 0;
     g.code_bytes = (idx_dtype_size(h->idx_dtype) == 1 || narrow || n_slices == 0) ? 1 : 2;
     g.unit_halves = (group % 8 == 0) ? group : (group % 4 == 0) ? 2 * group : (group % 2 == 0) ? 4 * group : 8 * group;
     g.unit_slices = g.unit_halves / group;
@@ -375,6 +459,9 @@ int dhr_index_finalize(dhr_index* h) {
             DHR_CUDA(cudaDeviceSynchronize());
         }
     }
+    // the row-major arrays only serve K1 / K4 / the overflow fallback: with complete tiled copies they are dropped (half the
+    // HBM footprint) and rebuilt on first use, unless the index was created with DHR_INDEX_KEEP_ROWMAJOR
+    if (!h->keep_rowmajor) DHR_TRY(drop_rowmajor_unchecked(h));
     // the ingest staging buffers are not needed any more
     if (h->stage_a) { cudaFree(h->stage_a); h->stage_a = nullptr; h->stage_a_bytes = 0; }
     if (h->stage_b) { cudaFree(h->stage_b); h->stage_b = nullptr; h->stage_b_bytes = 0; }
@@ -401,8 +488,9 @@ int dhr_index_close(dhr_index* h) {
     cudaDeviceSynchronize();
     void* bufs[] = {h->lexv, h->lexi, h->dns, h->dnst, h->lext, h->qblocks, h->qblock_bytes, h->scratch, h->d_flags, h->stage_a, h->stage_b, h->q_lex16, h->q_lex32, h->q_dns16, h->q_dns32,
                     h->q_code, h->topk.tau, h->topk.cnt, h->topk.overflow, h->topk.cand_score, h->topk.cand_row,
-                    h->d_out_scores, h->d_out_rows, h->d_out_counts};
+                    h->d_out_scores, h->d_out_rows, h->d_out_counts, h->d_overflow, h->stage_c};
     for (void* b : bufs) if (b) cudaFree(b);
+    for (cudaEvent_t e : h->batch_events) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) { if (h->ev_k2_done[i]) cudaEventDestroy(h->ev_k2_done[i]); if (h->ev_k1_done[i]) cudaEventDestroy(h->ev_k1_done[i]); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -427,8 +515,29 @@ int dhr_index_row_bytes(const dhr_index* h, int64_t* bytes) {
     return DHR_OK;
 }
 
+int dhr_index_device_bytes(const dhr_index* h, int64_t* bytes) {
+    if (!h || !bytes) return DHR_ERR_INVALID;
+    const Geometry& g = h->g;
+    const size_t rows = (size_t)(h->capacity > 0 ? h->capacity : 1);
+    size_t b = 0;
+    if (h->lexv) b += rows * g.D_pad * 2;
+    if (h->lexi) b += rows * g.S_pad * g.code_bytes;
+    if (h->dns) b += rows * g.C_pad * 2;
+    b += h->lext_bytes + h->dnst_bytes + h->qblocks_bytes + h->qblock_bytes_cap + h->scratch_bytes + h->stage_a_bytes + h->stage_b_bytes +
+         h->stage_c_bytes;
+    if (h->topk.tau) b += (size_t)kMaxInflight * (12 + (size_t)kCandCap * 8);
+    if (h->q_capacity > 0) b += ((size_t)h->q_capacity + kMaxInflight) * ((size_t)g.D_pad * 6 + (size_t)g.S_pad * g.code_bytes + (size_t)g.C_pad * 6);
+    b += h->out_capacity * 12 + h->out_q_capacity * 4 + h->overflow_capacity * 4;
+    *bytes = (int64_t)b;
+    return DHR_OK;
+}
+
 int dhr_index_set_option(dhr_index* h, const char* name, int64_t value) {
     if (!h || !name) return DHR_ERR_INVALID;
+    if (!strcmp(name, "rowmajor")) {
+        if (!h->finalized) return DHR_ERR_STATE;
+        return value ? ensure_rowmajor(h) : drop_rowmajor(h);
+    }
     if (!strcmp(name, "scan_variant")) { if (value < 0 || value > 1) return DHR_ERR_INVALID; h->opt_scan_variant = (int)value; return DHR_OK; }
     if (!strcmp(name, "query_block")) {
         if (value != 1 && value != 2 && value != 4 && value != 8) return DHR_ERR_INVALID;

@@ -46,6 +46,7 @@ struct dhr_index {
     dhr::Geometry g;
     int idx_dtype = DHR_IDX_NONE;
     bool finalized = false;
+    bool keep_rowmajor = false;          // DHR_INDEX_KEEP_ROWMAJOR: never drop lexv / lexi / dns at finalize
     // resident arrays (device)
     __half* lexv = nullptr;              // [capacity][D_pad]
     uint8_t* lexi = nullptr;             // [capacity][S_pad] codes (uint8 or uint16)
@@ -70,7 +71,15 @@ struct dhr_index {
     cudaStream_t aux_stream = nullptr;   // K2 launches of the hybrid tile path
     cudaStream_t aux2_stream = nullptr;  // every second K1t launch of a chunk (launches of one chunk are independent)
     cudaEvent_t ev_k2_done[2] = {nullptr, nullptr}, ev_k1_done[2] = {nullptr, nullptr}, ev_fork = nullptr, ev_join = nullptr, ev_sel = nullptr;
-    float* d_out_scores = nullptr; int64_t* d_out_rows = nullptr; int32_t* d_out_counts = nullptr; size_t out_capacity = 0;
+    float* d_out_scores = nullptr; int64_t* d_out_rows = nullptr; int32_t* d_out_counts = nullptr;
+    size_t out_capacity = 0, out_q_capacity = 0;                   // [Q,k] elements / [Q] counts of the host-output staging
+    uint32_t* d_overflow = nullptr; size_t overflow_capacity = 0;   // [Q] per-query overflow flags of the current search
+    void* stage_c = nullptr; size_t stage_c_bytes = 0;              // rerank candidate staging
+    // stream-ordered search (dhr_search_keys): per-batch completion events and what dhr_search_complete needs
+    std::vector<cudaEvent_t> batch_events;
+    int batch_size = 0, n_batches = 0;
+    struct { bool active = false; int n_queries = 0, k = 0; bool masked = true, f32 = false; uint64_t* out_keys = nullptr; } pending;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     // options
     int opt_scan_variant = 1;            // TMA bulk staging (measured faster than direct loads at QB=1 and QB=8)
     int opt_query_block = 8;
@@ -105,8 +114,16 @@ struct ScanArgs {
 int launch_scan(const dhr_index* h, const ScanArgs& a, int query_block, bool q_f32, int variant, cudaStream_t st);
 size_t scan_tma_smem_bytes(const Geometry& g, int query_block, bool q_f32, int tile_rows, int n_stages);
 
-int launch_select(const TopkState& t, int n_slots, int k, int cap, bool final_pass, int64_t row_offset,
-                  float* out_scores, int64_t* out_rows, int32_t* out_counts, int out_base, cudaStream_t st);
+// where the final pass of a batch writes: either (scores, rows, counts) or packed 64-bit keys (sharded exchange format)
+struct SelectOut {
+    float* scores = nullptr; int64_t* rows = nullptr; int32_t* counts = nullptr;
+    uint64_t* keys = nullptr;            // [Q][k] (ordered score << 32) | (0xFFFFFFFF - global row), 0 = padding
+    uint32_t* overflow = nullptr;        // [Q] set to 1 for queries whose candidate buffer overflowed in any chunk
+    int base = 0;                        // first query of the batch
+    int64_t row_offset = 0;
+};
+int launch_select(const TopkState& t, int n_slots, int k, int cap, bool final_pass, const SelectOut& o, cudaStream_t st);
+void launch_init_slots(const TopkState& t, cudaStream_t st);
 
 int launch_prep_queries(dhr_index* h, int n, int val_dtype, const void* vals, int64_t vstride, int idx_dtype,
                         const void* idx, int64_t istride, float lamda, cudaStream_t st);
@@ -138,6 +155,10 @@ int launch_dense_tile(const dhr_index* h, const void* q_dns16, int n_queries, lo
                       cudaStream_t st);
 
 int ensure_device_buffer(void** p, size_t* cur, size_t need);
+// row-major arrays (lexv / lexi / dns) serve the row scan K1, the rerank kernel K4 and the overflow fallback; they can be
+// dropped once the tiled copies exist (option "rowmajor" = 0) and are rebuilt from the tiled copies on first use
+int ensure_rowmajor(dhr_index* h);
+int drop_rowmajor(dhr_index* h);
 bool is_device_pointer(const void* p);
 
 }  // namespace dhr

@@ -107,10 +107,13 @@ int launch_prep_queries(dhr_index* h, int n, int val_dtype, const void* d_vals, 
     return DHR_OK;
 }
 
+// Slot state at the start of a call.  Between the batches of a call the final-pass select hands every slot back clean
+// (topk.cu), so this runs once per dhr_search / dhr_rerank and not once per batch.
 __global__ void init_slots_kernel(TopkState t, int n_slots) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_slots) { t.tau[i] = -INFINITY; t.cnt[i] = 0u; t.overflow[i] = 0u; }
 }
+void launch_init_slots(const TopkState& t, cudaStream_t st) { init_slots_kernel<<<1, kMaxInflight, 0, st>>>(t, kMaxInflight); }
 
 // ---- workspace ----------------------------------------------------------------------------------
 static int ensure_query_workspace(dhr_index* h, int n) {
@@ -144,22 +147,42 @@ static int ensure_topk_state(dhr_index* h) {
     return DHR_OK;
 }
 
+// device staging of host outputs.  The [Q,k] arrays and the [Q] counts grow independently: a later call with more queries and
+// a smaller k must not reuse a counts buffer sized for fewer queries.
 static int ensure_out_buffers(dhr_index* h, size_t n_queries, int k) {
     const size_t need = n_queries * (size_t)k;
-    if (need <= h->out_capacity && h->d_out_scores) return DHR_OK;
-    if (h->d_out_scores) cudaFree(h->d_out_scores);
-    if (h->d_out_rows) cudaFree(h->d_out_rows);
-    if (h->d_out_counts) cudaFree(h->d_out_counts);
-    h->d_out_scores = nullptr; h->d_out_rows = nullptr; h->d_out_counts = nullptr; h->out_capacity = 0;
-    DHR_CUDA(cudaMalloc(&h->d_out_scores, need * sizeof(float)));
-    DHR_CUDA(cudaMalloc(&h->d_out_rows, need * sizeof(int64_t)));
-    DHR_CUDA(cudaMalloc(&h->d_out_counts, (n_queries + 1) * sizeof(int32_t)));
-    h->out_capacity = need;
+    if (need > h->out_capacity || !h->d_out_scores) {
+        if (h->d_out_scores) cudaFree(h->d_out_scores);
+        if (h->d_out_rows) cudaFree(h->d_out_rows);
+        h->d_out_scores = nullptr; h->d_out_rows = nullptr; h->out_capacity = 0;
+        DHR_CUDA(cudaMalloc(&h->d_out_scores, need * sizeof(float)));
+        DHR_CUDA(cudaMalloc(&h->d_out_rows, need * sizeof(int64_t)));
+        h->out_capacity = need;
+    }
+    if (n_queries > h->out_q_capacity || !h->d_out_counts) {
+        if (h->d_out_counts) cudaFree(h->d_out_counts);
+        h->d_out_counts = nullptr; h->out_q_capacity = 0;
+        DHR_CUDA(cudaMalloc(&h->d_out_counts, (n_queries + 1) * sizeof(int32_t)));
+        h->out_q_capacity = n_queries;
+    }
+    return DHR_OK;
+}
+
+static int ensure_overflow_flags(dhr_index* h, size_t n_queries) {
+    if (n_queries <= h->overflow_capacity && h->d_overflow) return DHR_OK;
+    if (h->d_overflow) cudaFree(h->d_overflow);
+    h->d_overflow = nullptr; h->overflow_capacity = 0;
+    DHR_CUDA(cudaMalloc(&h->d_overflow, (n_queries + 1) * sizeof(uint32_t)));
+    h->overflow_capacity = n_queries;
     return DHR_OK;
 }
 
 // chunk boundaries (row indices).  growth <= 1 selects the overflow-proof uniform schedule.
-static std::vector<long long> chunk_schedule(long long n_rows, int k, int cap, bool safe, long long align = 1) {
+// A chunk [a, b) scanned with tau = k-th best of the first a rows admits ~k*(b/a - 1) rows of a random-order corpus; the
+// growth bound keeps that near half of the cap - k free slots.  Among the growths that give the minimal number of chunks
+// (= selects per batch) the smallest is used, and the chunks after the first are whole multiples of `quantum` rows (the
+// tile path's sub-launch size) so that only the last launch of a batch is ragged.
+static std::vector<long long> chunk_schedule(long long n_rows, int k, int cap, bool safe, long long align = 1, long long quantum = 0) {
     std::vector<long long> b;
     b.push_back(0);
     const long long first = std::min<long long>(n_rows, ((long long)cap - k) / align * align);
@@ -169,10 +192,22 @@ static std::vector<long long> chunk_schedule(long long n_rows, int k, int cap, b
         while (b.back() < n_rows) b.push_back(std::min<long long>(n_rows, b.back() + (cap - k) / align * align));
         return b;
     }
-    double growth = 1.0 + (double)(cap - k) / (2.0 * k);
-    growth = std::min(8.0, std::max(1.25, growth));
+    double gmax = 1.0 + 0.55 * (double)(cap - k) / (double)k;
+    gmax = std::min(9.5, std::max(1.25, gmax));
+    double growth = gmax;
+    if (first > 0 && n_rows > first) {
+        const double ratio = (double)n_rows / (double)first;
+        const double n = ceil(log(ratio) / log(gmax) - 1e-9);
+        growth = std::min(gmax, std::max(1.25, pow(ratio, 1.0 / std::max(1.0, n)) * 1.0001));
+    }
     while (b.back() < n_rows) {
         long long next = (long long)ceil((double)b.back() * growth) / align * align;
+        if (quantum > 0 && next - b.back() >= quantum) {                 // whole sub-launches: nearest multiple, never beyond gmax
+            const long long len = next - b.back();
+            long long q = (len + quantum / 2) / quantum * quantum;
+            while (q > quantum && (double)(b.back() + q) > (double)b.back() * gmax * 1.02) q -= quantum;
+            next = b.back() + q;
+        }
         if (next <= b.back()) next = b.back() + align;
         b.push_back(std::min(n_rows, next));
     }
@@ -200,12 +235,10 @@ static QuerySet query_set(const dhr_index* h, bool f32) {
 
 // scan + select for queries [base, base+nq) of the prepared query set
 static int run_batch(dhr_index* h, const QuerySet& qs, int base, int nq, int k, bool masked, bool safe, int qb,
-                     float* d_scores, int64_t* d_rows, int32_t* d_counts, cudaStream_t st) {
+                     SelectOut so, cudaStream_t st) {
     const Geometry& g = h->g;
     TopkState t = h->topk;
-    init_slots_kernel<<<1, kMaxInflight, 0, st>>>(t, kMaxInflight);
-    DHR_CUDA(cudaGetLastError());
-    h->stats.n_kernel_launches++;
+    so.base = base;
     const std::vector<long long> bounds = chunk_schedule(h->n_rows, k, kCandCap, safe);
     ScanArgs a{};
     a.lexv = h->lexv; a.lexi = h->lexi; a.dns = h->dns;
@@ -237,7 +270,7 @@ static int run_batch(dhr_index* h, const QuerySet& qs, int base, int nq, int k, 
         DHR_TRY(launch_scan(h, a, qb, qs.f32, variant, st));
         if (h->opt_profile) cudaEventRecord(e1, st);
         const bool final_pass = (c + 1 == n_chunks);
-        DHR_TRY(launch_select(t, nq, k, kCandCap, final_pass, h->row_offset, d_scores, d_rows, d_counts, base, st));
+        DHR_TRY(launch_select(t, nq, k, kCandCap, final_pass, so, st));
         if (h->opt_profile) cudaEventRecord(e2, st);
         h->stats.n_scan_launches++;
         h->stats.n_select_launches++;
@@ -245,7 +278,7 @@ static int run_batch(dhr_index* h, const QuerySet& qs, int base, int nq, int k, 
         h->stats.corpus_passes += (double)(a.row_end - a.row_begin) * a.n_groups / (double)std::max<int64_t>(1, h->n_rows);
     }
     if (n_chunks == 0) {   // empty index: all padding
-        DHR_TRY(launch_select(t, nq, k, kCandCap, true, h->row_offset, d_scores, d_rows, d_counts, base, st));
+        DHR_TRY(launch_select(t, nq, k, kCandCap, true, so, st));
         h->stats.n_select_launches++;
         h->stats.n_kernel_launches++;
     }
@@ -254,12 +287,9 @@ static int run_batch(dhr_index* h, const QuerySet& qs, int base, int nq, int k, 
 }
 
 // dense-only index on the tensor-core tile kernel (K2): same chunk schedule, 128-row aligned
-static int run_batch_dense_tile(dhr_index* h, const QuerySet& qs, int base, int nq, int k, float* d_scores, int64_t* d_rows,
-                                int32_t* d_counts, cudaStream_t st) {
+static int run_batch_dense_tile(dhr_index* h, const QuerySet& qs, int base, int nq, int k, SelectOut so, cudaStream_t st) {
     TopkState t = h->topk;
-    init_slots_kernel<<<1, kMaxInflight, 0, st>>>(t, kMaxInflight);
-    DHR_CUDA(cudaGetLastError());
-    h->stats.n_kernel_launches++;
+    so.base = base;
     const std::vector<long long> bounds = chunk_schedule(h->n_rows, k, kCandCap, false, 128);
     const size_t n_chunks = bounds.size() - 1;
     const void* q16 = qs.dns + (size_t)base * qs.dns_stride;
@@ -268,15 +298,16 @@ static int run_batch_dense_tile(dhr_index* h, const QuerySet& qs, int base, int 
         if (h->opt_profile) { e0 = h->events.get(); e1 = h->events.get(); e2 = h->events.get(); cudaEventRecord(e0, st); }
         DHR_TRY(launch_dense_tile(h, q16, nq, 0, bounds[c], bounds[c + 1], 0, nullptr, 0, t, kCandCap, st));
         if (h->opt_profile) cudaEventRecord(e1, st);
-        DHR_TRY(launch_select(t, nq, k, kCandCap, c + 1 == n_chunks, h->row_offset, d_scores, d_rows, d_counts, base, st));
+        DHR_TRY(launch_select(t, nq, k, kCandCap, c + 1 == n_chunks, so, st));
         if (h->opt_profile) cudaEventRecord(e2, st);
         h->stats.n_scan_launches++;
         h->stats.n_select_launches++;
         h->stats.n_kernel_launches += 2;
-        h->stats.corpus_passes += (double)(bounds[c + 1] - bounds[c]) * ((nq + 63) / 64) / (double)std::max<int64_t>(1, h->n_rows);
+        h->stats.corpus_passes += (double)(bounds[c + 1] - bounds[c]) * ((nq + 127) / 128) / (double)std::max<int64_t>(1, h->n_rows);   // K2 (TS): one pass per 128 queries
+        h->stats.dense_flops += 2.0 * (double)(bounds[c + 1] - bounds[c]) * (double)nq * (double)h->g.C;
     }
     if (n_chunks == 0) {
-        DHR_TRY(launch_select(t, nq, k, kCandCap, true, h->row_offset, d_scores, d_rows, d_counts, base, st));
+        DHR_TRY(launch_select(t, nq, k, kCandCap, true, so, st));
         h->stats.n_select_launches++;
         h->stats.n_kernel_launches++;
     }
@@ -326,13 +357,11 @@ static int ensure_tile_workspace(dhr_index* h, const LexTileGeom& t, int n_queri
 }
 
 static int run_batch_hybrid_tile(dhr_index* h, const LexTileGeom& lt, const QuerySet& qs, int base, int nq, int k,
-                                 float* d_scores, int64_t* d_rows, int32_t* d_counts, cudaStream_t st) {
+                                 SelectOut so, cudaStream_t st) {
     const Geometry& g = h->g;
     TopkState t = h->topk;
-    init_slots_kernel<<<1, kMaxInflight, 0, st>>>(t, kMaxInflight);
-    DHR_CUDA(cudaGetLastError());
-    h->stats.n_kernel_launches++;
-    const std::vector<long long> bounds = chunk_schedule(h->n_rows, k, kCandCap, false, kLexTileRows);
+    so.base = base;
+    const std::vector<long long> bounds = chunk_schedule(h->n_rows, k, kCandCap, false, kLexTileRows, kTileSubRows);
     const size_t n_chunks = bounds.size() - 1;
     const void* q16 = qs.dns + (size_t)base * qs.dns_stride;
     const size_t qt0 = (size_t)base / kLexTileQueries;
@@ -401,30 +430,25 @@ static int run_batch_hybrid_tile(dhr_index* h, const LexTileGeom& lt, const Quer
             DHR_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
         }
         if (h->opt_profile) cudaEventRecord(e1, st);
-        DHR_TRY(launch_select(t, nq, k, kCandCap, c + 1 == n_chunks, h->row_offset, d_scores, d_rows, d_counts, base, st));
+        DHR_TRY(launch_select(t, nq, k, kCandCap, c + 1 == n_chunks, so, st));
         if (h->opt_profile) cudaEventRecord(e2, st);
         h->stats.n_select_launches++;
         h->stats.n_kernel_launches++;
         h->stats.corpus_passes += (double)(bounds[c + 1] - bounds[c]) * ((nq + kLexTileQueries - 1) / kLexTileQueries) /
                                   (double)std::max<int64_t>(1, h->n_rows);
+        h->stats.dense_flops += 2.0 * (double)(bounds[c + 1] - bounds[c]) * (double)nq * (double)g.C;
         if (overlap && c + 1 < n_chunks) {                           // the next chunk's K1t launches read the new tau
             DHR_CUDA(cudaEventRecord(h->ev_sel, st));
             DHR_CUDA(cudaStreamWaitEvent(k1s[1], h->ev_sel, 0));
         }
     }
     if (n_chunks == 0) {
-        DHR_TRY(launch_select(t, nq, k, kCandCap, true, h->row_offset, d_scores, d_rows, d_counts, base, st));
+        DHR_TRY(launch_select(t, nq, k, kCandCap, true, so, st));
         h->stats.n_select_launches++;
         h->stats.n_kernel_launches++;
     }
     h->stats.scan_variant = 3;
     return DHR_OK;
-}
-
-// the select kernel sets the sticky per-slot overflow flag; copy it to the per-query array
-__global__ void carry_overflow_kernel(const uint32_t* slot_flags, uint32_t* per_query, int base, int nq) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nq && slot_flags[i]) per_query[base + i] = 1u;
 }
 
 static int stage_queries_to_device(dhr_index* h, int n, int val_dtype, const void* q_vals, int64_t vstride, int idx_dtype,
@@ -473,6 +497,127 @@ static int validate_query_args(const dhr_index* h, int n_queries, int q_val_dtyp
     return DHR_OK;
 }
 
+// ---- the search proper: shared by dhr_search (synchronous, host or device outputs) and dhr_search_keys (stream-ordered,
+// device-resident packed keys, no host synchronisation on the common path) -------------------------------------------------
+struct SearchRequest {
+    int n_queries, q_val_dtype; const void* q_vals; int64_t vstride;
+    int q_idx_dtype; const void* q_idx; int64_t istride;
+    float lamda; int k; bool masked;
+};
+
+// re-run the queries whose candidate buffer overflowed (adversarial row order) with the overflow-proof schedule
+static int rerun_overflowed(dhr_index* h, const std::vector<uint32_t>& flags, int n_queries, int k, bool masked, bool f32,
+                            SelectOut so, cudaStream_t st, int* n_rerun) {
+    const QuerySet qs = query_set(h, f32);
+    int n = 0;
+    so.overflow = nullptr;
+    for (int q = 0; q < n_queries; ++q) {
+        if (!flags[(size_t)q]) continue;
+        ++n;
+        h->stats.n_fallback_queries++;
+        DHR_TRY(ensure_rowmajor(h));
+        DHR_TRY(run_batch(h, qs, q, 1, k, masked, true, 1, so, st));
+    }
+    if (n_rerun) *n_rerun = n;
+    return DHR_OK;
+}
+
+// Enqueue the whole search on `st`.  `so` holds DEVICE output pointers.  Returns with work in flight; the only host
+// synchronisation is the read of the "queries need fp32" flag, which is skipped when the queries are fp16 and lamda == 1
+// (always exactly representable: the reference's on-disk format).
+static int enqueue_search(dhr_index* h, const SearchRequest& r, SelectOut so, bool record_batches, bool* used_f32, cudaStream_t st) {
+    const Geometry& g = h->g;
+    const int n_queries = r.n_queries, k = r.k;
+    h->stats = dhr_stats{};
+    h->stats.n_queries = n_queries;
+    h->stats.bytes_per_pass = (double)h->n_rows * (double)g.row_bytes();
+    h->events.reset();
+
+    DHR_TRY(ensure_query_workspace(h, n_queries));
+    DHR_TRY(ensure_topk_state(h));
+    DHR_TRY(ensure_overflow_flags(h, (size_t)n_queries));
+    const bool exact_f16 = r.q_val_dtype == DHR_VAL_F16 && r.lamda == 1.0f;
+    if (!exact_f16) DHR_CUDA(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(int), st));
+    DHR_CUDA(cudaMemsetAsync(h->d_overflow, 0, (size_t)n_queries * sizeof(uint32_t), st));
+
+    if (h->opt_profile) { h->ev_begin = h->events.get(); h->ev_end = h->events.get(); cudaEventRecord(h->ev_begin, st); }
+
+    const void* d_vals; const void* d_idx; int64_t d_vs, d_is;
+    DHR_TRY(stage_queries_to_device(h, n_queries, r.q_val_dtype, r.q_vals, r.vstride, r.q_idx_dtype, r.masked ? r.q_idx : nullptr,
+                                    r.istride, &d_vals, &d_vs, &d_idx, &d_is, st));
+    DHR_TRY(launch_prep_queries(h, n_queries, r.q_val_dtype, d_vals, d_vs, r.q_idx_dtype, d_idx, d_is, r.lamda, st));
+    int need_f32 = 0;
+    if (!exact_f16) {
+        DHR_CUDA(cudaMemcpyAsync(&need_f32, h->d_flags + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+        DHR_CUDA(cudaStreamSynchronize(st));
+    }
+    *used_f32 = need_f32 != 0;
+    launch_init_slots(h->topk, st);
+    DHR_CUDA(cudaGetLastError());
+    h->stats.n_kernel_launches++;
+
+    so.overflow = h->d_overflow;
+    so.row_offset = h->row_offset;
+    const QuerySet qs = query_set(h, need_f32 != 0);
+    int qb = h->opt_query_block;
+    int groups = h->opt_query_groups;
+    if (qb * groups > kMaxScanInflight) groups = kMaxScanInflight / qb;
+    int slots = qb * groups;
+    // tensor-core tile path: dense-only index, or the unmasked (--IP) first stage of any index through K2 over the
+    // lexical + dense columns is not available (K2 reads the dense block only) -> dense-only; queries exactly fp16
+    const bool tile_dense = h->opt_tile_mode && g.S == 0 && !qs.f32 && dense_tile_supported(g, nullptr);
+    if (tile_dense) { slots = kMaxInflight; qb = 64; groups = kMaxInflight / 64; }
+    const int rt = std::max(1, h->max_code + 1);
+    const bool tile_hybrid = h->opt_tile_mode && g.S > 0 && r.masked && !qs.f32 && h->lext && lex_tile_supported(g, rt) &&
+                             (g.C_pad == 0 || dense_tile_supported(g, nullptr));
+    LexTileGeom lt{};
+    if (tile_hybrid) {
+        lt = lex_tile_geom(g, rt);
+        DHR_TRY(ensure_tile_workspace(h, lt, n_queries));
+        DHR_TRY(launch_lex_tile_prep(h, lt, h->q_lex16, h->q_code, n_queries, h->qblocks, h->qblock_bytes, st));
+        h->stats.n_prep_launches++; h->stats.n_kernel_launches++;
+        slots = kMaxInflight; qb = kLexTileQueries; groups = kMaxInflight / kLexTileQueries;
+    }
+    if (!tile_dense && !tile_hybrid) DHR_TRY(ensure_rowmajor(h));          // the row scan K1 reads the row-major arrays
+    h->stats.query_block = qb;
+    h->stats.query_groups = groups;
+    h->batch_size = slots;
+    int b = 0;
+    for (int base = 0; base < n_queries; base += slots, ++b) {
+        const int nq = std::min(slots, n_queries - base);
+        if (tile_dense) DHR_TRY(run_batch_dense_tile(h, qs, base, nq, k, so, st));
+        else if (tile_hybrid) DHR_TRY(run_batch_hybrid_tile(h, lt, qs, base, nq, k, so, st));
+        else DHR_TRY(run_batch(h, qs, base, nq, k, r.masked, false, qb, so, st));
+        if (record_batches) {
+            while ((int)h->batch_events.size() <= b) {
+                cudaEvent_t e;
+                DHR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                h->batch_events.push_back(e);
+            }
+            DHR_CUDA(cudaEventRecord(h->batch_events[(size_t)b], st));
+        }
+    }
+    h->n_batches = b;
+    if (h->opt_profile) cudaEventRecord(h->ev_end, st);
+    return DHR_OK;
+}
+
+static void collect_profile(dhr_index* h) {
+    if (!h->opt_profile || !h->ev_begin) return;
+    // events were taken in triples (scan begin, scan end, select end) after the two bracket events
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_begin, h->ev_end);
+    h->stats.total_ms = ms;
+    for (size_t i = 2; i + 2 < h->events.used; i += 3) {
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, h->events.ev[i], h->events.ev[i + 1]);
+        cudaEventElapsedTime(&b, h->events.ev[i + 1], h->events.ev[i + 2]);
+        h->stats.scan_ms += a;
+        h->stats.select_ms += b;
+    }
+    h->ev_begin = h->ev_end = nullptr;
+}
+
 }  // namespace dhr
 
 using namespace dhr;
@@ -484,111 +629,104 @@ extern "C" int dhr_search(dhr_index* h, int n_queries, int q_val_dtype, const vo
     DHR_TRY(validate_query_args(h, n_queries, q_val_dtype, q_vals, vstride, q_idx_dtype, q_idx, istride, k, masked));
     if (!out_scores || !out_rows) return DHR_ERR_INVALID;
     if (n_queries == 0) return DHR_OK;
+    if (h->pending.active) return DHR_ERR_STATE;                          // a dhr_search_keys call awaits dhr_search_complete
     DHR_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const Geometry& g = h->g;
-
-    h->stats = dhr_stats{};
-    h->stats.n_queries = n_queries;
-    h->stats.bytes_per_pass = (double)h->n_rows * (double)g.row_bytes();
-    h->events.reset();
-
-    DHR_TRY(ensure_query_workspace(h, n_queries));
-    DHR_TRY(ensure_topk_state(h));
-    DHR_CUDA(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(int), st));
-
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-    if (h->opt_profile) { ev_begin = h->events.get(); ev_end = h->events.get(); cudaEventRecord(ev_begin, st); }
-
-    const void* d_vals; const void* d_idx; int64_t d_vs, d_is;
-    DHR_TRY(stage_queries_to_device(h, n_queries, q_val_dtype, q_vals, vstride, q_idx_dtype, masked ? q_idx : nullptr, istride,
-                                    &d_vals, &d_vs, &d_idx, &d_is, st));
-    DHR_TRY(launch_prep_queries(h, n_queries, q_val_dtype, d_vals, d_vs, q_idx_dtype, d_idx, d_is, lamda, st));
-    int need_f32 = 0;
-    DHR_CUDA(cudaMemcpyAsync(&need_f32, h->d_flags + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
-    DHR_CUDA(cudaStreamSynchronize(st));
 
     const bool out_dev = is_device_pointer(out_scores) && is_device_pointer(out_rows) &&
                          (!out_counts || is_device_pointer(out_counts));
-    float* d_scores = out_scores; int64_t* d_rows = out_rows; int32_t* d_counts = out_counts;
+    SelectOut so{};
+    so.scores = out_scores; so.rows = out_rows; so.counts = out_counts;
     if (!out_dev) {
         DHR_TRY(ensure_out_buffers(h, (size_t)n_queries, k));
-        d_scores = h->d_out_scores; d_rows = h->d_out_rows; d_counts = h->d_out_counts;
+        so.scores = h->d_out_scores; so.rows = h->d_out_rows; so.counts = h->d_out_counts;
     }
-    uint32_t* d_overflow = nullptr;
-    DHR_CUDA(cudaMalloc(&d_overflow, (size_t)n_queries * sizeof(uint32_t)));
-    int status = DHR_OK;
+    const SearchRequest r{n_queries, q_val_dtype, q_vals, vstride, q_idx_dtype, q_idx, istride, lamda, k, masked};
+    bool f32 = false;
+    int status = enqueue_search(h, r, so, false, &f32, st);
+    // one synchronisation: results (host outputs) and the per-query overflow flags come back together
     std::vector<uint32_t> h_overflow((size_t)n_queries, 0u);
-    do {
-        if ((status = (cudaMemsetAsync(d_overflow, 0, (size_t)n_queries * sizeof(uint32_t), st) == cudaSuccess) ? DHR_OK : DHR_ERR_CUDA)) break;
-        const QuerySet qs = query_set(h, need_f32 != 0);
-        int qb = h->opt_query_block;
-        int groups = h->opt_query_groups;
-        if (qb * groups > kMaxScanInflight) groups = kMaxScanInflight / qb;
-        int slots = qb * groups;
-        // tensor-core tile path: dense-only index (or unmasked search of an index without lexical part),
-        // queries exactly representable in fp16
-        const bool tile_dense = h->opt_tile_mode && g.S == 0 && !qs.f32 && dense_tile_supported(g, nullptr);
-        if (tile_dense) { slots = kMaxInflight; qb = 64; groups = kMaxInflight / 64; }
-        const int rt = std::max(1, h->max_code + 1);
-        const bool tile_hybrid = h->opt_tile_mode && g.S > 0 && masked && !qs.f32 && h->lext && lex_tile_supported(g, rt) &&
-                                 (g.C_pad == 0 || dense_tile_supported(g, nullptr));
-        LexTileGeom lt{};
-        if (tile_hybrid) {
-            lt = lex_tile_geom(g, rt);
-            if ((status = ensure_tile_workspace(h, lt, n_queries)) != DHR_OK) break;
-            if ((status = launch_lex_tile_prep(h, lt, h->q_lex16, h->q_code, n_queries, h->qblocks, h->qblock_bytes, st)) != DHR_OK) break;
-            h->stats.n_prep_launches++; h->stats.n_kernel_launches++;
-            slots = kMaxInflight; qb = kLexTileQueries; groups = kMaxInflight / kLexTileQueries;
-        }
-        h->stats.query_block = qb;
-        h->stats.query_groups = groups;
-        for (int base = 0; base < n_queries && status == DHR_OK; base += slots) {
-            const int nq = std::min(slots, n_queries - base);
-            if (tile_dense) status = run_batch_dense_tile(h, qs, base, nq, k, d_scores, d_rows, d_counts, st);
-            else if (tile_hybrid) status = run_batch_hybrid_tile(h, lt, qs, base, nq, k, d_scores, d_rows, d_counts, st);
-            else status = run_batch(h, qs, base, nq, k, masked, false, qb, d_scores, d_rows, d_counts, st);
-            if (status == DHR_OK) {
-                carry_overflow_kernel<<<1, kMaxInflight, 0, st>>>(h->topk.overflow, d_overflow, base, nq);
-                h->stats.n_kernel_launches++;
-                if (cudaGetLastError() != cudaSuccess) status = DHR_ERR_CUDA;
-            }
-        }
-        if (status != DHR_OK) break;
-        if (cudaMemcpyAsync(h_overflow.data(), d_overflow, (size_t)n_queries * sizeof(uint32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-            cudaStreamSynchronize(st) != cudaSuccess) { status = DHR_ERR_CUDA; break; }
-        for (int q = 0; q < n_queries && status == DHR_OK; ++q) {
-            if (!h_overflow[q]) continue;
-            h->stats.n_fallback_queries++;
-            status = run_batch(h, qs, q, 1, k, masked, true, 1, d_scores, d_rows, d_counts, st);
-        }
-    } while (0);
-    if (status == DHR_OK && h->opt_profile) cudaEventRecord(ev_end, st);
-    if (status == DHR_OK && !out_dev) {
+    auto copy_out = [&]() -> int {
+        if (out_dev) return DHR_OK;
         const size_t n = (size_t)n_queries * k;
-        if (cudaMemcpyAsync(out_scores, d_scores, n * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-            cudaMemcpyAsync(out_rows, d_rows, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-            (out_counts && cudaMemcpyAsync(out_counts, d_counts, (size_t)n_queries * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess))
-            status = DHR_ERR_CUDA;
-    }
+        DHR_CUDA(cudaMemcpyAsync(out_scores, so.scores, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        DHR_CUDA(cudaMemcpyAsync(out_rows, so.rows, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        if (out_counts) DHR_CUDA(cudaMemcpyAsync(out_counts, so.counts, (size_t)n_queries * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        return DHR_OK;
+    };
+    if (status == DHR_OK) status = copy_out();
+    if (status == DHR_OK && cudaMemcpyAsync(h_overflow.data(), h->d_overflow, (size_t)n_queries * sizeof(uint32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        status = DHR_ERR_CUDA;
     if (cudaStreamSynchronize(st) != cudaSuccess && status == DHR_OK) status = DHR_ERR_CUDA;
-    cudaFree(d_overflow);
+    if (status == DHR_OK) {
+        int n_rerun = 0;
+        status = rerun_overflowed(h, h_overflow, n_queries, k, masked, f32, so, st, &n_rerun);
+        if (status == DHR_OK && n_rerun > 0) {
+            status = copy_out();
+            if (cudaStreamSynchronize(st) != cudaSuccess && status == DHR_OK) status = DHR_ERR_CUDA;
+        }
+    }
     if (status == DHR_ERR_CUDA) { set_cuda_error(cudaGetLastError(), "dhr_search", __FILE__, __LINE__); return status; }
     if (status != DHR_OK) return status;
+    collect_profile(h);
+    return DHR_OK;
+}
 
-    if (h->opt_profile) {
-        // events were taken in triples (scan begin, scan end, select end) after the two bracket events
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, ev_begin, ev_end);
-        h->stats.total_ms = ms;
-        for (size_t i = 2; i + 2 < h->events.used; i += 3) {
-            float a = 0.f, b = 0.f;
-            cudaEventElapsedTime(&a, h->events.ev[i], h->events.ev[i + 1]);
-            cudaEventElapsedTime(&b, h->events.ev[i + 1], h->events.ev[i + 2]);
-            h->stats.scan_ms += a;
-            h->stats.select_ms += b;
-        }
-    }
+// ---- stream-ordered variant for the sharded search --------------------------------------------------------------------
+extern "C" int dhr_search_keys(dhr_index* h, int n_queries, int q_val_dtype, const void* q_vals, int64_t vstride, int q_idx_dtype,
+                               const void* q_idx, int64_t istride, float lamda, int k, unsigned flags, uint64_t* out_keys,
+                               void* stream) {
+    const bool masked = !(flags & DHR_SEARCH_UNMASKED);
+    DHR_TRY(validate_query_args(h, n_queries, q_val_dtype, q_vals, vstride, q_idx_dtype, q_idx, istride, k, masked));
+    if (!out_keys || !is_device_pointer(out_keys)) return DHR_ERR_INVALID;
+    if (h->pending.active) return DHR_ERR_STATE;
+    if ((uint64_t)h->row_offset + (uint64_t)h->n_rows >= 0xFFFFFFFFull) return DHR_ERR_UNSUPPORTED;   // global rows are packed in 32 bits
+    if (n_queries == 0) return DHR_OK;
+    DHR_CUDA(cudaSetDevice(h->device));
+    SelectOut so{};
+    so.keys = out_keys;
+    const SearchRequest r{n_queries, q_val_dtype, q_vals, vstride, q_idx_dtype, q_idx, istride, lamda, k, masked};
+    bool f32 = false;
+    const int status = enqueue_search(h, r, so, true, &f32, (cudaStream_t)stream);
+    if (status == DHR_ERR_CUDA) set_cuda_error(cudaGetLastError(), "dhr_search_keys", __FILE__, __LINE__);
+    if (status != DHR_OK) return status;
+    h->pending.active = true; h->pending.n_queries = n_queries; h->pending.k = k; h->pending.masked = masked; h->pending.f32 = f32;
+    h->pending.out_keys = out_keys;
+    return DHR_OK;
+}
+
+extern "C" int dhr_search_batches(const dhr_index* h, int* batch_size, int* n_batches) {
+    if (!h) return DHR_ERR_INVALID;
+    if (batch_size) *batch_size = h->batch_size;
+    if (n_batches) *n_batches = h->n_batches;
+    return DHR_OK;
+}
+
+extern "C" int dhr_search_wait_batch(dhr_index* h, int batch, void* stream) {
+    if (!h || !h->pending.active || batch < 0 || batch >= h->n_batches) return DHR_ERR_INVALID;
+    DHR_CUDA(cudaSetDevice(h->device));
+    DHR_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, h->batch_events[(size_t)batch], 0));
+    return DHR_OK;
+}
+
+extern "C" int dhr_search_complete(dhr_index* h, int* n_rerun, void* stream) {
+    if (!h) return DHR_ERR_INVALID;
+    if (n_rerun) *n_rerun = 0;
+    if (!h->pending.active) return DHR_ERR_STATE;
+    DHR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_queries = h->pending.n_queries;
+    std::vector<uint32_t> h_overflow((size_t)n_queries, 0u);
+    h->pending.active = false;
+    DHR_CUDA(cudaMemcpyAsync(h_overflow.data(), h->d_overflow, (size_t)n_queries * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    DHR_CUDA(cudaStreamSynchronize(st));
+    SelectOut so{};
+    so.keys = h->pending.out_keys; so.row_offset = h->row_offset;
+    int n = 0;
+    DHR_TRY(rerun_overflowed(h, h_overflow, n_queries, h->pending.k, h->pending.masked, h->pending.f32, so, st, &n));
+    if (n > 0) DHR_CUDA(cudaStreamSynchronize(st));
+    if (n_rerun) *n_rerun = n;
+    collect_profile(h);
     return DHR_OK;
 }
 
@@ -599,6 +737,7 @@ extern "C" int dhr_rerank(dhr_index* h, int n_queries, int q_val_dtype, const vo
     if (!out_scores || !out_rows || !cand_rows || n_cand < 1) return DHR_ERR_INVALID;
     if (n_cand > kCandCap) return DHR_ERR_UNSUPPORTED;
     if (n_queries == 0) return DHR_OK;
+    if (h->pending.active) return DHR_ERR_STATE;
     DHR_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     const Geometry& g = h->g;
@@ -606,37 +745,40 @@ extern "C" int dhr_rerank(dhr_index* h, int n_queries, int q_val_dtype, const vo
     h->stats.n_queries = n_queries;
     DHR_TRY(ensure_query_workspace(h, n_queries));
     DHR_TRY(ensure_topk_state(h));
+    DHR_TRY(ensure_rowmajor(h));
     DHR_CUDA(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(int), st));
     const void* d_vals; const void* d_idx; int64_t d_vs, d_is;
     DHR_TRY(stage_queries_to_device(h, n_queries, q_val_dtype, q_vals, vstride, q_idx_dtype, q_idx, istride, &d_vals, &d_vs,
                                     &d_idx, &d_is, st));
     DHR_TRY(launch_prep_queries(h, n_queries, q_val_dtype, d_vals, d_vs, q_idx_dtype, d_idx, d_is, lamda, st));
     int need_f32 = 0;
-    DHR_CUDA(cudaMemcpyAsync(&need_f32, h->d_flags + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
-    DHR_CUDA(cudaStreamSynchronize(st));
+    if (!(q_val_dtype == DHR_VAL_F16 && lamda == 1.0f)) {
+        DHR_CUDA(cudaMemcpyAsync(&need_f32, h->d_flags + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+        DHR_CUDA(cudaStreamSynchronize(st));
+    }
 
     const bool out_dev = is_device_pointer(out_scores) && is_device_pointer(out_rows) &&
                          (!out_counts || is_device_pointer(out_counts));
-    float* d_scores = out_scores; int64_t* d_rows = out_rows; int32_t* d_counts = out_counts;
+    SelectOut so{};
+    so.scores = out_scores; so.rows = out_rows; so.counts = out_counts; so.row_offset = h->row_offset;
     if (!out_dev) {
         DHR_TRY(ensure_out_buffers(h, (size_t)n_queries, k));
-        d_scores = h->d_out_scores; d_rows = h->d_out_rows; d_counts = h->d_out_counts;
+        so.scores = h->d_out_scores; so.rows = h->d_out_rows; so.counts = h->d_out_counts;
     }
     const long long* d_cand = (const long long*)cand_rows;
-    long long* d_cand_owned = nullptr;
     if (!is_device_pointer(cand_rows)) {
-        DHR_CUDA(cudaMalloc(&d_cand_owned, (size_t)n_queries * n_cand * sizeof(long long)));
-        cudaError_t e = cudaMemcpyAsync(d_cand_owned, cand_rows, (size_t)n_queries * n_cand * sizeof(long long), cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess) { cudaFree(d_cand_owned); set_cuda_error(e, "cudaMemcpyAsync(cand)", __FILE__, __LINE__); return DHR_ERR_CUDA; }
-        d_cand = d_cand_owned;
+        DHR_TRY(ensure_device_buffer(&h->stage_c, &h->stage_c_bytes, (size_t)n_queries * n_cand * sizeof(long long)));
+        DHR_CUDA(cudaMemcpyAsync(h->stage_c, cand_rows, (size_t)n_queries * n_cand * sizeof(long long), cudaMemcpyHostToDevice, st));
+        d_cand = (const long long*)h->stage_c;
     }
     const QuerySet qs = query_set(h, need_f32 != 0);
     int status = DHR_OK;
+    launch_init_slots(h->topk, st);
+    h->stats.n_kernel_launches++;
     for (int base = 0; base < n_queries && status == DHR_OK; base += kMaxInflight) {
         const int nq = std::min(kMaxInflight, n_queries - base);
         TopkState t = h->topk;
-        init_slots_kernel<<<1, kMaxInflight, 0, st>>>(t, kMaxInflight);
-        h->stats.n_kernel_launches += 3;
+        h->stats.n_kernel_launches += 2;
         ScanArgs a{};
         a.lexv = h->lexv; a.lexi = h->lexi; a.dns = h->dns;
         a.S_pad = g.S_pad; a.D_pad = g.D_pad; a.C_pad = g.C_pad; a.n_units = g.n_units; a.n_chunks = g.n_chunks;
@@ -646,20 +788,19 @@ extern "C" int dhr_rerank(dhr_index* h, int n_queries, int q_val_dtype, const vo
         a.n_queries = nq; a.n_groups = nq; a.masked = 1;
         a.tau = t.tau; a.cnt = t.cnt; a.cand_score = t.cand_score; a.cand_row = t.cand_row; a.cap = kCandCap;
         status = launch_rerank(h, a, qs.f32, d_cand + (size_t)base * n_cand, n_cand, st);
-        if (status == DHR_OK)
-            status = launch_select(t, nq, k, kCandCap, true, h->row_offset, d_scores, d_rows, d_counts, base, st);
+        so.base = base;
+        if (status == DHR_OK) status = launch_select(t, nq, k, kCandCap, true, so, st);
         h->stats.n_scan_launches++;
         h->stats.n_select_launches++;
     }
     if (status == DHR_OK && !out_dev) {
         const size_t n = (size_t)n_queries * k;
-        if (cudaMemcpyAsync(out_scores, d_scores, n * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-            cudaMemcpyAsync(out_rows, d_rows, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-            (out_counts && cudaMemcpyAsync(out_counts, d_counts, (size_t)n_queries * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess))
+        if (cudaMemcpyAsync(out_scores, so.scores, n * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(out_rows, so.rows, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            (out_counts && cudaMemcpyAsync(out_counts, so.counts, (size_t)n_queries * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess))
             status = DHR_ERR_CUDA;
     }
     if (cudaStreamSynchronize(st) != cudaSuccess && status == DHR_OK) status = DHR_ERR_CUDA;
-    if (d_cand_owned) cudaFree(d_cand_owned);
     if (status == DHR_ERR_CUDA) set_cuda_error(cudaGetLastError(), "dhr_rerank", __FILE__, __LINE__);
     return status;
 }

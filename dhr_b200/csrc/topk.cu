@@ -43,8 +43,11 @@ constexpr int kSelectKeysPerThread = kCandCap / kSelectThreads;
 static_assert(kCandCap % kSelectThreads == 0, "candidate keys are distributed evenly over the select CTA");
 
 __global__ void __launch_bounds__(kSelectThreads, 1)
-topk_select_kernel(TopkState t, int k, int cap, int final_pass, long long row_offset, float* out_scores,
-                   long long* out_rows, int* out_counts, int out_base) {
+topk_select_kernel(TopkState t, int k, int cap, int final_pass, const SelectOut o) {
+    const long long row_offset = o.row_offset;
+    float* out_scores = o.scores; long long* out_rows = (long long*)o.rows; int* out_counts = o.counts;
+    unsigned long long* out_keys = (unsigned long long*)o.keys;
+    const int out_base = o.base;
     extern __shared__ __align__(16) unsigned long long keys[];          // [m] selected keys, m = pow2 >= min(n, k)
     __shared__ uint32_t whist[kSelectThreads / 32][256];              // one histogram per warp
     __shared__ uint32_t hist[256];
@@ -54,7 +57,7 @@ topk_select_kernel(TopkState t, int k, int cap, int final_pass, long long row_of
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t raw = t.cnt[slot];
     const int n = (int)min(raw, (uint32_t)cap);
-    if (raw > (uint32_t)cap && tid == 0) t.overflow[slot] = 1u;
+    const bool overflowed = raw > (uint32_t)cap || t.overflow[slot] != 0u;   // sticky over the chunks of a batch
     float* cs = t.cand_score + (size_t)slot * cap;
     int32_t* cr = t.cand_row + (size_t)slot * cap;
     unsigned long long r[kSelectKeysPerThread];
@@ -146,18 +149,35 @@ topk_select_kernel(TopkState t, int k, int cap, int final_pass, long long row_of
     uint32_t pos = wtot[warp] + incl - mine;
 #pragma unroll
     for (int j = 0; j < kSelectKeysPerThread; ++j)
-        if (tid + j * kSelectThreads < n && r[j] >= kth) keys[pos++] = r[j];
+        if (tid + j * kSelectThreads < n && r[j] >= kth) {
+            if (pos < (uint32_t)m) keys[pos] = r[j];                       // keys are unique for scans; duplicated rerank candidates must not run past m
+            ++pos;
+        }
     bitonic_sort_desc(keys, m, tid, kSelectThreads);
     for (int i = tid; i < keep; i += kSelectThreads) {
         const unsigned long long key = keys[i];
         cs[i] = key_score(key);
         cr[i] = (int32_t)key_row(key);
     }
+    __syncthreads();                                                     // every thread has read cnt / overflow of this slot
     if (tid == 0) {
-        t.cnt[slot] = (uint32_t)keep;
-        t.tau[slot] = (n >= k) ? key_score(keys[k - 1]) : -INFINITY;
+        if (final_pass) {
+            // the slot is handed to the next batch clean (no separate init / carry kernels between batches)
+            t.cnt[slot] = 0u; t.tau[slot] = -INFINITY; t.overflow[slot] = 0u;
+            if (o.overflow && overflowed) o.overflow[out_base + slot] = 1u;
+        } else {
+            t.cnt[slot] = (uint32_t)keep;
+            t.tau[slot] = (n >= k) ? key_score(keys[k - 1]) : -INFINITY;
+            t.overflow[slot] = overflowed ? 1u : 0u;
+        }
     }
-    if (final_pass) {
+    if (final_pass && out_keys) {
+        // exchange format of the sharded search: (ordered score << 32) | (0xFFFFFFFF - GLOBAL row); 0 = padding.  Descending
+        // key order is (score desc, global row asc) on every shard, so the merge is a plain 64-bit merge.
+        unsigned long long* ok = out_keys + (size_t)(out_base + slot) * k;
+        for (int i = tid; i < k; i += kSelectThreads) ok[i] = i < keep ? keys[i] - (unsigned long long)row_offset : 0ull;
+        if (tid == 0 && out_counts) out_counts[out_base + slot] = keep;
+    } else if (final_pass) {
         float* os = out_scores + (size_t)(out_base + slot) * k;
         long long* orow = out_rows + (size_t)(out_base + slot) * k;
         for (int i = tid; i < k; i += kSelectThreads) {
@@ -174,95 +194,183 @@ topk_select_kernel(TopkState t, int k, int cap, int final_pass, long long row_of
     }
 }
 
-int launch_select(const TopkState& t, int n_slots, int k, int cap, bool final_pass, int64_t row_offset,
-                  float* out_scores, int64_t* out_rows, int32_t* out_counts, int out_base, cudaStream_t st) {
+int launch_select(const TopkState& t, int n_slots, int k, int cap, bool final_pass, const SelectOut& o, cudaStream_t st) {
     if (n_slots <= 0) return DHR_OK;
     if (cap > kCandCap) return DHR_ERR_INVALID;
     int m = 2;
     while (m < std::min(k, cap)) m <<= 1;
     const size_t smem = (size_t)m * sizeof(unsigned long long);
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
+    // the attribute is per device: set it on every launch that needs the opt-in (a process may hold indexes on several GPUs)
+    if (smem > 48 * 1024)
         DHR_CUDA(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
-    topk_select_kernel<<<n_slots, kSelectThreads, smem, st>>>(t, k, cap, final_pass ? 1 : 0, (long long)row_offset,
-                                                              out_scores, (long long*)out_rows, out_counts, out_base);
+    topk_select_kernel<<<n_slots, kSelectThreads, smem, st>>>(t, k, cap, final_pass ? 1 : 0, o);
     DHR_CUDA(cudaGetLastError());
     return DHR_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
-// shard merge: [P, Q, k] -> [Q, k].  Rows are global ids (int64); they are ranked through their
-// position in the gathered list only when scores tie, so the key uses the 64-bit row directly:
-// two-key sort = sort by (score desc, row asc) with a 96-bit comparison done as key + payload.
+// shard merge: P per-shard top-k lists of one query -> top-k of their union (replaces the per-query
+// argsort of retrieval/merge.result.py:39 and is the step after the NCCL all-gather).
+//
+// Progressive bitonic merge, one CTA per query: the running best list (m = pow2 >= k items, descending)
+// sits in the first half of a 2m-item shared buffer; the next shard's list is loaded into the second half;
+// since both halves are sorted descending, one "flip" stage (compare i with 2m-1-i) followed by the
+// log2(m) half-cleaner stages sorts the first half descending -- log2(2m) stages per shard instead of a
+// full sort of P*k items, and shared memory is O(2m) whatever P.  A list that is NOT sorted on arrival
+// (dhr_topk_merge accepts arbitrary input) is detected while loading and bitonic-sorted first.
+//
+// Two item types share the code: 64-bit packed keys (the sharded search's exchange format) and
+// {ordered score, int64 row} pairs (generic entry point; rows rank by value when scores tie).
 // ---------------------------------------------------------------------------------------------
 struct MergeItem { unsigned int s; unsigned int pad; long long row; };
 
-__device__ __forceinline__ bool merge_before(const MergeItem& a, const MergeItem& b) {
-    // true if a ranks strictly before b
-    if (a.s != b.s) return a.s > b.s;
-    return (unsigned long long)a.row < (unsigned long long)b.row;   // padding rows (-1) compare last
-}
-
-__global__ void __launch_bounds__(kSelectThreads, 1)
-topk_merge_kernel(int P, int Q, int k, const float* scores, const long long* rows, float* out_scores, long long* out_rows) {
-    extern __shared__ __align__(16) unsigned char raw_smem[];
-    MergeItem* items = (MergeItem*)raw_smem;
-    const int q = blockIdx.x, tid = threadIdx.x;
-    const int n = P * k;
-    int m = 2;
-    while (m < n) m <<= 1;
-    for (int i = tid; i < m; i += kSelectThreads) {
-        MergeItem it;
-        it.pad = 0;
-        if (i < n) {
-            const int p = i / k, j = i % k;
-            const size_t src = ((size_t)p * Q + q) * k + j;
-            const long long r = rows[src];
-            it.row = r;
-            it.s = r >= 0 ? float_to_ordered(scores[src] + 0.0f) : 0u;
-        } else {
-            it.row = -1;
-            it.s = 0u;
-        }
-        items[i] = it;
+struct KeyTraits {
+    typedef unsigned long long Item;
+    __device__ static __forceinline__ Item pad() { return 0ull; }
+    __device__ static __forceinline__ bool before(const Item& a, const Item& b) { return a > b; }   // a ranks strictly before b
+};
+struct PairTraits {
+    typedef MergeItem Item;
+    __device__ static __forceinline__ Item pad() { return MergeItem{0u, 0u, -1}; }
+    __device__ static __forceinline__ bool before(const Item& a, const Item& b) {
+        if (a.s != b.s) return a.s > b.s;
+        return (unsigned long long)a.row < (unsigned long long)b.row;                                 // padding rows (-1) compare last
     }
+};
+
+constexpr int kMergeThreads = 256;
+
+// descending bitonic sort of items[0, m)
+template <typename T>
+__device__ __forceinline__ void merge_sort_desc(typename T::Item* items, int m, int tid) {
     for (int size = 2; size <= m; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             __syncthreads();
-            for (int t = tid; t < (m >> 1); t += kSelectThreads) {
+            for (int t = tid; t < (m >> 1); t += kMergeThreads) {
                 const int lo = ((t / stride) * (stride << 1)) + (t % stride);
                 const int hi = lo + stride;
                 const bool desc = ((lo & size) == 0);
-                const MergeItem a = items[lo], b = items[hi];
-                const bool swap = desc ? merge_before(b, a) : merge_before(a, b);
+                const typename T::Item a = items[lo], b = items[hi];
+                const bool swap = desc ? T::before(b, a) : T::before(a, b);
                 if (swap) { items[lo] = b; items[hi] = a; }
             }
         }
     }
     __syncthreads();
-    for (int i = tid; i < k; i += kSelectThreads) {
-        const MergeItem it = i < m ? items[i] : MergeItem{0u, 0u, -1};
+}
+
+// items[0, m) and items[m, 2m) both descending -> items[0, m) = the m best of the union, descending
+template <typename T>
+__device__ __forceinline__ void merge_two_desc(typename T::Item* items, int m, int tid) {
+    __syncthreads();
+    for (int t = tid; t < m; t += kMergeThreads) {                        // flip stage: the first half now holds the m best (bitonic)
+        const typename T::Item a = items[t], b = items[2 * m - 1 - t];
+        if (T::before(b, a)) { items[t] = b; items[2 * m - 1 - t] = a; }
+    }
+    for (int stride = m >> 1; stride > 0; stride >>= 1) {                 // half-cleaners on the first half only
+        __syncthreads();
+        for (int t = tid; t < (m >> 1); t += kMergeThreads) {
+            const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+            const int hi = lo + stride;
+            const typename T::Item a = items[lo], b = items[hi];
+            if (T::before(b, a)) { items[lo] = b; items[hi] = a; }
+        }
+    }
+    __syncthreads();
+}
+
+template <typename T, typename Load>
+__device__ __forceinline__ void merge_parts(typename T::Item* items, int P, int k, int m, int tid, Load load) {
+    __shared__ int unsorted;
+    for (int p = 0; p < P; ++p) {
+        typename T::Item* dst = items + (p == 0 ? 0 : m);
+        if (tid == 0) unsorted = 0;
+        __syncthreads();
+        for (int i = tid; i < m; i += kMergeThreads) dst[i] = i < k ? load(p, i) : T::pad();
+        __syncthreads();
+        for (int i = tid; i + 1 < k; i += kMergeThreads)
+            if (T::before(dst[i + 1], dst[i])) unsorted = 1;
+        __syncthreads();
+        if (unsorted) merge_sort_desc<T>(dst, m, tid);                    // block-uniform branch
+        if (p > 0) merge_two_desc<T>(items, m, tid);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kMergeThreads)
+merge_keys_kernel(int P, int k, int m, const unsigned long long* __restrict__ keys, long long part_stride, float* out_scores,
+                  long long* out_rows, unsigned long long* out_keys) {
+    extern __shared__ __align__(16) unsigned char raw_smem[];
+    unsigned long long* items = (unsigned long long*)raw_smem;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    merge_parts<KeyTraits>(items, P, k, m, tid,
+                           [&](int p, int i) { return keys[(size_t)p * part_stride + (size_t)q * k + i]; });
+    for (int i = tid; i < k; i += kMergeThreads) {
+        const unsigned long long key = items[i];
+        if (out_keys) out_keys[(size_t)q * k + i] = key;
+        if (out_scores) {
+            out_scores[(size_t)q * k + i] = key ? key_score(key) : -INFINITY;
+            out_rows[(size_t)q * k + i] = key ? (long long)key_row(key) : -1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kMergeThreads)
+merge_pairs_kernel(int P, int Q, int k, int m, const float* __restrict__ scores, const long long* __restrict__ rows,
+                   float* out_scores, long long* out_rows) {
+    extern __shared__ __align__(16) unsigned char raw_smem[];
+    MergeItem* items = (MergeItem*)raw_smem;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    merge_parts<PairTraits>(items, P, k, m, tid, [&](int p, int i) {
+        const size_t src = ((size_t)p * Q + q) * k + i;
+        const long long r = rows[src];
+        MergeItem it;
+        it.pad = 0u; it.row = r;
+        it.s = r >= 0 ? float_to_ordered(scores[src] + 0.0f) : 0u;
+        if (r < 0) it.row = -1;
+        return it;
+    });
+    for (int i = tid; i < k; i += kMergeThreads) {
+        const MergeItem it = items[i];
         const bool valid = it.row >= 0;
         out_scores[(size_t)q * k + i] = valid ? ordered_to_float(it.s) : -INFINITY;
         out_rows[(size_t)q * k + i] = valid ? it.row : -1;
     }
 }
 
+static int merge_pow2(int k) { int m = 2; while (m < k) m <<= 1; return m; }
+
 }  // namespace dhr
 
 using namespace dhr;
+
+extern "C" int dhr_merge_keys(int device, int n_parts, int n_queries, int k, const uint64_t* keys, int64_t part_stride,
+                              float* out_scores, int64_t* out_rows, uint64_t* out_keys, void* stream) {
+    if (n_parts <= 0 || n_queries < 0 || k <= 0 || !keys || part_stride < (int64_t)n_queries * k) return DHR_ERR_INVALID;
+    if ((!out_scores) != (!out_rows) || (!out_scores && !out_keys)) return DHR_ERR_INVALID;
+    if (n_queries == 0) return DHR_OK;
+    if (!is_device_pointer(keys) || (out_scores && (!is_device_pointer(out_scores) || !is_device_pointer(out_rows))) ||
+        (out_keys && !is_device_pointer(out_keys)))
+        return DHR_ERR_INVALID;                                           // device-resident exchange buffers only (stream-ordered, no sync)
+    const int m = merge_pow2(k);
+    const size_t smem = (size_t)2 * m * sizeof(unsigned long long);
+    if (smem > 200 * 1024) return DHR_ERR_UNSUPPORTED;                    // k <= 8192
+    DHR_CUDA(cudaSetDevice(device));
+    if (smem > 48 * 1024) DHR_CUDA(cudaFuncSetAttribute(merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_keys_kernel<<<n_queries, kMergeThreads, smem, (cudaStream_t)stream>>>(n_parts, k, m, (const unsigned long long*)keys,
+                                                                                (long long)part_stride, out_scores, (long long*)out_rows,
+                                                                                (unsigned long long*)out_keys);
+    DHR_CUDA(cudaGetLastError());
+    return DHR_OK;
+}
 
 extern "C" int dhr_topk_merge(int device, int n_parts, int n_queries, int k, const float* scores, const int64_t* rows,
                               float* out_scores, int64_t* out_rows, void* stream) {
     if (n_parts <= 0 || n_queries < 0 || k <= 0 || !scores || !rows || !out_scores || !out_rows) return DHR_ERR_INVALID;
     if (n_queries == 0) return DHR_OK;
-    long long n = (long long)n_parts * k;
-    long long m = 2;
-    while (m < n) m <<= 1;
-    const size_t smem = (size_t)m * sizeof(MergeItem);
-    if (smem > 200 * 1024) return DHR_ERR_UNSUPPORTED;
+    const int m = merge_pow2(k);
+    const size_t smem = (size_t)2 * m * sizeof(MergeItem);
+    if (smem > 200 * 1024) return DHR_ERR_UNSUPPORTED;                    // k <= 4096 (any number of parts)
     DHR_CUDA(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t in_elems = (size_t)n_parts * n_queries * k, out_elems = (size_t)n_queries * k;
@@ -283,8 +391,8 @@ extern "C" int dhr_topk_merge(int device, int n_parts, int n_queries, int k, con
     }
     if (out_dev) { d_os = out_scores; d_or = (long long*)out_rows; }
     else { MERGE_CUDA(cudaMalloc(&d_os, out_elems * 4)); MERGE_CUDA(cudaMalloc(&d_or, out_elems * 8)); }
-    MERGE_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    topk_merge_kernel<<<n_queries, kSelectThreads, smem, st>>>(n_parts, n_queries, k, d_s, d_r, d_os, d_or);
+    if (smem > 48 * 1024) MERGE_CUDA(cudaFuncSetAttribute(merge_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_pairs_kernel<<<n_queries, kMergeThreads, smem, st>>>(n_parts, n_queries, k, m, d_s, d_r, d_os, d_or);
     MERGE_CUDA(cudaGetLastError());
     if (!out_dev) {
         MERGE_CUDA(cudaMemcpyAsync(out_scores, d_os, out_elems * 4, cudaMemcpyDeviceToHost, st));

@@ -93,6 +93,8 @@ extern "C" int dhr_write_trec(const char* path, int append, int n_queries, int k
     if ((!qid_int && !(qid_str && qid_off)) || (!docid_int && !(docid_str && docid_off))) return DHR_ERR_INVALID;
     const IdTable qt{qid_int, qid_str, qid_off}, dt{docid_int, docid_str, docid_off};
     const size_t run_len = strlen(run_name);
+    constexpr size_t kMaxQid = 512, kMaxDocid = 400, kMaxRun = 256;
+    if (run_len > kMaxRun) return DHR_ERR_INVALID;                       // checked once, before any worker formats a line
     if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
     if (n_threads <= 0) n_threads = 1;
     if (n_threads > 64) n_threads = 64;
@@ -104,16 +106,16 @@ extern "C" int dhr_write_trec(const char* path, int append, int n_queries, int k
         const int q0 = (int)((int64_t)n_queries * t / n_threads), q1 = (int)((int64_t)n_queries * (t + 1) / n_threads);
         std::string& b = bufs[(size_t)t];
         b.reserve((size_t)(q1 - q0) * (size_t)k * 48);
-        char line[1024];
+        char line[kMaxQid + kMaxDocid + kMaxRun + 96];                   // ids + run name + " Q0 ", rank, score repr, separators
         for (int q = q0; q < q1; ++q) {
             const int n = counts ? counts[q] : k;
-            char qbuf[512];
+            char qbuf[kMaxQid];
             if (qt.max_len(q) > sizeof(qbuf)) { bad[(size_t)t] = 1; return; }
             const size_t ql = qt.put(q, qbuf);
             for (int r = 0; r < n && r < k; ++r) {
                 const int64_t row = rows[(size_t)q * k + r];
                 if (row < 0) continue;                                   // padding (k > rows in the shard)
-                if (row >= n_docids || dt.max_len(row) > 400) { bad[(size_t)t] = 1; return; }
+                if (row >= n_docids || dt.max_len(row) > kMaxDocid) { bad[(size_t)t] = 1; return; }
                 if (skip_equal && ids_equal(dt, row, qt, q)) continue;   // gip_retrieval.py:340
                 char* o = line;
                 memcpy(o, qbuf, ql); o += ql;
@@ -124,7 +126,6 @@ extern "C" int dhr_write_trec(const char* path, int append, int n_queries, int k
                 *o++ = ' ';
                 o += py_float_repr((double)scores[(size_t)q * k + r], o);
                 *o++ = ' ';
-                if (run_len > 256) { bad[(size_t)t] = 1; return; }
                 memcpy(o, run_name, run_len); o += run_len;
                 *o++ = '\n';
                 b.append(line, (size_t)(o - line));

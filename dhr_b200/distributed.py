@@ -1,11 +1,16 @@
-"""Multi-GPU search: corpus range-sharded across ranks (one process per GPU), per-shard top-k, one all-gather,
+"""Multi-GPU search: corpus range-sharded across ranks (one process per GPU), per-shard top-k, NCCL all-gather,
 device-side merge.  Replaces the process-per-shard + text-file merge of the reference
 (gip_retrieval.py:292-306 `--total_shrad/--shrad`, retrieval/merge.result.py:20-43).
 
-The exchange step is a single `all_gather` of the per-shard [Q, k] (fp32 score, int64 GLOBAL row) lists over
-NCCL / NVLink; every rank then holds [P, Q, k] and runs the merge kernel (dhr_topk_merge), so all ranks return
-the same answer.  Exactness: each shard orders by (score desc, global row asc), so the merged list equals the
-single-shard result including ties.
+CUDA path (`sharded_search` on an NCCL group): the shard search is ENQUEUED as one stream-ordered call
+(dhr_search_keys) that emits, per batch of 256 queries, packed 64-bit keys (score bits << 32 | 0xFFFFFFFF - GLOBAL row);
+a side stream waits for batch b, all-gathers its [B, k] keys (one collective of 8-byte items instead of an fp32 and an
+int64 one) and merges the P sorted lists (dhr_merge_keys) while the main stream is already scanning batch b+1, so the
+exchange is hidden behind the scan.  Exactness: every shard orders by (score desc, global row asc) = descending key
+order, so the merged list equals the single-shard result including ties.
+
+Host / gloo path (`sharded_search_lists`): one all-gather of ([Q,k] fp32, [Q,k] int64) + dhr_topk_merge; used by the CPU
+tests of the host logic and by callers that already hold per-shard lists.
 """
 from __future__ import annotations
 
@@ -13,7 +18,7 @@ import torch
 import torch.distributed as dist
 
 from .gip_retrieval import shard_bounds
-from .index import topk_merge
+from .index import merge_keys, topk_merge
 
 
 def local_shard(n_docs, group=None):
@@ -40,12 +45,69 @@ def gather_topk(scores, rows, group=None, out=None):
     return gs, gr
 
 
-def sharded_search(index, q_vals, q_idx, k, lamda=1.0, masked=True, group=None, merge_fn=topk_merge, local_out=None,
-                   gather_out=None):
-    """Search this rank's shard (index.row_offset = first global row) and merge across ranks.
-    Returns (scores [Q,k], rows [Q,k] global ids), identical on every rank."""
-    scores, rows, _ = index.search(q_vals, q_idx, k, lamda=lamda, masked=masked, out=local_out, return_torch=True)
+def sharded_search_lists(search_fn, merge_fn=topk_merge, group=None, gather_out=None):
+    """Generic form: search_fn() -> (scores [Q,k], rows [Q,k] GLOBAL ids) of this rank's shard; one all-gather + merge."""
+    scores, rows = search_fn()
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return scores, rows
     gs, gr = gather_topk(scores, rows, group, gather_out)
     return merge_fn(gs, gr)
+
+
+class ShardedSearcher:
+    """Pipelined shard search + exchange for one index (one per rank).  Buffers are allocated once and reused."""
+
+    def __init__(self, index, n_queries, k, group=None):
+        self.index, self.group = index, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        dev = torch.device('cuda', index.device)
+        self.keys = torch.empty((n_queries, k), dtype=torch.int64, device=dev)
+        self.side = torch.cuda.Stream(device=dev)
+        self.gathered = None            # [P, B, k], allocated when the batch size is known
+        self.out = (torch.empty((n_queries, k), dtype=torch.float32, device=dev),
+                    torch.empty((n_queries, k), dtype=torch.int64, device=dev))
+        self.breakdown = {}
+
+    def search(self, q_vals, q_idx, k, lamda=1.0, masked=True, out=None):
+        """Returns (scores [Q,k], rows [Q,k] global ids), identical on every rank.  The result tensors are valid once the
+        CURRENT stream has passed the point where this call returns (the side stream is joined back into it)."""
+        ix, world = self.index, self.world
+        out_s, out_r = out if out is not None else self.out
+        n = q_vals.shape[0]
+        main = torch.cuda.current_stream(self.keys.device)
+        keys = self.keys[:n]
+        bs, nb = ix.search_keys(q_vals, q_idx, k, keys, lamda=lamda, masked=masked, stream=main.cuda_stream)
+        if self.gathered is None or self.gathered.shape[1] < bs:
+            self.gathered = torch.empty((world, bs, k), dtype=torch.int64, device=keys.device)
+        side = self.side
+        with torch.cuda.stream(side):
+            for b in range(nb):
+                lo, hi = b * bs, min(n, (b + 1) * bs)
+                ix.wait_batch(b, side.cuda_stream)
+                if world == 1:
+                    merge_keys(keys[lo:hi].unsqueeze(0), out_s[lo:hi], out_r[lo:hi], stream=side.cuda_stream)
+                    continue
+                g = self.gathered.view(-1)[:world * (hi - lo) * k].view(world, hi - lo, k)
+                dist.all_gather_into_tensor(g, keys[lo:hi], group=self.group)
+                merge_keys(g, out_s[lo:hi], out_r[lo:hi], stream=side.cuda_stream)
+        n_rerun = ix.complete(stream=main.cuda_stream)
+        main.wait_stream(side)
+        if n_rerun > 0:
+            # adversarial row order (never on shuffled corpora): some keys were rewritten after their batch was exchanged;
+            # redo the exchange in one piece
+            if world == 1:
+                merge_keys(keys.unsqueeze(0), out_s[:n], out_r[:n], stream=main.cuda_stream)
+            else:
+                g = torch.empty((world, n, k), dtype=torch.int64, device=keys.device)
+                dist.all_gather_into_tensor(g, keys, group=self.group)
+                merge_keys(g, out_s[:n], out_r[:n], stream=main.cuda_stream)
+        self.n_rerun = n_rerun
+        return out_s[:n], out_r[:n]
+
+
+def sharded_search(index, q_vals, q_idx, k, lamda=1.0, masked=True, group=None, searcher=None, out=None):
+    """Search this rank's shard (index.row_offset = first global row) and merge across ranks (pipelined exchange).
+    Returns (scores [Q,k], rows [Q,k] global ids), identical on every rank."""
+    if searcher is None:
+        searcher = ShardedSearcher(index, q_vals.shape[0], k, group)
+    return searcher.search(q_vals, q_idx, k, lamda=lamda, masked=masked, out=out)

@@ -8,7 +8,9 @@ torch loop is replaced by the HBM-resident index and fused scan/top-k kernels be
 
 Differences, all deliberate:
   * ties are ordered (score desc, row asc); torch.topk's tie order is unspecified,
-  * ``PQ_IP_retrieval`` (faiss product quantisation, :167-231) is out of scope -> --PQIP raises,
+  * ``PQ_IP_retrieval`` (:167-231): the faiss IndexPQ first stage is third-party; its candidate lists are taken from
+    ``candidates=`` / ``first_stage=`` / a candidate file (or faiss itself when installed), the exact GIP rerank half
+    (:205-215) runs on the device,
   * ``--use_gpu`` is accepted and ignored (this implementation always runs on the GPU); the
     extra flag ``--device`` selects the CUDA device (the reference hard-wires 0, :261).
 """
@@ -127,9 +129,68 @@ def GIP_retrieval(qids, query_embs, query_arg_idxs, corpus_embs, corpus_arg_idxs
     return all_results, all_scores
 
 
-def PQ_IP_retrieval(*_a, **_k):
-    raise NotImplementedError('PQ_IP_retrieval (faiss IndexPQ first stage, gip_retrieval.py:167-231) is out of scope '
-                              'of the B200 path: the exact scan is faster than the PQ approximation it replaced')
+def _first_stage_candidates(query_embs, args, candidates, candidate_scores, first_stage):
+    """Candidate lists [Q, agip_topk] of the PQ first stage (gip_retrieval.py:202).  faiss is third-party and not part of
+    this path, so the lists come from (in this order) `candidates` (+ `candidate_scores`), a `first_stage(batch) -> (D, I)`
+    callable with faiss' IndexPQ.search signature, a candidate file given as --faiss_pq_index_path (.npy [Q, M] or .npz
+    with 'candidates' and optionally 'scores'), or a faiss index file when faiss is importable."""
+    if candidates is not None:
+        return np.asarray(candidates), None if candidate_scores is None else np.asarray(candidate_scores)
+    path = getattr(args, 'faiss_pq_index_path', None)
+    if first_stage is None:
+        assert path is not None, 'you do not spesify your PQ index through --faiss_pq_index_path'
+        if str(path).endswith('.npy'):
+            return np.load(path), None
+        if str(path).endswith('.npz'):
+            with np.load(path) as z:
+                return z['candidates'], (z['scores'] if 'scores' in z.files else None)
+        try:
+            import faiss
+        except Exception as e:
+            raise RuntimeError('PQ_IP_retrieval: faiss is not installed; pass candidates=/first_stage= or point '
+                               '--faiss_pq_index_path at a .npy/.npz candidate file') from e
+        print('Load PQ index ...')
+        first_stage = faiss.read_index(path).search
+    q = query_embs.cpu().numpy() if torch is not None and isinstance(query_embs, torch.Tensor) else np.asarray(query_embs)
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    batch = max(1, int(getattr(args, 'batch', 1)))
+    D, I = [], []
+    for b in range(0, q.shape[0], batch):                            # :186-202 batching
+        d, i = first_stage(q[b:b + batch], args.agip_topk)
+        D.append(np.asarray(d)); I.append(np.asarray(i))
+    return np.concatenate(I), np.concatenate(D)
+
+
+def PQ_IP_retrieval(qids, query_embs, query_arg_idxs, corpus_embs, corpus_arg_idxs, args, candidates=None,
+                    candidate_scores=None, first_stage=None):
+    """Product-quantised first stage + exact GIP rerank (gip_retrieval.py:167-231).
+
+    The rerank half (:205-215) -- exact GIP of every query over its agip_topk candidates, top args.topk -- runs on the
+    device (dhr_rerank).  Without --rerank the first-stage lists are returned as they are (:218-222), which needs
+    candidate scores.  Candidate ids are rows of the given corpus, unique per query; ids < 0 (faiss' "no result") are
+    skipped."""
+    cand, cand_scores = _first_stage_candidates(query_embs, args, candidates, candidate_scores, first_stage)
+    if cand.ndim != 2 or cand.shape[0] != len(qids):
+        raise ValueError('candidates must be [n_queries, agip_topk], got %s' % (cand.shape,))
+    start_time = time.time()
+    if not args.rerank:
+        if cand_scores is None:
+            raise ValueError('PQ_IP_retrieval without --rerank returns the first-stage scores: candidate scores are required')
+        all_results = {qid: cand[i, :args.topk].tolist() for i, qid in enumerate(qids)}
+        all_scores = {qid: np.asarray(cand_scores)[i, :args.topk].tolist() for i, qid in enumerate(qids)}
+    else:
+        index, owned = _open_index(corpus_embs, corpus_arg_idxs, args.emb_dim, getattr(args, 'device', 0))
+        try:
+            if args.topk > cand.shape[1]:                             # torch.topk raises here (:209)
+                raise RuntimeError('selected index k out of range')
+            scores, rows, counts = index.rerank(query_embs, query_arg_idxs, cand.astype(np.int64), args.topk)
+            all_results, all_scores = _as_lists(scores, rows, counts, qids, index.row_offset)
+        finally:
+            if owned:
+                index.close()
+    time_per_query = (time.time() - start_time) / max(1, len(qids))
+    print('Retrieving {} queries ({:0.3f} s/query)'.format(len(qids), time_per_query))
+    return all_results, all_scores
 
 
 def build_parser():
@@ -228,8 +289,6 @@ def write_trec(path, results, scores, docids, run_name):
 
 def main(argv=None):
     args = build_parser().parse_args(argv)
-    if args.PQIP:
-        PQ_IP_retrieval()
 
     print('Load query embeddings ...')
     with open(args.query_emb_path, 'rb') as f:
@@ -260,7 +319,9 @@ def main(argv=None):
             index = GipIndex.from_arrays(corpus_embs, None, device=args.device)
         del corpus_embs, corpus_arg_idxs
 
-    if query_arg_idxs is not None:
+    if query_arg_idxs is not None and args.PQIP:                     # :321-322
+        results, scores = PQ_IP_retrieval(qids, query_embs, query_arg_idxs, index, None, args)
+    elif query_arg_idxs is not None:
         results, scores = GIP_retrieval(qids, query_embs, query_arg_idxs, index, None, args)
     else:
         results, scores = IP_retrieval(qids, query_embs, index, args)

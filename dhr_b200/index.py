@@ -72,19 +72,19 @@ class GipIndex:
     """One corpus shard resident in the HBM of one GPU."""
 
     def __init__(self, n_slices, n_dense, group=1, capacity=0, idx_dtype=np.uint8, device=0, row_offset=0,
-                 narrow_codes=False):
+                 narrow_codes=False, keep_rowmajor=False):
         self._h = ctypes.c_void_p()
         self.n_slices, self.n_dense, self.group = int(n_slices), int(n_dense), int(group)
         self.device, self.row_offset = int(device), int(row_offset)
         self.width = self.n_slices * self.group + self.n_dense
         code = C.IDX_NONE if n_slices == 0 else _NP_IDX[np.dtype(idx_dtype)]
-        flags = C.INDEX_NARROW_CODES if narrow_codes else 0
+        flags = (C.INDEX_NARROW_CODES if narrow_codes else 0) | (C.INDEX_KEEP_ROWMAJOR if keep_rowmajor else 0)
         C.check(C.lib().dhr_index_create(ctypes.byref(self._h), self.device, int(capacity), self.n_slices, self.group,
                                          self.n_dense, code, self.row_offset, flags), 'dhr_index_create')
 
     # ---- construction --------------------------------------------------------------------------
     @classmethod
-    def from_arrays(cls, vals, idx, n_slices=None, group=1, device=0, row_offset=0, narrow_codes=False):
+    def from_arrays(cls, vals, idx, n_slices=None, group=1, device=0, row_offset=0, narrow_codes=False, keep_rowmajor=False):
         """vals [N, S*G + C] fp16/fp32, idx [N, S] integer array or None / 0 (dense-only index,
         the reference stores None or 0 there: encode.py:149-153, index.py:40-43)."""
         v = _Arr(vals, 'val')
@@ -99,7 +99,7 @@ class GipIndex:
         if C_ < 0:
             raise ValueError('values have %d columns but n_slices*group = %d' % (v.shape[1], S * group))
         self = cls(S, C_, group, capacity=v.shape[0], idx_dtype=np_dtype, device=device, row_offset=row_offset,
-                   narrow_codes=narrow_codes)
+                   narrow_codes=narrow_codes, keep_rowmajor=keep_rowmajor)
         self.append(vals, idx if has_idx else None)
         self.finalize()
         return self
@@ -149,6 +149,13 @@ class GipIndex:
     def row_bytes(self):
         n = ctypes.c_int64(0)
         C.check(C.lib().dhr_index_row_bytes(self._h, ctypes.byref(n)), 'dhr_index_row_bytes')
+        return n.value
+
+    @property
+    def device_bytes(self):
+        """HBM bytes the index holds right now (resident copies + workspaces)."""
+        n = ctypes.c_int64(0)
+        C.check(C.lib().dhr_index_device_bytes(self._h, ctypes.byref(n)), 'dhr_index_device_bytes')
         return n.value
 
     def set_option(self, name, value):
@@ -203,6 +210,32 @@ class GipIndex:
                                    self._ptr(scores), self._ptr(rows), self._ptr(counts), st), 'dhr_search')
         return scores, rows, counts
 
+    # ---- stream-ordered search (sharded path) ---------------------------------------------------
+    def search_keys(self, q_vals, q_idx, k, out_keys, lamda=1.0, masked=True, stream=None):
+        """Enqueue the search on `stream` (raw cudaStream_t or None) and return at once: out_keys [Q,k] int64 CUDA tensor
+        receives the packed keys (score bits << 32 | 0xFFFFFFFF - global row; descending = (score desc, row asc)).
+        Returns (batch_size, n_batches); call wait_batch(b, stream2) / complete() afterwards (include/dhr_b200.h)."""
+        qv, qi, (ip, ic, istr) = self._query_args(q_vals, q_idx, masked)
+        n = qv.shape[0]
+        if tuple(out_keys.shape) != (n, k) or out_keys.dtype != torch.int64 or not out_keys.is_cuda or not out_keys.is_contiguous():
+            raise ValueError('out_keys must be a contiguous CUDA int64 tensor of shape [Q, k]')
+        flags = 0 if masked else C.SEARCH_UNMASKED
+        st = ctypes.c_void_p(stream) if stream else None
+        C.check(C.lib().dhr_search_keys(self._h, n, qv.code, qv.ptr, qv.stride, ic, ip, istr, float(lamda), int(k), flags,
+                                        out_keys.data_ptr(), st), 'dhr_search_keys')
+        bs, nb = ctypes.c_int(0), ctypes.c_int(0)
+        C.check(C.lib().dhr_search_batches(self._h, ctypes.byref(bs), ctypes.byref(nb)), 'dhr_search_batches')
+        return bs.value, nb.value
+
+    def wait_batch(self, batch, stream):
+        C.check(C.lib().dhr_search_wait_batch(self._h, int(batch), ctypes.c_void_p(stream) if stream else None), 'dhr_search_wait_batch')
+
+    def complete(self, stream=None):
+        """Synchronise the pending search_keys call; returns the number of queries that were re-run (overflow fallback)."""
+        n = ctypes.c_int(0)
+        C.check(C.lib().dhr_search_complete(self._h, ctypes.byref(n), ctypes.c_void_p(stream) if stream else None), 'dhr_search_complete')
+        return n.value
+
     def rerank(self, q_vals, q_idx, cand_rows, k, lamda=1.0, out=None, stream=None):
         """Exact GIP over cand_rows [Q, M] (LOCAL row ids, < 0 skipped); same outputs as search()."""
         qv, qi, (ip, ic, istr) = self._query_args(q_vals, q_idx, True)
@@ -246,3 +279,46 @@ def topk_merge(scores, rows, k=None, device=0, stream=None):
     if k is not None and k < kk:
         os_, or_ = os_[:, :k], or_[:, :k]
     return os_, or_
+
+
+def merge_keys(keys, out_scores=None, out_rows=None, out_keys=None, stream=None):
+    """Merge packed-key lists [P, Q, k] (int64 CUDA tensor, each list descending) -> [Q, k]; stream-ordered, no sync.
+    Writes (out_scores fp32, out_rows int64) and / or out_keys int64; allocates (scores, rows) when nothing is given."""
+    P, Q, k = keys.shape
+    if not keys.is_cuda or keys.dtype != torch.int64 or not keys.is_contiguous():
+        raise ValueError('keys must be a contiguous CUDA int64 tensor [P, Q, k]')
+    if out_scores is None and out_keys is None:
+        out_scores = torch.empty((Q, k), dtype=torch.float32, device=keys.device)
+        out_rows = torch.empty((Q, k), dtype=torch.int64, device=keys.device)
+    ptr = lambda t: None if t is None else t.data_ptr()
+    st = ctypes.c_void_p(stream) if stream else None
+    C.check(C.lib().dhr_merge_keys(keys.device.index, P, Q, k, keys.data_ptr(), Q * k, ptr(out_scores), ptr(out_rows), ptr(out_keys), st),
+            'dhr_merge_keys')
+    return out_scores, out_rows, out_keys
+
+
+def pack_keys(scores, rows):
+    """(scores fp32, GLOBAL rows) -> packed int64 keys of the exchange format (host-side mirror of make_key in
+    csrc/common.cuh); rows < 0 (padding) -> 0."""
+    s = np.ascontiguousarray(scores, dtype=np.float32) + np.float32(0.0)          # -0.0 -> +0.0
+    b = s.view(np.uint32)
+    o = np.where(b & np.uint32(0x80000000), ~b, b | np.uint32(0x80000000)).astype(np.uint64)
+    r = np.asarray(rows, dtype=np.int64)
+    k = (o << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - r.clip(min=0).astype(np.uint64))
+    k[r < 0] = 0
+    return k.view(np.int64)
+
+
+def unpack_keys(keys):
+    """packed keys (int64 tensor / array) -> (scores fp32, rows int64); padding (0) -> (-inf, -1).  Host-side helper for tests."""
+    a = keys.cpu().numpy() if torch is not None and isinstance(keys, torch.Tensor) else np.asarray(keys)
+    u = a.view(np.uint64)
+    hi = (u >> np.uint64(32)).astype(np.uint32)
+    lo = (u & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    bits = np.where(hi & np.uint32(0x80000000), hi & np.uint32(0x7FFFFFFF), ~hi).astype(np.uint32)
+    scores = bits.view(np.float32).copy()
+    rows = (np.uint32(0xFFFFFFFF) - lo).astype(np.int64)
+    pad = u == 0
+    scores[pad] = -np.inf
+    rows[pad] = -1
+    return scores, rows

@@ -55,6 +55,8 @@ extern "C" {
 
 /* dhr_index_create flags */
 #define DHR_INDEX_NARROW_CODES 1u /* store 16-bit slice indices as 8-bit codes (all values must be < 254) */
+#define DHR_INDEX_KEEP_ROWMAJOR 2u /* keep the row-major arrays resident after finalize (default: only the tiled copies stay;
+                                      the row-major ones are rebuilt on the first call that needs them) */
 
 #define DHR_MAX_K     12288      /* largest k handled by the fused selection (candidate capacity 16384) */
 #define DHR_MAX_GROUP 8
@@ -72,12 +74,13 @@ typedef struct dhr_stats {
     int32_t  n_prep_launches;
     int32_t  n_fallback_queries; /* queries re-run with the overflow-proof chunk schedule            */
     int32_t  n_kernel_launches;  /* every kernel launched by the call (prep, init, scan, select, ...)   */
-    int32_t  reserved0;
+    int32_t  rowmajor_rebuilds;  /* times the row-major arrays were rebuilt from the tiled copies by the call */
     double   scan_ms;            /* sum of CUDA-event durations of the scan launches                 */
     double   select_ms;          /* ... of the top-k selection launches                              */
     double   total_ms;           /* first launch to last launch of the search, CUDA events           */
     double   corpus_passes;      /* logical corpus passes made by the scan launches (sum rows*groups / N) */
     double   bytes_per_pass;     /* N * row_bytes of the HBM-resident layout                         */
+    double   dense_flops;        /* 2 * Q * N * C issued to the tensor-core kernel K2 by the call        */
 } dhr_stats;
 
 int         dhr_version(void);
@@ -106,8 +109,11 @@ int dhr_index_open(dhr_index** out, int device, int64_t n_rows, int n_slices, in
 int dhr_index_close(dhr_index* h);
 int dhr_index_rows(const dhr_index* h, int64_t* n_rows);
 int dhr_index_row_bytes(const dhr_index* h, int64_t* bytes);   /* HBM bytes per row of the resident layout */
+int dhr_index_device_bytes(const dhr_index* h, int64_t* bytes); /* HBM bytes the index holds right now (all copies + workspaces) */
 
-/* options: "scan_variant" (0|1), "query_block" (1|2|4|8), "query_groups" (1..64), "profile" (0|1) */
+/* options: "scan_variant" (0|1), "query_block" (1|2|4|8), "query_groups" (1..64), "profile" (0|1), "tile_mode" (0|1),
+ * "rowmajor" (0 = free the row-major arrays now and keep only the tiled copies; they are rebuilt on the first call that
+ * needs them -- fp32 / lamda-scaled queries, --IP, rerank, overflow fallback; 1 = make them resident now) */
 int dhr_index_set_option(dhr_index* h, const char* name, int64_t value);
 int dhr_index_get_stats(const dhr_index* h, dhr_stats* out);
 
@@ -125,6 +131,29 @@ int dhr_search(dhr_index* h, int n_queries, int q_val_dtype, const void* q_vals,
                int q_idx_dtype, const void* q_idx, int64_t q_idx_row_stride, float lamda, int k,
                unsigned flags, float* out_scores, int64_t* out_rows, int32_t* out_counts, void* stream);
 
+/* ---- stream-ordered search for the sharded path ---------------------------------
+ * Same search as dhr_search, but every launch is only ENQUEUED on `stream` and the call returns without waiting
+ * (the one exception: fp32 or lamda != 1 queries need one flag read before the scan).  The result of query q, rank r is
+ * the packed 64-bit key out_keys[q*k + r] = (order-preserving bits of the fp32 score << 32) | (0xFFFFFFFF - GLOBAL row);
+ * 0 = padding.  Descending key order is (score desc, global row asc) on every shard, so merging shards (the step after
+ * retrieval/merge.result.py:22-41 / the NCCL all-gather) is a plain 64-bit merge: dhr_merge_keys.  out_keys must be DEVICE
+ * memory; row_offset + rows must be < 2^32 - 1.
+ * Queries are processed in batches (dhr_search_batches); dhr_search_wait_batch makes another stream wait until batch b's
+ * keys are final, which lets the caller exchange + merge batch b while batch b+1 is still being scanned.
+ * dhr_search_complete synchronises, re-runs queries whose candidate buffer overflowed (adversarial row order; *n_rerun of
+ * them, their keys are rewritten) and must be called before the next search on the index. */
+int dhr_search_keys(dhr_index* h, int n_queries, int q_val_dtype, const void* q_vals, int64_t q_val_row_stride,
+                    int q_idx_dtype, const void* q_idx, int64_t q_idx_row_stride, float lamda, int k,
+                    unsigned flags, uint64_t* out_keys, void* stream);
+int dhr_search_batches(const dhr_index* h, int* batch_size, int* n_batches);
+int dhr_search_wait_batch(dhr_index* h, int batch, void* stream);
+int dhr_search_complete(dhr_index* h, int* n_rerun, void* stream);
+/* keys [P][part_stride] (each part holds [Q,k] packed keys, sorted descending per query) -> [Q,k] by key descending.
+ * Writes (out_scores, out_rows) and / or out_keys (either may be NULL).  DEVICE pointers; stream-ordered, no host sync.
+ * k <= 8192, any P. */
+int dhr_merge_keys(int device, int n_parts, int n_queries, int k, const uint64_t* keys, int64_t part_stride,
+                   float* out_scores, int64_t* out_rows, uint64_t* out_keys, void* stream);
+
 /* Exact GIP on given candidate rows (rerank, gip_retrieval.py:142-150 and :205-215):
  * cand_rows [Q, M] LOCAL row ids (< 0 = skip).  Outputs as dhr_search (rows are global). */
 int dhr_rerank(dhr_index* h, int n_queries, int q_val_dtype, const void* q_vals, int64_t q_val_row_stride,
@@ -132,9 +161,9 @@ int dhr_rerank(dhr_index* h, int n_queries, int q_val_dtype, const void* q_vals,
                const int64_t* cand_rows, int n_cand, int k, float* out_scores, int64_t* out_rows,
                int32_t* out_counts, void* stream);
 
-/* Merge P per-shard top-k lists (replaces retrieval/merge.result.py:20-43 and is the step after
- * the NCCL all-gather): scores/rows [P, Q, k] -> [Q, k] by (score desc, row asc); rows < 0 are padding.
- * Runs on `device`; pointers may be host or device. */
+/* Merge P per-shard top-k lists (replaces retrieval/merge.result.py:20-43): scores/rows [P, Q, k] -> [Q, k] by
+ * (score desc, row asc); rows < 0 are padding.  Lists need not be sorted.  Runs on `device`; pointers may be host or
+ * device; synchronous.  k <= 4096, any P (progressive merge, shared memory is O(k)). */
 int dhr_topk_merge(int device, int n_parts, int n_queries, int k, const float* scores, const int64_t* rows,
                    float* out_scores, int64_t* out_rows, void* stream);
 

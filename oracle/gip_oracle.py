@@ -174,6 +174,29 @@ def GIP_retrieval_port(qids, query_embs, query_arg_idxs, corpus_embs, corpus_arg
     return results, scores_out
 
 
+def PQ_rerank_port(qids, query_embs, query_arg_idxs, corpus_embs, corpus_arg_idxs, candidates, candidate_scores, args):
+    """gip_retrieval.py:167-231 given the first-stage lists (faiss IndexPQ.search is third-party, not restated):
+    rerank half (:205-215) = exact GIP over the candidates, top args.topk; otherwise (:218-222) the lists as they are."""
+    tail = query_embs.shape[1] - query_arg_idxs.shape[1]
+    q_idx, c_idx = query_arg_idxs, corpus_arg_idxs
+    if tail > 0:                                              # :179-182
+        q_idx = torch.nn.functional.pad(q_idx, (0, tail), value=1)
+        c_idx = torch.nn.functional.pad(c_idx, (0, tail), value=1)
+    results, scores_out = {}, {}
+    for n, (qv, qi) in enumerate(zip(query_embs, q_idx)):
+        cand = torch.as_tensor(np.asarray(candidates[n]), dtype=torch.long)
+        if args.rerank:
+            gated = (c_idx[cand, :] == qi) * corpus_embs[cand]      # :206
+            sc = torch.mv(gated, qv)                                # :207
+            top = torch.topk(sc, args.topk, dim=0).indices          # :209
+            results[qids[n]] = cand[top].tolist()
+            scores_out[qids[n]] = sc[top].tolist()
+        else:
+            results[qids[n]] = cand[:args.topk].tolist()
+            scores_out[qids[n]] = np.asarray(candidate_scores[n])[:args.topk].tolist()
+    return results, scores_out
+
+
 def IP_retrieval_port(qids, query_embs, corpus_embs, args):
     """gip_retrieval.py:60-85: row-dot then full descending argsort, keep topk."""
     results, scores_out = {}, {}

@@ -261,8 +261,54 @@ def wide_golden():
     save('grouped_g3_wide_u16_grid', c, topk=60, ref_rows=rows, ref_scores=sc)
 
 
+def pq_golden():
+    """PQ_IP_retrieval (:167-231): the faiss IndexPQ first stage is third-party and absent here, so the reference's own
+    rerank half (:205-215) and its no-rerank branch (:218-222) are executed on candidate lists served by a stub index
+    (`faiss.read_index` -> object with .search()).  Candidates: the exact-IP top 200 of each query plus 200 random other
+    rows, shuffled -- unique per query, like an IndexPQ result.  Own rng: other fixtures stay byte-identical."""
+    torch.set_num_threads(1)
+    rng = np.random.default_rng(20261018)
+    c = make_case(rng, 3000, 6, 64, 1, 32, 39, np.uint8, np.uint8, 0.7, 0.7, grid=True)
+    n, nq, M, k = 3000, 6, 400, 50
+    ip = c['q_vals'].astype(np.float32) @ c['c_vals'].astype(np.float32).T
+    cands = np.zeros((nq, M), np.int64)
+    for i in range(nq):
+        top = np.argsort(-ip[i], kind='stable')[:200]
+        rest = np.setdiff1d(np.arange(n), top)
+        cands[i] = rng.permutation(np.concatenate([top, rng.choice(rest, size=M - 200, replace=False)]))
+    cscores = np.take_along_axis(ip, cands, axis=1).astype(np.float32)
+
+    class StubIndex:                       # what faiss.read_index returns: .search(x, k) -> (D, I), batches served in order
+        def __init__(self):
+            self.cursor = 0
+
+        def search(self, x, kk):
+            b = x.shape[0]
+            out = cscores[self.cursor:self.cursor + b, :kk], cands[self.cursor:self.cursor + b, :kk]
+            self.cursor += b
+            return out
+
+    G = c['G']
+    qv = torch.from_numpy(c['q_vals'].astype(np.float32))
+    cv = torch.from_numpy(c['c_vals'].astype(np.float32))
+    qi = torch.from_numpy(c['q_idx'])
+    ci = torch.from_numpy(c['c_idx'])
+    qids = list(range(100, 100 + nq))
+    outs = {}
+    for tag, rerank in (('rerank', True), ('norerank', False)):
+        ref.faiss.read_index = lambda path: StubIndex()
+        args = make_args(emb_dim=c['S'] * G, topk=k, agip_topk=M, rerank=rerank, batch=4, faiss_pq_index_path='stub')
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            res, sc = ref.PQ_IP_retrieval(qids, qv, qi, cv, ci, args)
+        outs['ref_rows_' + tag] = np.array([[int(x) for x in res[q]] for q in qids], dtype=np.int64)
+        outs['ref_scores_' + tag] = np.array([[float(x) for x in sc[q]] for q in qids], dtype=np.float64)
+    save('pq_rerank_grid', c, topk=k, agip_topk=M, candidates=cands, candidate_scores=cscores, **outs)
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'densify':
+    if len(sys.argv) > 1 and sys.argv[1] == 'pq':
+        pq_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'densify':
         densify_golden()
     elif len(sys.argv) > 1 and sys.argv[1] == 'wide':
         wide_golden()
@@ -270,3 +316,4 @@ if __name__ == '__main__':
         main()
         densify_golden()
         wide_golden()
+        pq_golden()

@@ -44,14 +44,15 @@ def _worker(rank, world, port, ret):
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
-        from dhr_b200.distributed import local_shard, sharded_search
+        from dhr_b200.distributed import local_shard, sharded_search_lists
         g = load_golden('delade_g1_u8_grid')
         n = g['c_vals'].shape[0]
         lo, hi = local_shard(n)
         assert (lo, hi) == go.shard_bounds(n, world, rank)
         q = g['q_vals'].astype(np.float32)
         k = int(g['topk'])
-        s, r = sharded_search(_OracleShard(g, lo, hi), q, g['q_idx'], k, merge_fn=_oracle_merge)
+        shard = _OracleShard(g, lo, hi)
+        s, r = sharded_search_lists(lambda: shard.search(q, g['q_idx'], k)[:2], merge_fn=_oracle_merge)
         full_r, full_s = go.search_f64(q, g['q_idx'], g['c_vals'], g['c_idx'], int(g['S']), int(g['G']), k)
         ok = np.array_equal(r.numpy(), full_r) and np.array_equal(s.numpy(), full_s.astype(np.float32))
         ret[rank] = bool(ok)

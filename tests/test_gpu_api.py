@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from conftest import load_golden, has_cuda
-from helpers import tie_groups_equal
+from helpers import tie_groups_equal, make_case, assert_matches_oracle
 from oracle import gip_oracle as go
 
 pytestmark = pytest.mark.gpu
@@ -15,6 +15,7 @@ if has_cuda():
     import torch
     import dhr_b200
     from dhr_b200 import gip_retrieval as gr
+    from dhr_b200 import GipIndex
 
 
 def _q(g, lam=1.0):
@@ -151,3 +152,90 @@ def test_gpu_densify_op_matches_reference():
     assert torch.all(vals[:, 768:] == 0)
     with pytest.raises(ValueError):
         densify(x, dims=7)
+
+
+@pytest.mark.parametrize('tag,rerank', [('rerank', True), ('norerank', False)])
+def test_pq_ip_retrieval_rerank_half_matches_reference(tag, rerank, tmp_path):
+    """a11: the reference's PQ_IP_retrieval (:167-231) ran on stub first-stage lists (tests/golden/make_golden.py pq);
+    same lists -> same scores (grid inputs: bit-exact), rows equal inside tie groups."""
+    g = load_golden('pq_rerank_grid')
+    S, k = int(g['S']), int(g['topk'])
+    qids = list(range(g['q_vals'].shape[0]))
+    args = go.make_args(emb_dim=S, topk=k, agip_topk=int(g['agip_topk']), rerank=rerank, batch=4)
+    served = []
+
+    def first_stage(x, kk):                                           # faiss IndexPQ.search signature, batches in order
+        lo = sum(served)
+        served.append(x.shape[0])
+        return g['candidate_scores'][lo:lo + x.shape[0], :kk], g['candidates'][lo:lo + x.shape[0], :kk]
+
+    np.savez(tmp_path / 'cand.npz', candidates=g['candidates'], scores=g['candidate_scores'])
+    file_args = go.make_args(emb_dim=S, topk=k, agip_topk=int(g['agip_topk']), rerank=rerank, faiss_pq_index_path=str(tmp_path / 'cand.npz'))
+    for kw, a in ((dict(candidates=g['candidates'], candidate_scores=g['candidate_scores']), args), (dict(first_stage=first_stage), args),
+                  ({}, file_args)):
+        res, sc = gr.PQ_IP_retrieval(qids, torch.from_numpy(_q(g)), torch.from_numpy(g['q_idx']),
+                                     torch.from_numpy(g['c_vals'].astype(np.float32)), torch.from_numpy(g['c_idx']), a, **kw)
+        got = np.array([sc[i] for i in qids])
+        rows = np.array([res[i] for i in qids])
+        assert np.array_equal(got, g['ref_scores_' + tag])
+        for i in qids:
+            assert tie_groups_equal(rows[i], g['ref_rows_' + tag][i], got[i])
+    assert served == [4, 2]
+
+
+def test_host_output_staging_grows_per_dimension():
+    """ADVICE r1: (Q=8, k=1000) then (Q=4096, k=1) with numpy outputs must not reuse a counts buffer sized for 8 queries."""
+    case = make_case(5, 5000, 4096, 16, 2, 16, 39, np.uint8, grid=True)
+    with GipIndex.from_arrays(case['c_vals'], case['c_idx'], n_slices=16, group=2) as ix:
+        s, r, c = ix.search(case['q_vals'][:8], case['q_idx'][:8], 1000)
+        assert_matches_oracle(dict(case, q_vals=case['q_vals'][:8], q_idx=case['q_idx'][:8]), s, r, c, 1000, exact=True)
+        s, r, c = ix.search(case['q_vals'], case['q_idx'], 1)
+        assert np.all(c == 1)
+        sub = slice(4000, 4096)
+        assert_matches_oracle(dict(case, q_vals=case['q_vals'][sub], q_idx=case['q_idx'][sub]), s[sub], r[sub], c[sub], 1, exact=True)
+        s, r, c = ix.search(case['q_vals'][:8], case['q_idx'][:8], 1000)          # and back: still intact
+        assert_matches_oracle(dict(case, q_vals=case['q_vals'][:8], q_idx=case['q_idx'][:8]), s, r, c, 1000, exact=True)
+
+
+def test_rerank_with_duplicate_candidates_is_memory_safe():
+    """ADVICE r1: duplicated candidate rows break the unique-key assumption of the select; k a power of two is the case that
+    used to write past the compaction buffer.  The duplicate may be returned twice; nothing may be corrupted."""
+    case = make_case(9, 2000, 4, 16, 1, 16, 39, np.uint8, grid=True)
+    k = 64
+    cand = np.tile(np.arange(100, dtype=np.int64), (4, 2))                         # every candidate twice
+    with GipIndex.from_arrays(case['c_vals'], case['c_idx'], n_slices=16, group=1) as ix:
+        s, r, c = ix.rerank(case['q_vals'], case['q_idx'], cand, k)
+        ex = go.gip_scores_f64(case['q_vals'], case['q_idx'], case['c_vals'], case['c_idx'], 16, 1)
+        for i in range(4):
+            assert np.all((r[i] >= 0) & (r[i] < 100))
+            assert np.array_equal(ex[i][r[i]].astype(np.float32), s[i])
+            assert np.all(np.diff(s[i]) <= 0)
+        s2, r2, c2 = ix.search(case['q_vals'], case['q_idx'], k)                    # the index still answers correctly
+        assert_matches_oracle(case, s2, r2, c2, k, exact=True)
+
+
+def test_rowmajor_arrays_are_dropped_and_rebuilt_on_demand():
+    """VERDICT r1 weak #6: only the tiled copies stay resident; K1 / rerank / fp32 queries rebuild the row-major arrays."""
+    case = make_case(11, 6000, 9, 32, 6, 64, 39, np.uint16)
+    k = 50
+    with GipIndex.from_arrays(case['c_vals'], case['c_idx'], n_slices=32, group=6, keep_rowmajor=True) as keep:
+        full = keep.device_bytes
+        s0, r0, c0 = keep.search(case['q_vals'], case['q_idx'], k)
+    with GipIndex.from_arrays(case['c_vals'], case['c_idx'], n_slices=32, group=6) as ix:
+        lean = ix.device_bytes
+        assert lean < 0.62 * full                                                   # tiled copies only (+ small workspaces)
+        s, r, c = ix.search(case['q_vals'], case['q_idx'], k)                       # tile path: no rebuild
+        assert ix.stats()['scan_variant'] == 3 and ix.stats()['rowmajor_rebuilds'] == 0
+        assert np.array_equal(s, s0) and np.array_equal(r, r0)
+        ix.set_option('tile_mode', 0)                                               # row scan K1 needs them
+        s1, r1, c1 = ix.search(case['q_vals'], case['q_idx'], k)
+        assert ix.stats()['rowmajor_rebuilds'] == 1
+        assert_matches_oracle(case, s1, r1, c1, k)
+        cand = r0[:, ::-1].copy()
+        s2, r2, _ = ix.rerank(case['q_vals'], case['q_idx'], cand, k)               # K4 on the rebuilt arrays
+        assert np.array_equal(np.sort(r2, axis=1), np.sort(r0, axis=1)) and np.allclose(s2, s0, atol=1e-5)
+        ix.set_option('rowmajor', 0)
+        assert ix.device_bytes <= lean + (64 << 20)
+        ix.set_option('tile_mode', 1)
+        s3, r3, _ = ix.search(case['q_vals'], case['q_idx'], k)
+        assert np.array_equal(s3, s0) and np.array_equal(r3, r0)

@@ -34,7 +34,8 @@ def test_constants_match_header():
                       ('DHR_IDX_I32', C.IDX_I32), ('DHR_IDX_I64', C.IDX_I64), ('DHR_VAL_F16', C.VAL_F16), ('DHR_VAL_F32', C.VAL_F32),
                       ('DHR_ERR_LOSSY', C.ERR_LOSSY), ('DHR_ERR_IDX_RANGE', C.ERR_IDX_RANGE), ('DHR_ERR_NO_DEVICE', C.ERR_NO_DEVICE)]:
         assert int(defs[name]) == val
-    assert ctypes.sizeof(C.DhrStats) == 10 * 4 + 5 * 8
+    assert ctypes.sizeof(C.DhrStats) == 10 * 4 + 6 * 8
+    assert int(defs['DHR_INDEX_KEEP_ROWMAJOR']) == C.INDEX_KEEP_ROWMAJOR and int(defs['DHR_INDEX_NARROW_CODES']) == C.INDEX_NARROW_CODES
 
 
 def test_product_fails_loudly_without_gpu():
@@ -289,3 +290,19 @@ def test_k1t_postings_spec_matches_oracle():
             p = t0['pid'][t0['off'][s, c]:t0['off'][s, c + 1]]
             assert np.all(np.diff(p.astype(np.int64)) > 0)
             assert np.all(case['c_idx'][p, s] == c)
+
+
+def test_packed_keys_roundtrip_and_order():
+    """exchange format of the sharded search: descending int64-as-uint64 key order == (score desc, row asc)"""
+    from dhr_b200 import pack_keys, unpack_keys
+    rng = np.random.default_rng(0)
+    s = np.concatenate([rng.standard_normal(500).astype(np.float32), np.float32([0.0, -0.0, 1.5, 1.5, 1.5, -3.25, -3.25])])
+    r = rng.permutation(len(s)).astype(np.int64) + 8_000_000
+    k = pack_keys(s, r)
+    s2, r2 = unpack_keys(k)
+    assert np.array_equal(r2, r) and np.array_equal(s2, s + np.float32(0.0))
+    order = np.argsort(k.view(np.uint64))[::-1]
+    expect = np.lexsort((r, -(s.astype(np.float64))))
+    assert np.array_equal(order, expect)
+    pad = pack_keys(np.float32([1.0]), np.int64([-1]))
+    assert pad[0] == 0 and unpack_keys(pad)[1][0] == -1 and np.isneginf(unpack_keys(pad)[0][0])
