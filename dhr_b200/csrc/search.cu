@@ -579,6 +579,8 @@ static int enqueue_search(dhr_index* h, const SearchRequest& r, SelectOut so, bo
         slots = kMaxInflight; qb = kLexTileQueries; groups = kMaxInflight / kLexTileQueries;
     }
     if (!tile_dense && !tile_hybrid) DHR_TRY(ensure_rowmajor(h));          // the row scan K1 reads the row-major arrays
+    else if (g.C_pad > 0 && (!h->dnst || h->opt_dense_variant != 1 || !dense_tile_ts_supported(g)))
+        DHR_TRY(ensure_rowmajor(h));                                      // K2's SS variant streams the row-major dense block
     h->stats.query_block = qb;
     h->stats.query_groups = groups;
     h->batch_size = slots;
@@ -644,6 +646,7 @@ extern "C" int dhr_search(dhr_index* h, int n_queries, int q_val_dtype, const vo
     const SearchRequest r{n_queries, q_val_dtype, q_vals, vstride, q_idx_dtype, q_idx, istride, lamda, k, masked};
     bool f32 = false;
     int status = enqueue_search(h, r, so, false, &f32, st);
+    const bool enqueue_failed = status != DHR_OK;                        // its CUDA error text is already recorded
     // one synchronisation: results (host outputs) and the per-query overflow flags come back together
     std::vector<uint32_t> h_overflow((size_t)n_queries, 0u);
     auto copy_out = [&]() -> int {
@@ -666,7 +669,7 @@ extern "C" int dhr_search(dhr_index* h, int n_queries, int q_val_dtype, const vo
             if (cudaStreamSynchronize(st) != cudaSuccess && status == DHR_OK) status = DHR_ERR_CUDA;
         }
     }
-    if (status == DHR_ERR_CUDA) { set_cuda_error(cudaGetLastError(), "dhr_search", __FILE__, __LINE__); return status; }
+    if (status == DHR_ERR_CUDA && !enqueue_failed) set_cuda_error(cudaGetLastError(), "dhr_search", __FILE__, __LINE__);
     if (status != DHR_OK) return status;
     collect_profile(h);
     return DHR_OK;
@@ -688,7 +691,6 @@ extern "C" int dhr_search_keys(dhr_index* h, int n_queries, int q_val_dtype, con
     const SearchRequest r{n_queries, q_val_dtype, q_vals, vstride, q_idx_dtype, q_idx, istride, lamda, k, masked};
     bool f32 = false;
     const int status = enqueue_search(h, r, so, true, &f32, (cudaStream_t)stream);
-    if (status == DHR_ERR_CUDA) set_cuda_error(cudaGetLastError(), "dhr_search_keys", __FILE__, __LINE__);
     if (status != DHR_OK) return status;
     h->pending.active = true; h->pending.n_queries = n_queries; h->pending.k = k; h->pending.masked = masked; h->pending.f32 = f32;
     h->pending.out_keys = out_keys;

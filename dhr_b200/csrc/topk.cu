@@ -200,9 +200,9 @@ int launch_select(const TopkState& t, int n_slots, int k, int cap, bool final_pa
     int m = 2;
     while (m < std::min(k, cap)) m <<= 1;
     const size_t smem = (size_t)m * sizeof(unsigned long long);
-    // the attribute is per device: set it on every launch that needs the opt-in (a process may hold indexes on several GPUs)
-    if (smem > 48 * 1024)
-        DHR_CUDA(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the attribute is per device, so it is set on every launch (a process may hold indexes on several GPUs); the kernel's
+    // 33 KiB of static shared memory count against the 48 KiB default, so even small k needs the opt-in
+    DHR_CUDA(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     topk_select_kernel<<<n_slots, kSelectThreads, smem, st>>>(t, k, cap, final_pass ? 1 : 0, o);
     DHR_CUDA(cudaGetLastError());
     return DHR_OK;
