@@ -3,21 +3,29 @@
 
     python bench.py --gpus 1 --steps K --warmup W                 # this repo's CUDA path
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference ...                          # reference algorithm on the host cores
+    python bench.py --impl reference ...                          # the reference's own gip_retrieval.py on the host cores
 
 A step = one search of the whole query set (Q queries, top-k) over the resident corpus.
-`value`   queries/sec with queries and results resident in HBM (device pointers through the API),
-`e2e`     the same through the public API with HOST (pinned) query buffers and host result buffers,
-          i.e. with the H2D / D2H copies inside the timed region,
-`roofline` achieved HBM bandwidth of the dominant kernel (the fused scan K1): logical corpus passes x
-          N x row_bytes / summed CUDA-event duration of the scan launches, vs the measured HBM peak,
-`cpu_baseline` the torch-op port of the reference loop (oracle/gip_oracle.py) on the host cores, on a
-          bounded sample (rank 0, N=1 only).
+`value`    queries/sec with queries and results resident in HBM (device pointers through the C ABI),
+`e2e`      the same through the public API with HOST (pinned) query buffers and host result buffers,
+           i.e. with the H2D / D2H copies inside the timed region,
+`roofline` the scan kernels (K2 tcgen05 dense block + K1t lexical tile walk, or K2 alone for a dense-only index) against the
+           ceiling that bounds them: algorithmic bytes (DESIGN.md units) / summed CUDA-event duration of the scan launches
+           vs the measured HBM peak, and 2*Q*N*C / time vs the measured sustained tensor peak; next to them the
+           physical DRAM rate (ncu `dram__bytes` per launch, profiles/traffic.json) and the CUDA-core lane-op ceiling,
+`verified` the answer checked where it is benchmarked: sample queries spread over the super-batches are re-scored over the
+           WHOLE corpus with plain torch fp32 ops (the reference's own operator sequence, gip_retrieval.py:119-120) on the
+           same device and compared with the returned top-k (scores, completeness, order); at N > 1 the merged NCCL
+           result is what is checked; at N = 1 the tile path is also compared with the independent row-scan kernel K1,
+`cpu_baseline` the reference file itself (oracle/_ref, kind "reference"; the torch-op port when the copy is absent) on the
+           host cores, on a bounded sample (rank 0, N=1 only).
 Synthetic encoded vectors of MS MARCO shape (dhr_b200/synth.py); inputs are far larger than L2.
 """
 from __future__ import annotations
 
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -48,9 +56,13 @@ def parse():
     ap.add_argument('--overlap', type=int, default=None, help='hybrid tile path: K2 on a second stream (1, default) or in line (0)')
     ap.add_argument('--dense-multicast', type=int, default=None, help='K2: cluster of two query groups sharing corpus tiles by TMA multicast (1, default) or not (0)')
     ap.add_argument('--dense-variant', type=int, default=None, help='K2: 1 = queries in TMEM (default), 0 = both operands in shared memory')
+    ap.add_argument('--option', action='append', default=[], help='extra index option name=value (repeatable)')
     ap.add_argument('--cpu-rows', type=int, default=400000, help='rows of the bounded CPU-baseline sample')
-    ap.add_argument('--cpu-queries', type=int, default=24)
+    ap.add_argument('--cpu-queries', type=int, default=12)
+    ap.add_argument('--cpu-full', action='store_true', help='--impl reference: the full SURVEY 8(d) procedure (16 shards, 1 thread and all cores)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-verify', action='store_true')
+    ap.add_argument('--verify-queries', type=int, default=16)
     return ap.parse_args()
 
 
@@ -59,7 +71,7 @@ def load_peaks():
     if os.path.exists(p):
         with open(p) as f:
             return json.load(f), 'measured'
-    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0}, 'fallback'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
 
 
 class ClockSampler:
@@ -105,38 +117,59 @@ class ClockSampler:
                 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
-class CpuPort:
-    """Torch-op port of the reference loop (gip_retrieval.py:110-126 / :70-79) on a bounded sample of `rows` rows; the
-    algorithm is exactly linear in N, so q/s at n_total rows = measured q/s * rows / n_total."""
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own file (oracle/_ref) or, when the copy is absent, the torch-op port
+# ---------------------------------------------------------------------------------------------------------------------
+class CpuArm:
+    """Times `GIP_retrieval` / `IP_retrieval` exactly as the reference's main() prepares its inputs (fp32 CPU tensors,
+    gip_retrieval.py:275,313) on a bounded sample of `rows` rows; the algorithm is exactly linear in N (one pass per query,
+    :115), so q/s at n_total rows = measured q/s * rows / n_total.  G > 1 workloads hand the reference one idx per value
+    column (np.repeat) so that :119 computes the grouped sum."""
 
-    def __init__(self, workload, rows, n_queries, topk, threads):
+    def __init__(self, workload, rows, n_queries, topk):
         import torch
         from dhr_b200 import synth
         from oracle import gip_oracle as go
-        self.go, self.torch = go, torch
+        from oracle import refshim
+        self.torch, self.go = torch, go
         self.cfg = cfg = synth.CONFIGS[workload]
-        torch.set_num_threads(threads)
+        if refshim.copy_available():
+            self.kind, self.ref = 'reference', refshim.load_copy()
+            self.what = 'castorini/dhr retrieval/gip_retrieval.py (verbatim copy under oracle/_ref), GIP_retrieval / IP_retrieval'
+        else:
+            self.kind, self.ref = 'port', None
+            self.what = 'torch-op port of gip_retrieval.py:110-126 (oracle/_ref copy absent)'
         cv, ci = synth.corpus_numpy(workload, 0, rows)
         qv, qi = synth.queries_numpy(workload, n_queries)
         G = cfg['G']
+        self.rows = rows
         self.c = torch.from_numpy(cv.astype(np.float32))              # :313 the CPU path works on fp32 copies
         self.q = torch.from_numpy(qv.astype(np.float32))
         self.qids = list(range(n_queries))
         self.k = min(topk, rows)
-        if cfg['S'] > 0:                                              # G > 1: one idx per value column (SURVEY 8d)
+        if cfg['S'] > 0:
             self.cidx = torch.from_numpy(np.repeat(ci, G, axis=1).astype(np.int16))
             self.qidx = torch.from_numpy(np.repeat(qi, G, axis=1).astype(np.int16))
 
-    def run(self, n=None):
-        """time the port on the first n (default all) sample queries"""
-        go, cfg = self.go, self.cfg
+    def run(self, n=None, rows=None, threads=None):
+        """seconds for the first n sample queries over the first `rows` sample rows with `threads` torch threads"""
+        torch, go, cfg = self.torch, self.go, self.cfg
         n = len(self.qids) if n is None else min(n, len(self.qids))
+        rows = self.rows if rows is None else min(rows, self.rows)
+        if threads:
+            torch.set_num_threads(threads)
+        c = self.c[:rows]
+        k = min(self.k, rows)
+        sink = io.StringIO()
         t0 = time.perf_counter()
-        if cfg['S'] > 0:
-            go.GIP_retrieval_port(self.qids[:n], self.q[:n], self.qidx[:n], self.c, self.cidx,
-                                  go.make_args(emb_dim=cfg['S'] * cfg['G'], topk=self.k, brute_force=True))
-        else:
-            go.IP_retrieval_port(self.qids[:n], self.q[:n], self.c, go.make_args(topk=self.k))
+        with contextlib.redirect_stdout(sink), contextlib.redirect_stderr(sink):
+            if cfg['S'] > 0:
+                args = go.make_args(emb_dim=cfg['S'] * cfg['G'], topk=k, brute_force=True)
+                fn = self.ref.GIP_retrieval if self.ref else go.GIP_retrieval_port
+                fn(self.qids[:n], self.q[:n], self.qidx[:n], c, self.cidx[:rows], args)
+            else:
+                fn = self.ref.IP_retrieval if self.ref else go.IP_retrieval_port
+                fn(self.qids[:n], self.q[:n], c, go.make_args(topk=k))
         return time.perf_counter() - t0
 
 
@@ -147,9 +180,33 @@ def workload_string(workload, n_total, n_q, k):
         workload, n_total, n_q, cfg['S'], cfg['G'], cfg['idx'], cfg['C'], k)
 
 
+def cpu_baseline_block(args, n_total, k, threads):
+    """bounded sample (about 10-30 s of CPU work): all cores at two sizes (linearity), one thread as shipped (:259)"""
+    arm = CpuArm(args.workload, min(args.cpu_rows, n_total), args.cpu_queries, k)
+    rows = arm.rows
+    arm.run(1, threads=threads)                                       # warm-up
+    t_all = arm.run(threads=threads)
+    t_half = arm.run(rows=rows // 2, threads=threads)
+    n1 = max(1, min(2, args.cpu_queries))
+    t_one = arm.run(n1, threads=1)
+    nq = args.cpu_queries
+    v = nq / t_all * rows / n_total
+    return {
+        'value': v, 'unit': 'queries/s', 'cores': threads, 'kind': arm.kind,
+        'sample': '%d queries x %d rows (%.1f s), %s, torch.set_num_threads(%d), scaled linearly to %d rows' % (
+            nq, rows, t_all, arm.what, threads, n_total),
+        'one_thread': {'value': n1 / t_one * rows / n_total, 'unit': 'queries/s', 'cores': 1,
+                       'sample': '%d queries x %d rows (%.1f s), as shipped: torch.set_num_threads(1) (gip_retrieval.py:259)' % (n1, rows, t_one)},
+        'linearity': {'rows': [rows // 2, rows], 's_per_query': [t_half / nq, t_all / nq],
+                      'ratio': (t_all / nq) / max(1e-12, t_half / nq)},
+    }
+
+
 def run_reference(args):
-    """--impl reference: the reference algorithm (torch-op port, kind "port": the reference is pure Python and
-    /root/reference does not exist on the GPU box) on the host cores, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref copy of gip_retrieval.py; the
+    torch-op port if the copy is absent) on the host cores.  Each step is a bounded sample of the workload; --cpu-full runs
+    SURVEY 8(d)'s whole procedure once (T=16 shards through the reference's range-sharding rule, >= 20 queries per shard,
+    one thread as shipped and all cores, plus a 1 M-row linearity point)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -157,27 +214,118 @@ def run_reference(args):
     import torch
     n_total = args.rows or synth.N_MSMARCO
     threads = os.cpu_count() or 1
-    rows = min(args.cpu_rows, n_total)
     n_q = args.queries or synth.Q_MSMARCO
-    port = CpuPort(args.workload, rows, args.cpu_queries, args.topk, threads)
+    extra = {}
+    if args.cpu_full:
+        per = n_total // 16
+        nq = max(20, args.cpu_queries)
+        arm = CpuArm(args.workload, max(per, min(1000000, n_total)), nq, args.topk)
+        arm.run(1, rows=per, threads=threads)
+        shard_all = [arm.run(rows=per, threads=threads) for _ in range(2)]
+        shard_one = arm.run(4, rows=per, threads=1)
+        lin = arm.run(4, rows=min(1000000, n_total), threads=threads)
+        # every shard holds statistically identical rows, so 16 shard passes = 16 x one measured shard pass
+        extra = {'procedure': 'SURVEY 8(d): T=16 shards of %d rows (gip_retrieval.py:292-306), %d queries per shard; per-query time = 16 x shard time' % (per, nq),
+                 'all_cores': {'cores': threads, 's_per_query_mean': 16 * float(np.mean(shard_all)) / nq, 's_per_query_min': 16 * min(shard_all) / nq,
+                               'queries_per_s': nq / (16 * float(np.mean(shard_all)))},
+                 'one_thread': {'cores': 1, 's_per_query': 16 * shard_one / 4, 'queries_per_s': 4 / (16 * shard_one)},
+                 'linearity_1m': {'rows': min(1000000, n_total), 's_per_query': lin / 4, 'shard_rows': per,
+                                  's_per_query_shard': float(np.mean(shard_all)) / nq,
+                                  'ratio_time': (lin / 4) / (float(np.mean(shard_all)) / nq), 'ratio_rows': min(1000000, n_total) / per}}
+        rows, nqs = per, nq
+    else:
+        rows, nqs = min(args.cpu_rows, n_total), args.cpu_queries
+        arm = CpuArm(args.workload, rows, nqs, args.topk)
     times = []
     for i in range(args.warmup + args.steps):
-        dt = port.run()
+        dt = arm.run(rows=rows, threads=threads)
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
-    qps = args.cpu_queries / (ms / 1e3) * rows / n_total
-    sample = '%d queries x %d rows per step, torch %s CPU, %d threads, scaled linearly to %d rows' % (
-        args.cpu_queries, rows, torch.__version__, threads, n_total)
+    qps = nqs / (ms / 1e3) * rows / n_total
+    sample = '%d queries x %d rows per step, %s, torch %s CPU, %d threads, scaled linearly to %d rows' % (
+        nqs, rows, arm.what, torch.__version__, threads, n_total)
     line = {
         'impl': 'reference', 'metric': 'queries/sec', 'value': qps, 'unit': 'queries/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': workload_string(args.workload, n_total, n_q, args.topk)},
-        'cpu_baseline': {'value': qps, 'unit': 'queries/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': qps, 'unit': 'queries/s', 'cores': threads, 'kind': arm.kind, 'sample': sample},
         'e2e': {'value': qps, 'unit': 'queries/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
+    if extra:
+        line['cpu_full'] = extra
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# verification at the benchmarked size: plain torch fp32 re-scoring of sample queries over the whole (shard of the) corpus
+# ---------------------------------------------------------------------------------------------------------------------
+def torch_reference_scores(workload, lo, hi, qv, qi, dev):
+    """fp32 scores [n_sample, hi - lo] by the reference's operator sequence (gip_retrieval.py:119-120): eq-mask * values,
+    row dot; corpus rows regenerated segment by segment from the same seeds as the index build."""
+    import torch
+    from dhr_b200 import synth
+    cfg = synth.CONFIGS[workload]
+    S, G, C = cfg['S'], cfg['G'], cfg['C']
+    n = qv.shape[0]
+    out = torch.empty((n, hi - lo), dtype=torch.float32, device=dev)
+    q = qv.to(torch.float32)
+    q_lex = q[:, :S * G].reshape(n, S, G) if S > 0 else None
+    q_dns = q[:, S * G:] if C > 0 else None
+    q_idx = qi.to(torch.int32) if S > 0 else None
+    pos = 0
+    for vals, idx in synth.corpus_torch_segments(workload, lo, hi, dev):
+        m = vals.shape[0]
+        v = vals.to(torch.float32)
+        sc = torch.zeros((n, m), dtype=torch.float32, device=dev)
+        if C > 0:
+            sc += q_dns @ v[:, S * G:].T
+        if S > 0:
+            c_lex = v[:, :S * G].reshape(m, S, G)
+            c_idx = idx.to(torch.int32)
+            for i in range(n):
+                per_slice = (c_lex * q_lex[i]).sum(dim=2)                             # [m, S] grouped inner products
+                sc[i] += (per_slice * (c_idx == q_idx[i])).sum(dim=1)
+        out[:, pos:pos + m] = sc
+        pos += m
+    return out
+
+
+def verify_results(workload, lo, hi, sample, qv, qi, res_scores, res_rows, k, dev, world, dist, tol=1e-3, eps=2e-5):
+    """res_* [n_sample, k]: the benchmarked answer (global rows) for the sample queries.  Every rank checks the rows of its
+    shard [lo, hi); counts are summed over ranks."""
+    import torch
+    ref = torch_reference_scores(workload, lo, hi, qv, qi, dev)
+    n = ref.shape[0]
+    rows = res_rows.to(dev)
+    scores = res_scores.to(dev)
+    mine = (rows >= lo) & (rows < hi)
+    local = (rows - lo).clamp(0, hi - lo - 1)
+    ref_at = torch.gather(ref, 1, local)
+    err = torch.where(mine, (ref_at - scores).abs(), torch.zeros_like(scores))
+    max_err = float(err.max().item()) if err.numel() else 0.0
+    # completeness: no row outside the answer may beat the k-th returned score by more than fp32 reorder noise
+    kth = scores[:, -1:].clone()
+    covered = ref.clone()
+    covered.scatter_(1, local, torch.where(mine, torch.full_like(scores, -float('inf')), torch.gather(ref, 1, local)))
+    missed = int((covered > kth + eps).sum().item())
+    n_mine = int(mine.sum().item())
+    cnt = torch.tensor([n_mine, missed], dtype=torch.int64, device=dev)
+    mx = torch.tensor([max_err], dtype=torch.float32, device=dev)
+    if world > 1:
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    s = res_scores.cpu().numpy().astype(np.float64)
+    r = res_rows.cpu().numpy()
+    order_ok = bool(np.all((s[:, :-1] > s[:, 1:]) | ((s[:, :-1] == s[:, 1:]) & (r[:, :-1] < r[:, 1:]))))
+    unique_ok = all(len(set(row.tolist())) == k for row in r)
+    out = {'queries': n, 'sample': [int(x) for x in sample], 'rows_checked': int(cnt[0].item()), 'rows_expected': n * k,
+           'max_abs_score_err': float(mx[0].item()), 'tolerance': tol, 'missed_rows': int(cnt[1].item()),
+           'order_score_desc_row_asc': order_ok, 'rows_unique': unique_ok,
+           'against': 'torch fp32 eq-mask * values row-dot over all %d rows (gip_retrieval.py:119-120) on the same device' % (hi - lo)}
+    out['ok'] = bool(out['rows_checked'] == n * k and out['max_abs_score_err'] <= tol and out['missed_rows'] == 0 and order_ok and unique_ok)
+    return out
 
 
 def main():
@@ -187,7 +335,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from dhr_b200 import GipIndex, synth, topk_merge
+    from dhr_b200 import GipIndex, synth
     from dhr_b200.gip_retrieval import shard_bounds
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -203,6 +351,7 @@ def main():
         dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    torch.backends.cuda.matmul.allow_tf32 = False
 
     cfg = synth.CONFIGS[args.workload]
     n_total = args.rows or synth.N_MSMARCO
@@ -218,18 +367,13 @@ def main():
     ix.finalize()
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build
-    if args.query_block is not None:
-        ix.set_option('query_block', args.query_block)
-    if args.query_groups is not None:
-        ix.set_option('query_groups', args.query_groups)
-    if args.scan_variant is not None:
-        ix.set_option('scan_variant', args.scan_variant)
-    if args.overlap is not None:
-        ix.set_option('overlap', args.overlap)
-    if args.dense_variant is not None:
-        ix.set_option('dense_variant', args.dense_variant)
-    if args.dense_multicast is not None:
-        ix.set_option('dense_multicast', args.dense_multicast)
+    for name, val in (('query_block', args.query_block), ('query_groups', args.query_groups), ('scan_variant', args.scan_variant),
+                      ('overlap', args.overlap), ('dense_variant', args.dense_variant), ('dense_multicast', args.dense_multicast)):
+        if val is not None:
+            ix.set_option(name, val)
+    for kv in args.option:
+        name, val = kv.split('=')
+        ix.set_option(name, int(val))
     ix.set_option('profile', 1)
 
     qv_dev, qi_dev = synth.queries_torch(args.workload, n_q, dev)
@@ -239,11 +383,11 @@ def main():
                torch.empty((n_q,), dtype=torch.int32, device=dev))
     out_host = (torch.empty((n_q, k), dtype=torch.float32).pin_memory(), torch.empty((n_q, k), dtype=torch.int64).pin_memory(),
                 torch.empty((n_q,), dtype=torch.int32).pin_memory())
+    searcher = None
     if world > 1:
-        gat_s = torch.empty((world, n_q, k), dtype=torch.float32, device=dev)
-        gat_r = torch.empty((world, n_q, k), dtype=torch.int64, device=dev)
-
-    from dhr_b200.distributed import sharded_search
+        from dhr_b200.distributed import ShardedSearcher
+        searcher = ShardedSearcher(ix, n_q, k)
+        searcher.profile = True
 
     def step(host_io):
         """one search of all queries over the (sharded) corpus; returns the final [Q,k] (scores, rows)"""
@@ -252,10 +396,11 @@ def main():
             res = ix.search(qv, qi, k, out=out_host if host_io else out_dev)[:2]
             st = ix.stats()
         else:
-            # per-shard search, then the exchange step: NCCL all-gather of the [Q,k] lists + merge kernel
-            res = sharded_search(ix, qv, qi, k, local_out=out_dev, gather_out=(gat_s, gat_r))
+            # per-shard search enqueued as one stream-ordered call; per batch of 256 queries the packed keys are all-gathered
+            # (NCCL) and merged on a side stream while the next batch is scanned
+            res = searcher.search(qv, qi, k, out=out_dev[:2])
             st = ix.stats()
-            st['n_kernel_launches'] += 1
+            st['n_kernel_launches'] += searcher.n_merge_launches
             if host_io and rank == 0:
                 out_host[0].copy_(res[0], non_blocking=True)
                 out_host[1].copy_(res[1], non_blocking=True)
@@ -281,100 +426,171 @@ def main():
 
     for _ in range(max(3, args.warmup)):
         step(False)
+    index_bytes = ix.device_bytes                                     # resident during the timed region
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     ms_dev, stats = timed(args.steps, False)
     clocks = sampler.stop() if rank == 0 else None
+    exch = dict(searcher.breakdown) if searcher is not None else None
     step(True)
     ms_e2e, _ = timed(args.steps, True)
 
-    # HBM-bound operating point of the scan (K1, one query per corpus pass, one group per launch): bounded sample
+    # ---- the answer, checked where it is benchmarked ----
+    verified = None
+    if not args.no_verify:
+        res, _ = step(False)
+        torch.cuda.synchronize()
+        nv = min(args.verify_queries, n_q)
+        sample = np.unique(np.linspace(0, n_q - 1, nv).astype(np.int64))
+        st = torch.from_numpy(sample).to(dev)
+        verified = verify_results(args.workload, lo, hi, sample, qv_dev[st], qi_dev[st] if qi_dev is not None else None,
+                                  res[0][st], res[1][st], k, dev, world, dist)
+    tile_first = None
+    if world == 1 and not args.no_verify:
+        n_s = min(8, n_q)
+        tile_first = (out_dev[0][:n_s].clone(), out_dev[1][:n_s].clone())
+
+    # HBM-bound operating point of the scan (K1, one query per corpus pass, one group per launch): bounded sample.  K1 reads the
+    # row-major arrays, which are rebuilt from the tiled copies for this leg and dropped again afterwards.
     qb1 = None
-    if cfg['S'] > 0 or True:
+    if world == 1:
         n_s = min(8, n_q)
         ix.set_option('tile_mode', 0); ix.set_option('query_block', 1); ix.set_option('query_groups', 1); ix.set_option('scan_variant', 1)
-        ix.search(qv_dev[:n_s], qi_dev[:n_s] if qi_dev is not None else None, k, out=tuple(o[:n_s] for o in out_dev))
-        ix.search(qv_dev[:n_s], qi_dev[:n_s] if qi_dev is not None else None, k, out=tuple(o[:n_s] for o in out_dev))
+        k1_out = tuple(torch.empty_like(o[:n_s]) for o in out_dev)
+        ix.search(qv_dev[:n_s], qi_dev[:n_s] if qi_dev is not None else None, k, out=k1_out)
+        ix.search(qv_dev[:n_s], qi_dev[:n_s] if qi_dev is not None else None, k, out=k1_out)
         s1 = ix.stats()
         qb1 = {'scan_ms': s1['scan_ms'], 'passes': s1['corpus_passes'], 'queries': n_s, 'total_ms': s1['total_ms']}
+        torch.cuda.synchronize()
+        if tile_first is not None and verified is not None:
+            same_rows = float((tile_first[1] == k1_out[1]).float().mean().item())
+            d = float((tile_first[0] - k1_out[0]).abs().max().item())
+            verified['cross_kernel'] = {'queries': n_s, 'rows_equal_frac': same_rows, 'max_abs_score_diff': d,
+                                        'what': 'tile path (K2 + K1t) vs row-scan kernel K1 on the same queries at full size; positions may '
+                                                'differ only inside fp32-reorder near-ties'}
+            verified['ok'] = bool(verified['ok'] and same_rows >= 0.99 and d <= 1e-3)
+        ix.set_option('tile_mode', 1); ix.set_option('rowmajor', 0)
 
-    # ---- roofline of the dominant kernel (K1 scan), from CUDA events inside the library ----
+    # ---- roofline of the scan kernels, from CUDA events inside the library ----
     scan_ms = sum(s['scan_ms'] for s in stats)
     select_ms = sum(s['select_ms'] for s in stats)
     passes = sum(s['corpus_passes'] for s in stats)
     launches = sum(s['n_scan_launches'] for s in stats)
+    alg_bytes = sum(s['alg_bytes'] for s in stats)
+    dense_flops = sum(s['dense_flops'] for s in stats)
     bytes_per_pass = stats[0]['bytes_per_pass']
+    variant = stats[0]['scan_variant']
     peaks, peak_src = load_peaks()
-    achieved = passes * bytes_per_pass / (scan_ms / 1e3) / 1e9 if scan_ms > 0 else 0.0
-    traffic = None
+    traffic_all = {}
     tp = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tp):
         try:
             with open(tp) as f:
-                traffic = json.load(f).get(args.workload)
+                traffic_all = json.load(f)
         except Exception:
-            traffic = None
+            traffic_all = {}
+    tw = traffic_all.get(args.workload) if isinstance(traffic_all.get(args.workload), dict) else None
 
     if rank == 0:
         qps = n_q * args.steps / (ms_dev / 1e3)
         qps_e2e = n_q * args.steps / (ms_e2e / 1e3)
-        W = cfg['S'] * cfg['G'] + cfg['C']
         h2d = int(qv_host.numel() * qv_host.element_size() + (qi_host.numel() * qi_host.element_size() if qi_host is not None else 0))
         d2h = int(n_q * k * 12 + (n_q * 4 if world == 1 else 0))
+        scan_s = scan_ms / 1e3
+        hbm_achieved = alg_bytes / scan_s / 1e9 if scan_s > 0 else 0.0
+        tensor_achieved = dense_flops / scan_s / 1e12 if scan_s > 0 else 0.0
+        tensor_peak = peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops'))
+        kernel_names = {1: 'gip_scan_tma (K1)', 0: 'gip_scan_direct (K1)', 2: 'dense_tile_ts (K2, tcgen05, queries in TMEM)',
+                        3: 'lex_tile (K1t) + dense_tile_ts (K2, tcgen05, queries in TMEM)'}
+        if variant == 2:      # dense-only: a GEMM -> tensor ceiling (sustained: timed inside a long step)
+            roof = {'bound': 'tensor', 'achieved': tensor_achieved, 'peak': tensor_peak, 'unit': 'TFLOP/s',
+                    'frac': tensor_achieved / tensor_peak, 'peak_kind': 'bf16 sustained (fp16 runs at the same rate)',
+                    'hbm': {'achieved': hbm_achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': hbm_achieved / peaks['hbm_gbs'],
+                            'what': 'N x C_pad x 2 bytes per group of 128 queries / scan time'}}
+        else:
+            roof = {'bound': 'hbm', 'achieved': hbm_achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': hbm_achieved / peaks['hbm_gbs'],
+                    'what': 'algorithmic bytes in DESIGN.md units (K1t: lexical bytes per tile of 64 queries; K2: dense bytes per 128 queries; '
+                            'K1: row bytes per group) / summed scan-launch time'}
+            if dense_flops > 0:
+                roof['tensor'] = {'achieved': tensor_achieved, 'peak': tensor_peak, 'unit': 'TFLOP/s', 'frac': tensor_achieved / tensor_peak,
+                                  'what': 'K2 flops (2*Q*N*C) over the WHOLE scan time (K2 shares the SMs with K1t)'}
+            if cfg['S'] > 0:
+                # SURVEY 8(d) lexical lane-op count of the compare-everything formulation vs the CUDA-core ceiling; the tile walk is
+                # O(matches), so it may exceed that "ceiling"
+                lane_ops = float(n_q) * args.steps * (hi - lo) * (cfg['S'] + cfg['S'] * cfg['G'])
+                lane_peak = 148 * 128 * 1.965e9
+                roof['alu'] = {'achieved': lane_ops / scan_s if scan_s > 0 else 0.0, 'peak': lane_peak, 'unit': 'lane-ops/s',
+                               'frac': lane_ops / scan_s / lane_peak if scan_s > 0 else 0.0,
+                               'what': 'Q*N*S compare+select + Q*N*D FMA lane-ops (SURVEY 8d) / scan time vs 148 SMs x 128 lanes x 1.965 GHz; '
+                                       'K1t walks only the matching (query, passage, slice) triples, so > 1 is possible'}
+        if tw:
+            roof['traffic'] = tw.get('dram_bytes_per_launch')
+            if tw.get('dram_bytes_per_launch') and tw.get('launch_kind'):
+                roof['traffic_note'] = tw['launch_kind']
+            for key in ('issue_active_pct', 'lsu_wavefront_pct', 'tensor_pipe_pct', 'dram_pct', 'source'):
+                if key in tw:
+                    roof.setdefault('ncu', {})[key] = tw[key]
+            if tw.get('dram_bytes_per_step_estimate'):
+                phys = tw['dram_bytes_per_step_estimate'] * args.steps / scan_s / 1e9 if scan_s > 0 else 0.0
+                roof['physical_dram'] = {'achieved': phys, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': phys / peaks['hbm_gbs'],
+                                         'what': 'ncu dram__bytes per launch x launches per step / scan time'}
+        else:
+            roof['traffic'] = None
+        roof.update({'peak_source': peak_src, 'kernel': kernel_names.get(variant, '?'), 'queries_per_pass': stats[0]['query_block'],
+                     'bytes_per_launch': alg_bytes / max(1, launches), 'launch_ms_avg': scan_ms / max(1, launches),
+                     'corpus_passes_per_step': passes / args.steps, 'logical_pass_bytes': bytes_per_pass,
+                     'scan_share_of_step': scan_ms / ms_dev, 'select_share_of_step': select_ms / ms_dev})
         line = {
             'metric': 'queries/sec', 'value': qps, 'unit': 'queries/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
             'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-            'dtype': 'f32',  # fp16 storage, exact fp16 x fp16 products accumulated in fp32 (FHFMA)
+            'dtype': 'f32',  # fp16 storage, exact fp16 x fp16 products accumulated in fp32 (FHFMA / tcgen05 kind::f16)
             'data': 'synthetic',
             'config': {
                 'workload': workload_string(args.workload, n_total, n_q, k),
-                'row_bytes': ix.row_bytes, 'corpus_bytes': ix.row_bytes * n_total, 'parallelism': 'range-shard x%d' % world,
-                'query_block': stats[0]['query_block'], 'query_groups': stats[0]['query_groups'], 'scan_variant': stats[0]['scan_variant'],
+                'row_bytes': ix.row_bytes, 'corpus_bytes': ix.row_bytes * n_total, 'index_bytes': index_bytes,
+                'parallelism': 'range-shard x%d' % world,
+                'query_block': stats[0]['query_block'], 'query_groups': stats[0]['query_groups'], 'scan_variant': variant,
                 'l2': 'inputs (%.1f GB per GPU) far exceed the 126 MB L2' % (ix.row_bytes * (hi - lo) / 1e9),
                 'index_build_s': t_build,
             },
-            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'],
-                         'traffic': traffic, 'peak_source': peak_src,
-                         'kernel': {1: 'gip_scan_tma (K1)', 0: 'gip_scan_direct (K1)', 2: 'dense_tile_ts (K2, tcgen05, queries in TMEM)',
-                                    3: 'dense_tile_ts (K2, tcgen05, queries in TMEM) + lex_tile (K1t)'}.get(stats[0]['scan_variant'], '?'),
-                         'queries_per_pass': stats[0]['query_block'],
-                         'note': 'achieved = logical corpus passes (one per query tile of `queries_per_pass`) x N x row_bytes / kernel time; '
-                                 'query tiles in flight share the pass through L2, so DRAM traffic is lower (see traffic)',
-                         'bytes_per_launch': passes * bytes_per_pass / max(1, launches), 'launch_ms_avg': scan_ms / max(1, launches),
-                         'corpus_passes_per_step': passes / args.steps, 'scan_share_of_step': scan_ms / ms_dev,
-                         'select_share_of_step': select_ms / ms_dev},
+            'roofline': roof,
             'e2e': {'value': qps_e2e, 'unit': 'queries/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': int(sum(s['n_kernel_launches'] for s in stats)),
             'clocks': clocks,
             'fallback_queries': int(sum(s['n_fallback_queries'] for s in stats)),
         }
+        if verified is not None:
+            line['verified'] = verified
+        if world > 1:
+            step_ms = ms_dev / args.steps
+            line['breakdown'] = {'step_ms': step_ms, 'scan_ms': scan_ms / args.steps, 'select_ms': select_ms / args.steps,
+                                 'exchange_ms_overlapped': (exch or {}).get('exchange_ms'), 'exchange_tail_ms': (exch or {}).get('tail_ms'),
+                                 'other_ms': step_ms - (scan_ms + select_ms) / args.steps,
+                                 'what': 'rank 0, last timed step for the exchange: scan/select = summed launch times on the main stream; exchange = '
+                                         'NCCL all-gather + key merge per 256-query batch on the side stream (hidden behind the scan); tail = '
+                                         'part of the exchange after the last scan launch; other = prep, launch gaps, rank skew'}
         if qb1 and qb1['scan_ms'] > 0:
             a1 = qb1['passes'] * bytes_per_pass / (qb1['scan_ms'] / 1e3) / 1e9
             line['roofline_qb1'] = {'bound': 'hbm', 'achieved': a1, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': a1 / peaks['hbm_gbs'],
                                     'kernel': 'gip_scan_tma (K1), one query per corpus pass', 'queries': qb1['queries'],
                                     'queries_per_sec': qb1['queries'] / (qb1['total_ms'] / 1e3) if qb1['total_ms'] > 0 else None}
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            rows = min(args.cpu_rows, n_total)
-            port = CpuPort(args.workload, rows, args.cpu_queries, k, threads)
-            port.run(2)                       # warm-up on two queries
-            dt = port.run()
-            v = args.cpu_queries / dt * rows / n_total
-            line['cpu_baseline'] = {
-                'value': v, 'unit': 'queries/s', 'cores': threads, 'kind': 'port',
-                'sample': '%d queries x %d rows (%.1f s), torch-op port of gip_retrieval.py:110-126, scaled linearly to %d rows' % (
-                    args.cpu_queries, rows, dt, n_total)}
+            line['cpu_baseline'] = cpu_baseline_block(args, n_total, k, os.cpu_count() or 1)
         if world > 1:
             import ctypes
             ctypes.CDLL(None).fflush(None)                  # C stdio may still buffer the banner
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+    ok = verified is None or verified['ok']
     ix.close()
     if world > 1:
         dist.destroy_process_group()
+    if not ok:
+        sys.stderr.write('bench.py: VERIFICATION FAILED: %s\n' % json.dumps(verified))
+        sys.exit(3)
 
 
 if __name__ == '__main__':

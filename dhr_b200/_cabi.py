@@ -39,7 +39,7 @@ class DhrStats(ctypes.Structure):
         ('n_prep_launches', ctypes.c_int32), ('n_fallback_queries', ctypes.c_int32),
         ('n_kernel_launches', ctypes.c_int32), ('rowmajor_rebuilds', ctypes.c_int32),
         ('scan_ms', ctypes.c_double), ('select_ms', ctypes.c_double), ('total_ms', ctypes.c_double),
-        ('corpus_passes', ctypes.c_double), ('bytes_per_pass', ctypes.c_double), ('dense_flops', ctypes.c_double),
+        ('corpus_passes', ctypes.c_double), ('bytes_per_pass', ctypes.c_double), ('dense_flops', ctypes.c_double), ('alg_bytes', ctypes.c_double),
     ]
 
     def as_dict(self):

@@ -276,6 +276,7 @@ static int run_batch(dhr_index* h, const QuerySet& qs, int base, int nq, int k, 
         h->stats.n_select_launches++;
         h->stats.n_kernel_launches += 2;
         h->stats.corpus_passes += (double)(a.row_end - a.row_begin) * a.n_groups / (double)std::max<int64_t>(1, h->n_rows);
+        h->stats.alg_bytes += (double)(a.row_end - a.row_begin) * a.n_groups * (double)g.row_bytes();
     }
     if (n_chunks == 0) {   // empty index: all padding
         DHR_TRY(launch_select(t, nq, k, kCandCap, true, so, st));
@@ -305,6 +306,7 @@ static int run_batch_dense_tile(dhr_index* h, const QuerySet& qs, int base, int 
         h->stats.n_kernel_launches += 2;
         h->stats.corpus_passes += (double)(bounds[c + 1] - bounds[c]) * ((nq + 127) / 128) / (double)std::max<int64_t>(1, h->n_rows);   // K2 (TS): one pass per 128 queries
         h->stats.dense_flops += 2.0 * (double)(bounds[c + 1] - bounds[c]) * (double)nq * (double)h->g.C;
+        h->stats.alg_bytes += (double)(bounds[c + 1] - bounds[c]) * ((nq + 127) / 128) * (double)h->g.C_pad * 2.0;
     }
     if (n_chunks == 0) {
         DHR_TRY(launch_select(t, nq, k, kCandCap, true, so, st));
@@ -437,6 +439,9 @@ static int run_batch_hybrid_tile(dhr_index* h, const LexTileGeom& lt, const Quer
         h->stats.corpus_passes += (double)(bounds[c + 1] - bounds[c]) * ((nq + kLexTileQueries - 1) / kLexTileQueries) /
                                   (double)std::max<int64_t>(1, h->n_rows);
         h->stats.dense_flops += 2.0 * (double)(bounds[c + 1] - bounds[c]) * (double)nq * (double)g.C;
+        h->stats.alg_bytes += (double)(bounds[c + 1] - bounds[c]) *
+                              (((nq + kLexTileQueries - 1) / kLexTileQueries) * ((double)g.D_pad * 2.0 + (double)g.S_pad * lt.tcode_bytes) +
+                               ((nq + 127) / 128) * (double)g.C_pad * 2.0);
         if (overlap && c + 1 < n_chunks) {                           // the next chunk's K1t launches read the new tau
             DHR_CUDA(cudaEventRecord(h->ev_sel, st));
             DHR_CUDA(cudaStreamWaitEvent(k1s[1], h->ev_sel, 0));

@@ -67,6 +67,9 @@ class ShardedSearcher:
         self.out = (torch.empty((n_queries, k), dtype=torch.float32, device=dev),
                     torch.empty((n_queries, k), dtype=torch.int64, device=dev))
         self.breakdown = {}
+        self.profile = False            # bench.py: time the side-stream exchange (CUDA events) into self.breakdown
+        self.n_merge_launches = 0
+        self.n_rerun = 0
 
     def search(self, q_vals, q_idx, k, lamda=1.0, masked=True, out=None):
         """Returns (scores [Q,k], rows [Q,k] global ids), identical on every rank.  The result tensors are valid once the
@@ -80,17 +83,31 @@ class ShardedSearcher:
         if self.gathered is None or self.gathered.shape[1] < bs:
             self.gathered = torch.empty((world, bs, k), dtype=torch.int64, device=keys.device)
         side = self.side
+        prof = self.profile
+        if prof:
+            ev_main_end = torch.cuda.Event(enable_timing=True)
+            ev_main_end.record(main)                                     # after the last scan / select launch of the call
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nb)]
         with torch.cuda.stream(side):
             for b in range(nb):
                 lo, hi = b * bs, min(n, (b + 1) * bs)
                 ix.wait_batch(b, side.cuda_stream)
+                if prof:
+                    evs[b][0].record(side)
                 if world == 1:
                     merge_keys(keys[lo:hi].unsqueeze(0), out_s[lo:hi], out_r[lo:hi], stream=side.cuda_stream)
-                    continue
-                g = self.gathered.view(-1)[:world * (hi - lo) * k].view(world, hi - lo, k)
-                dist.all_gather_into_tensor(g, keys[lo:hi], group=self.group)
-                merge_keys(g, out_s[lo:hi], out_r[lo:hi], stream=side.cuda_stream)
+                else:
+                    g = self.gathered.view(-1)[:world * (hi - lo) * k].view(world, hi - lo, k)
+                    dist.all_gather_into_tensor(g, keys[lo:hi], group=self.group)
+                    merge_keys(g, out_s[lo:hi], out_r[lo:hi], stream=side.cuda_stream)
+                if prof:
+                    evs[b][1].record(side)
+        self.n_merge_launches = nb
         n_rerun = ix.complete(stream=main.cuda_stream)
+        if prof:
+            side.synchronize()
+            self.breakdown = {'exchange_ms': sum(a.elapsed_time(b_) for a, b_ in evs), 'tail_ms': max(0.0, ev_main_end.elapsed_time(evs[-1][1])),
+                              'batches': nb}
         main.wait_stream(side)
         if n_rerun > 0:
             # adversarial row order (never on shuffled corpora): some keys were rewritten after their batch was exchanged;

@@ -81,6 +81,8 @@ typedef struct dhr_stats {
     double   corpus_passes;      /* logical corpus passes made by the scan launches (sum rows*groups / N) */
     double   bytes_per_pass;     /* N * row_bytes of the HBM-resident layout                         */
     double   dense_flops;        /* 2 * Q * N * C issued to the tensor-core kernel K2 by the call        */
+    double   alg_bytes;          /* algorithmic bytes of the scan launches: K1 rows*row_bytes per group of QB queries, K1t
+                                    rows*(lexical value + code bytes) per tile of 64 queries, K2 rows*C_pad*2 per 128 queries */
 } dhr_stats;
 
 int         dhr_version(void);
