@@ -283,7 +283,7 @@ def torch_reference_scores(workload, lo, hi, qv, qi, dev):
             sc += q_dns @ v[:, S * G:].T
         if S > 0:
             c_lex = v[:, :S * G].reshape(m, S, G)
-            c_idx = idx.to(torch.int32)
+            c_idx = (idx.view(torch.int16).to(torch.int32) & 0xFFFF) if idx.dtype == torch.uint16 else idx.to(torch.int32)
             for i in range(n):
                 per_slice = (c_lex * q_lex[i]).sum(dim=2)                             # [m, S] grouped inner products
                 sc[i] += (per_slice * (c_idx == q_idx[i])).sum(dim=1)
@@ -444,8 +444,9 @@ def main():
         nv = min(args.verify_queries, n_q)
         sample = np.unique(np.linspace(0, n_q - 1, nv).astype(np.int64))
         st = torch.from_numpy(sample).to(dev)
-        verified = verify_results(args.workload, lo, hi, sample, qv_dev[st], qi_dev[st] if qi_dev is not None else None,
-                                  res[0][st], res[1][st], k, dev, world, dist)
+        qi_s = qi_dev.view(torch.int16)[st].to(torch.int32) & 0xFFFF if (qi_dev is not None and qi_dev.dtype == torch.uint16) else \
+            (qi_dev[st] if qi_dev is not None else None)                  # torch cannot index uint16 tensors on the device
+        verified = verify_results(args.workload, lo, hi, sample, qv_dev[st], qi_s, res[0][st], res[1][st], k, dev, world, dist)
     tile_first = None
     if world == 1 and not args.no_verify:
         n_s = min(8, n_q)
