@@ -527,15 +527,16 @@ def main():
                                        'K1t walks only the matching (query, passage, slice) triples, so > 1 is possible'}
         if tw:
             roof['traffic'] = tw.get('dram_bytes_per_launch')
-            if tw.get('dram_bytes_per_launch') and tw.get('launch_kind'):
-                roof['traffic_note'] = tw['launch_kind']
-            for key in ('issue_active_pct', 'lsu_wavefront_pct', 'tensor_pipe_pct', 'dram_pct', 'source'):
-                if key in tw:
-                    roof.setdefault('ncu', {})[key] = tw[key]
-            if tw.get('dram_bytes_per_step_estimate'):
-                phys = tw['dram_bytes_per_step_estimate'] * args.steps / scan_s / 1e9 if scan_s > 0 else 0.0
+            roof['traffic_note'] = '%s over %d rows x %d queries in flight (ncu --set full, %s)' % (
+                tw.get('launch_kind', ''), tw.get('rows_per_launch', 0), tw.get('queries_in_flight', 0), tw.get('source', ''))
+            roof['ncu'] = {key: tw[key] for key in ('issue_active_pct', 'lsu_shared_wavefront_pct', 'tensor_pipe_pct', 'dram_pct',
+                                                    'pred_on_threads_per_inst', 'dominant') if key in tw}
+            if tw.get('dram_bytes_per_launch') and tw.get('rows_per_launch'):
+                batches = -(-n_q // tw.get('queries_in_flight', 256))
+                per_step = tw['dram_bytes_per_launch'] / tw['rows_per_launch'] * (hi - lo) * batches
+                phys = per_step * args.steps / scan_s / 1e9 if scan_s > 0 else 0.0
                 roof['physical_dram'] = {'achieved': phys, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': phys / peaks['hbm_gbs'],
-                                         'what': 'ncu dram__bytes per launch x launches per step / scan time'}
+                                         'what': 'ncu dram__bytes per sub-chunk launch / rows per launch x rows x query batches / scan time'}
         else:
             roof['traffic'] = None
         roof.update({'peak_source': peak_src, 'kernel': kernel_names.get(variant, '?'), 'queries_per_pass': stats[0]['query_block'],

@@ -313,11 +313,97 @@ struct DenseTsArgs {
     int n_stages;
     int n_qgroups;                     // 128-query groups in flight
     int n_queries;                     // valid queries in flight (slots)
-    int mode;                          // 0 = filter + append, 1 = write scratch
-    float* scratch;                    // [row - scratch_row0][scratch_slots]  (mode 1)
+    int mode;                          // 0 = filter + append, 1 = write scratch, 2 = scratch += scores, 3 = (scores + scratch) -> filter + append
+    float* scratch;                    // [row - scratch_row0][scratch_slots]  (modes 1-3)
     long long scratch_slots;
     float* tau; uint32_t* cnt; float* cand_score; int32_t* cand_row; int cap;
 };
+
+// ---- epilogue bodies shared by the cta_group::1 and cta_group::2 kernels: thread = one query, v = its 128 passage scores ----
+// v += scratch (modes 2 and 3: partial sums of an earlier column pass, written by mode 1 / 2)
+__device__ __forceinline__ void dense_ts_add_scratch(const DenseTsArgs& a, uint32_t (&v)[kTS_N / 32][32], int slot, long long row0) {
+    if ((long long)slot < a.scratch_slots) {
+        const float* src = a.scratch + (size_t)(row0 - a.scratch_row0) * a.scratch_slots + slot;
+#pragma unroll
+        for (int c = 0; c < kTS_N; ++c) {
+            const long long row = row0 + c;
+            if (row >= a.row_begin && row < a.row_end)
+                v[c >> 5][c & 31] = __float_as_uint(__uint_as_float(v[c >> 5][c & 31]) + src[(size_t)c * a.scratch_slots]);
+        }
+    }
+}
+
+__device__ __forceinline__ void dense_ts_store_scratch(const DenseTsArgs& a, const uint32_t (&v)[kTS_N / 32][32], int slot, long long row0) {
+    // scratch[row][slot]: for a fixed passage the 32 lanes of a warp write 32 consecutive slots (one 128-byte line)
+    if ((long long)slot < a.scratch_slots) {
+        float* dst = a.scratch + (size_t)(row0 - a.scratch_row0) * a.scratch_slots + slot;
+        if (a.scratch_slots == kMaxInflight && row0 >= a.row_begin && row0 + kTS_N <= a.row_end) {
+            // whole tile in range, compile-time row pitch: one store instruction per passage
+#pragma unroll
+            for (int c = 0; c < kTS_N; ++c) dst[(size_t)c * kMaxInflight] = __uint_as_float(v[c >> 5][c & 31]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < kTS_N; ++c) {
+                const long long row = row0 + c;
+                if (row >= a.row_begin && row < a.row_end)
+                    dst[(size_t)c * a.scratch_slots] = __uint_as_float(v[c >> 5][c & 31]);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void dense_ts_filter_append(const DenseTsArgs& a, uint32_t (&v)[kTS_N / 32][32], int slot, long long row0, float tau_q) {
+    // dense-only index: strict admission threshold.  Lanes without a valid query carry tau = +inf and never pass.  Rows pass
+    // rarely once tau is set (about one (query, row) pair per warp and tile in the last chunk), so the work is kept O(passes)
+    // and the code small: the lane's 128 scores are reduced to 16 group maxima and their maximum; only a lane that can pass
+    // walks its groups, and a group that can pass counts its passing rows, reserves their slots with ONE atomicAdd and writes
+    // them (one round trip per flagged group instead of one per appended row -- in the first chunk every row passes).
+    // Measured forms (last chunk of a batch, 7.8 M rows x 256 queries, micro-benchmark pace 3.3 ms): one atomic per row 5.6 ms;
+    // flat count / write passes over all 128 registers 8.3 ms (3,500 dependent instructions per warp and tile: the epilogue,
+    // not the tensor pipe, was the bottleneck); whole-warp scan of one flagged lane at a time through shared memory 4.65 ms but
+    // 2.3x slower in the middle chunks where many lanes pass; this form 4.9 ms and the fastest over a whole batch.
+    if (!(row0 >= a.row_begin && row0 + kTS_N <= a.row_end)) {            // edge tile: rows outside the launch range never pass
+#pragma unroll
+        for (int c = 0; c < kTS_N; ++c) {
+            const long long row = row0 + c;
+            if (row < a.row_begin || row >= a.row_end) v[c >> 5][c & 31] = 0xFF800000u;      // -inf
+        }
+    }
+    float gm[kTS_N / 8];
+#pragma unroll
+    for (int j = 0; j < kTS_N / 8; ++j) {
+        float m = __uint_as_float(v[j >> 2][(j & 3) * 8]);
+#pragma unroll
+        for (int c = 1; c < 8; ++c) m = fmaxf(m, __uint_as_float(v[j >> 2][(j & 3) * 8 + c]));
+        gm[j] = m;
+    }
+    float m = gm[0];
+#pragma unroll
+    for (int j = 1; j < kTS_N / 8; ++j) m = fmaxf(m, gm[j]);
+    if (!(m > tau_q)) return;                                              // the common exit of (almost) every lane
+    uint32_t* cnt = a.cnt + slot;
+    float* cs = a.cand_score + (size_t)slot * a.cap;
+    int32_t* cr = a.cand_row + (size_t)slot * a.cap;
+    const int32_t r0 = (int32_t)row0;
+    const uint32_t cap = (uint32_t)a.cap;
+#pragma unroll
+    for (int j = 0; j < kTS_N / 8; ++j) {
+        if (gm[j] > tau_q) {
+            uint32_t n = 0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) n += (__uint_as_float(v[j >> 2][(j & 3) * 8 + c]) > tau_q) ? 1u : 0u;
+            uint32_t pos = atomicAdd(cnt, n);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float sc = __uint_as_float(v[j >> 2][(j & 3) * 8 + c]);
+                if (sc > tau_q) {
+                    if (pos < cap) { cs[pos] = sc + 0.0f; cr[pos] = r0 + 8 * j + c; }
+                    ++pos;
+                }
+            }
+        }
+    }
+}
 
 __global__ void __launch_bounds__(kTS_Threads, 1)
 dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_q, const DenseTsArgs a) {
@@ -465,7 +551,7 @@ dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
         const int qi = quarter * 32 + lane;
         const int slot = qg * kTS_M + qi;
         const bool q_ok = slot < a.n_queries;
-        const float tau_q = (q_ok && a.mode == 0) ? a.tau[slot] : INFINITY;
+        const float tau_q = (q_ok && (a.mode == 0 || a.mode == 3)) ? a.tau[slot] : INFINITY;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a_cols;
         int i = 0;
         for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q, ++i) {
@@ -481,50 +567,10 @@ dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
             if (lane == 0) mbar_arrive(&tempty_bar[0]);                  // D is free again: the next tile's MMAs may start
             if (threadIdx.x == 64) K2_TRACE(6, i);
             const long long row0 = a.tile_row0 + (long long)t * kTS_N;
+            if (a.mode >= 2) dense_ts_add_scratch(a, v, slot, row0);
             if (K2_DBG() & 4) {
-            } else if (a.mode == 1) {
-                // scratch[row][slot]: for a fixed passage the 32 lanes of a warp write 32 consecutive slots (one 128-byte line)
-                if ((long long)slot < a.scratch_slots) {
-                    float* dst = a.scratch + (size_t)(row0 - a.scratch_row0) * a.scratch_slots + slot;
-                    if (a.scratch_slots == kMaxInflight && row0 >= a.row_begin && row0 + kTS_N <= a.row_end) {
-                        // whole tile in range, compile-time row pitch: one store instruction per passage
-#pragma unroll
-                        for (int c = 0; c < kTS_N; ++c) dst[(size_t)c * kMaxInflight] = __uint_as_float(v[c >> 5][c & 31]);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < kTS_N; ++c) {
-                            const long long row = row0 + c;
-                            if (row >= a.row_begin && row < a.row_end)
-                                dst[(size_t)c * a.scratch_slots] = __uint_as_float(v[c >> 5][c & 31]);
-                        }
-                    }
-                }
-            } else if (q_ok) {
-                // dense-only index: strict admission threshold.  Rows pass rarely once tau is set (~0.1 %), so each group of 8
-                // passages is first reduced to its maximum and scanned only when something can pass; small groups keep the
-                // probability that ANY lane of the warp takes the scan low.
-                const bool full = row0 >= a.row_begin && row0 + kTS_N <= a.row_end;
-#pragma unroll
-                for (int j = 0; j < kTS_N / 8; ++j) {
-                    float m = __uint_as_float(v[j >> 2][(j & 3) * 8]);
-#pragma unroll
-                    for (int c = 1; c < 8; ++c) m = fmaxf(m, __uint_as_float(v[j >> 2][(j & 3) * 8 + c]));
-                    if (m > tau_q) {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const long long row = row0 + 8 * j + c;
-                            const float sc = __uint_as_float(v[j >> 2][(j & 3) * 8 + c]) + 0.0f;
-                            if (sc > tau_q && (full || (row >= a.row_begin && row < a.row_end))) {
-                                const uint32_t pos = atomicAdd(a.cnt + slot, 1u);
-                                if (pos < (uint32_t)a.cap) {
-                                    a.cand_score[(size_t)slot * a.cap + pos] = sc;
-                                    a.cand_row[(size_t)slot * a.cap + pos] = (int32_t)row;
-                                }
-                            }
-                        }
-                    }
-                }
-            }
+            } else if (a.mode == 1 || a.mode == 2) dense_ts_store_scratch(a, v, slot, row0);
+            else dense_ts_filter_append(a, v, slot, row0, tau_q);
         }
     }
     if (threadIdx.x == 64) K2_TRACE(0, 3);
@@ -533,6 +579,199 @@ dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
     else __syncthreads();
     if (threadIdx.x == 0) K2_TRACE(0, 4);
     if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- TS2 variant: a CTA pair works as one M = 256 tensor-core unit (cta_group::2) ----------------------------------------
+// The two 128-query groups of a batch run as a cluster of two CTAs on the two SMs of a TPC.  Each CTA keeps ITS 128 queries
+// in ITS tensor memory (the A operand, M = 256 over the pair) and stages only HALF of every corpus tile (64 of the 128
+// passages of a k-block, 8 KiB) in its shared memory; one thread of the leader CTA (cluster rank 0) issues
+// tcgen05.mma.cta_group::2 M256 x N128 x K16, for which the hardware reads each CTA's half of the B operand from that CTA's
+// shared memory and writes D[128 queries x 128 passages] into each CTA's own TMEM.  Against the cta_group::1 kernel this
+// halves the shared-memory traffic per SM (TMA fill + operand read) and the L2 -> SM traffic per tensor instruction, which
+// is what holds the single-CTA kernel at ~150 cycles per instruction against the 64-cycle floor.
+//   full[s]   lives in the leader: both CTAs' TMA loads complete_tx on it (the peer through the .cta_group::2 form with the
+//             leader's barrier address), the leader's producer posts the expect_tx for both halves;
+//   empty[s]  in each CTA, signalled by the leader's tcgen05.commit multicast once the MMAs have read the stage;
+//   tfull     in each CTA, same multicast commit after the last k-block of a tile;
+//   tempty    in the leader, 8 arrivals: the four epilogue warps of both CTAs (the peer's arrive remotely).
+constexpr int kTS2_HalfN = kTS_N / 2;                       // passages staged per CTA and k-block
+constexpr int kTS2_StageBytes = kTS2_HalfN * kDT_KB * 2;    // 8 KiB
+constexpr int kTS2_MaxStages = 24;                          // 192 KiB ring = two corpus tiles deep per CTA (also stages the query operand)
+
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA 2-D load into THIS CTA's shared memory whose completion is counted on a barrier of the CTA pair's leader
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* tmap, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts_2sm(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+__global__ void __launch_bounds__(kTS_Threads, 1)
+dense_tile_ts2_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_q, const DenseTsArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[kTS2_MaxStages];      // used in the leader only
+    __shared__ __align__(8) uint64_t empty_bar[kTS2_MaxStages];
+    __shared__ __align__(8) uint64_t tfull_bar;
+    __shared__ __align__(8) uint64_t tempty_bar;                     // used in the leader only
+    __shared__ __align__(8) uint64_t q_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();
+    const bool leader = crank == 0;
+    const int qg = (int)crank;                                       // query group of this CTA (a.n_qgroups == 2)
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const uint32_t a_cols = (uint32_t)a.n_kblocks * 32u;
+    uint8_t* ring = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tfull_bar, 1);
+        mbar_init(&tempty_bar, 8);
+        mbar_init(&q_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc_2sm(&tmem_base_smem, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    // ---- query operand -> TMEM (as in the cta_group::1 kernel; every CTA loads its own group through the idle ring) ----
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_arrive_expect_tx(&q_bar, (uint32_t)a.n_kblocks * (uint32_t)(kTS_M * kDT_KB * 2));
+            for (int kb = 0; kb < a.n_kblocks; ++kb)
+                tma_load_2d(ring + (size_t)kb * (kTS_M * kDT_KB * 2), &tmap_q, &q_bar, kb * kDT_KB, qg * kTS_M);
+        }
+        __syncwarp();
+    } else if (warp >= 2) {
+        const int quarter = warp & 3;
+        const int qi = quarter * 32 + lane;
+        mbar_wait(&q_bar, 0);
+        for (int kb = 0; kb < a.n_kblocks; ++kb) {
+            const uint8_t* row = ring + (size_t)kb * (kTS_M * kDT_KB * 2) + (size_t)qi * 128;
+            uint32_t r[32];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                const uint4 x = *(const uint4*)(row + ((v ^ (qi & 7)) << 4));
+                r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+            }
+            tmem_st_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)kb * 32u, r);
+        }
+        tmem_st_wait();
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    cluster_sync_all();                          // barriers initialised and both query operands in place before any cross-CTA signal
+    tc_fence_after();
+
+    if (warp == 0) {
+        // ===== TMA producer: this CTA's half (64 passages) of every corpus stage =====
+        int s = 0; uint32_t ph = 0;
+        const uint32_t full0 = mapa_shared(smem_u32(&full_bar[0]), 0u);          // the leader's full barriers
+        for (int t = pair; t < a.n_tiles; t += n_pairs) {
+            const int row0 = (int)(a.tile_row0 + (long long)t * kTS_N);
+            for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                if (elect_one()) {
+                    const int tp = t + kTS_Prefetch * n_pairs;
+                    if (leader && tp < a.n_tiles) {
+                        const int rowp = row0 + kTS_Prefetch * n_pairs * kTS_N;
+                        if (a.blocked) tma_prefetch_l2_2d(&tmap_c, 0, (rowp / kTS_N * a.n_kblocks + kb) * kTS_N);
+                        else tma_prefetch_l2_2d(&tmap_c, kb * kDT_KB, rowp);
+                    }
+                    if (leader) mbar_arrive_expect_tx(&full_bar[s], 2u * kTS2_StageBytes);
+                    const int half = (int)crank * kTS2_HalfN;
+                    uint8_t* dst = ring + (size_t)s * kTS2_StageBytes;
+                    const uint32_t bar = full0 + (uint32_t)s * 8u;
+                    if (a.blocked) tma_load_2d_2sm(dst, &tmap_c, bar, 0, (row0 / kTS_N * a.n_kblocks + kb) * kTS_N + half);
+                    else tma_load_2d_2sm(dst, &tmap_c, bar, kb * kDT_KB, row0 + half);
+                }
+                __syncwarp();
+                if (++s == a.n_stages) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: the leader CTA only =====
+        if (leader) {
+            constexpr uint32_t idesc = umma_idesc_f16(2 * kTS_M, kTS_N);
+            const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);
+            const uint32_t d_tmem = tmem_u + a_cols;
+            int s = 0; uint32_t ph = 0;
+            int i = 0;
+            for (int t = pair; t < a.n_tiles; t += n_pairs, ++i) {
+                mbar_wait(&tempty_bar, ((uint32_t)i & 1u) ^ 1u);
+                tc_fence_after();
+                for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t b_addr = smem_u32(ring + (size_t)s * kTS2_StageBytes);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < kDT_KB / 16; ++k)
+                            umma_f16_ts_2sm(d_tmem, tmem_u + (uint32_t)kb * 32u + (uint32_t)k * 8u, umma_smem_desc(b_addr + k * 32), idesc,
+                                            (kb | k) != 0 ? 1u : 0u);
+                        umma_commit_2sm(&empty_bar[s], 3);                 // both CTAs may refill the stage
+                    }
+                    __syncwarp();
+                    if (++s == a.n_stages) { s = 0; ph ^= 1u; }
+                }
+                if (elect_one()) umma_commit_2sm(&tfull_bar, 3);           // accumulator tile complete in both CTAs
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== epilogue warps (both CTAs): thread = one query of this CTA's group, registers = 128 passages =====
+        const int quarter = warp & 3;
+        const int qi = quarter * 32 + lane;
+        const int slot = qg * kTS_M + qi;
+        const bool q_ok = slot < a.n_queries;
+        const float tau_q = (q_ok && (a.mode == 0 || a.mode == 3)) ? a.tau[slot] : INFINITY;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a_cols;
+        const uint32_t tempty_leader = mapa_shared(smem_u32(&tempty_bar), 0u);
+        int i = 0;
+        for (int t = pair; t < a.n_tiles; t += n_pairs, ++i) {
+            mbar_wait(&tfull_bar, (uint32_t)i & 1u);
+            tc_fence_after();
+            uint32_t v[kTS_N / 32][32];
+#pragma unroll
+            for (int j = 0; j < kTS_N / 32; ++j) tmem_ld_32x32(taddr + 32u * j, v[j]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_leader);           // D of this CTA is free again
+            const long long row0 = a.tile_row0 + (long long)t * kTS_N;
+            if (a.mode >= 2) dense_ts_add_scratch(a, v, slot, row0);
+            if (a.mode == 1 || a.mode == 2) dense_ts_store_scratch(a, v, slot, row0);
+            else dense_ts_filter_append(a, v, slot, row0, tau_q);
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();                          // no CTA of the pair exits (or frees TMEM) while the other may still signal it
+    if (warp == 1) tmem_dealloc_2sm(tmem_base, 512);
 }
 
 // ---- host side --------------------------------------------------------------------------------------
@@ -585,22 +824,26 @@ bool dense_tile_ts_supported(const Geometry& g) {
     return g.C_pad > 0 && (g.C_pad + kDT_KB - 1) / kDT_KB * 32 <= kTS_MaxACols;
 }
 
-static int launch_dense_tile_ts(const dhr_index* h, const void* q_dns16, int n_queries, long long tile_row0, long long row_begin,
-                                long long row_end, int mode, float* scratch, long long scratch_slots, const TopkState& t, int cap,
-                                cudaStream_t st) {
-    const Geometry& g = h->g;
+// One column pass of the TS kernels: scores[q][row] (+)= sum over `cols` fp16 columns of a corpus block and the matching
+// query columns.  The corpus block is either the K-blocked copy of the dense block (`blocked`) or any row-major fp16 array
+// with row pitch `c_pitch` (the dense block itself, or a column range of the lexical values for the unmasked --IP stage).
+int launch_dense_pass(const dhr_index* h, const __half* blocked, const __half* rowmajor, int c_pitch, int cols, const void* q16,
+                      int q_pitch, int n_queries, long long tile_row0, long long row_begin, long long row_end, int mode, float* scratch,
+                      long long scratch_slots, const TopkState& t, int cap, cudaStream_t st) {
+    if (row_end <= row_begin || n_queries <= 0) return DHR_OK;
+    if (cols <= 0 || (cols + kDT_KB - 1) / kDT_KB * 32 > kTS_MaxACols) return DHR_ERR_UNSUPPORTED;
     CUtensorMap tmap_c, tmap_q;
-    const int nkb = (g.C_pad + kDT_KB - 1) / kDT_KB;
+    const int nkb = (cols + kDT_KB - 1) / kDT_KB;
     // corpus operand (built below): the K-blocked copy viewed as [blocks * 128 rows][64 cols] (one box = one contiguous piece
-    // of HBM), or the row-major block when the copy could not be allocated
-    DHR_TRY(make_tmap_f16(&tmap_q, q_dns16, (uint64_t)n_queries, (uint64_t)g.C_pad, (uint64_t)g.C_pad, kTS_M));
+    // of HBM), or a row-major block
+    DHR_TRY(make_tmap_f16(&tmap_q, q16, (uint64_t)n_queries, (uint64_t)cols, (uint64_t)q_pitch, kTS_M));
     DenseTsArgs a{};
     a.row_begin = row_begin; a.row_end = row_end;
     a.tile_row0 = row_begin / kTS_N * kTS_N;                     // absolute 128-row tiles (the K-blocked copy is tiled from row 0)
-    a.blocked = h->dnst != nullptr;
+    a.blocked = blocked != nullptr;
     a.scratch_row0 = tile_row0;
     a.n_tiles = (int)((row_end - a.tile_row0 + kTS_N - 1) / kTS_N);
-    a.n_kblocks = (g.C_pad + kDT_KB - 1) / kDT_KB;
+    a.n_kblocks = nkb;
     a.n_stages = kTS_MaxStages;
     a.n_qgroups = (n_queries + kTS_M - 1) / kTS_M;
     a.n_queries = n_queries;
@@ -609,6 +852,7 @@ static int launch_dense_tile_ts(const dhr_index* h, const void* q_dns16, int n_q
     a.tau = t.tau; a.cnt = t.cnt; a.cand_score = t.cand_score; a.cand_row = t.cand_row; a.cap = cap;
     const size_t smem = (size_t)a.n_stages * kTS_BBytes + 1024;
     DHR_CUDA(cudaFuncSetAttribute(dense_tile_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DHR_CUDA(cudaFuncSetAttribute(dense_tile_ts2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTS2_MaxStages * kTS2_StageBytes + 1024));
     int per_q = h->num_sms / a.n_qgroups;
     if (per_q < 1) per_q = 1;
     if (per_q > a.n_tiles) per_q = a.n_tiles;
@@ -616,25 +860,30 @@ static int launch_dense_tile_ts(const dhr_index* h, const void* q_dns16, int n_q
     // free up, and a cluster needs both SMs of a pair at once (measured 1.5 % slower), so scratch mode stays unicast unless
     // asked for (dense_multicast = 2).
     a.cluster = (a.n_qgroups == 2 && ((h->opt_dense_multicast == 1 && mode == 0) || h->opt_dense_multicast == 2)) ? 1 : 0;
+    // cta_group::2 form (dense_variant 2): the two query groups of a batch as one CTA pair; needs exactly two groups in flight
+    const bool pair_mma = h->opt_dense_variant == 2 && a.n_qgroups == 2 && h->num_sms >= 2;
+    if (pair_mma) { a.cluster = 1; a.n_stages = kTS2_MaxStages; }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(per_q * a.n_qgroups));
     cfg.blockDim = dim3(kTS_Threads);
-    cfg.dynamicSmemBytes = smem;
+    cfg.dynamicSmemBytes = pair_mma ? (size_t)kTS2_MaxStages * kTS2_StageBytes + 1024 : smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     if (a.cluster) {
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        static int max_clusters = -1;                                  // pairs the device can keep resident (same for every launch)
-        if (max_clusters < 0) {
+        // pairs the device can keep resident: probed per launch configuration and device (cheap host-side query)
+        int max_clusters = 0;
+        {
             cudaLaunchConfig_t probe = cfg;
             probe.gridDim = dim3((unsigned)(h->num_sms / 2 * 2));
-            int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, dense_tile_ts_kernel, &probe) != cudaSuccess || n < 1) { cudaGetLastError(); n = 0; }
-            max_clusters = n;
+            cudaError_t pe = pair_mma ? cudaOccupancyMaxActiveClusters(&max_clusters, dense_tile_ts2_kernel, &probe)
+                                      : cudaOccupancyMaxActiveClusters(&max_clusters, dense_tile_ts_kernel, &probe);
+            if (pe != cudaSuccess || max_clusters < 1) { cudaGetLastError(); max_clusters = 0; }
         }
         if (max_clusters < 1) {                                        // no cluster launch on this device / partition: unicast
+            if (pair_mma) return DHR_ERR_UNSUPPORTED;
             a.cluster = 0;
             cfg.attrs = nullptr; cfg.numAttrs = 0;
         } else if (per_q > max_clusters) {
@@ -642,12 +891,16 @@ static int launch_dense_tile_ts(const dhr_index* h, const void* q_dns16, int n_q
             cfg.gridDim = dim3((unsigned)(per_q * 2));
         }
     }
-    // with multicast the corpus map delivers half a stage (64 passages) per load
+    // with multicast / the CTA-pair form the corpus map delivers half a stage (64 passages) per load
     const int box_rows = a.cluster ? kTS_N / 2 : kTS_N;
-    if (h->dnst)
-        DHR_TRY(make_tmap_f16(&tmap_c, h->dnst, (uint64_t)round_up(h->n_rows, kTS_N) * nkb, (uint64_t)kDT_KB, (uint64_t)kDT_KB, box_rows));
+    if (blocked)
+        DHR_TRY(make_tmap_f16(&tmap_c, blocked, (uint64_t)round_up(h->n_rows, kTS_N) * nkb, (uint64_t)kDT_KB, (uint64_t)kDT_KB, box_rows));
     else
-        DHR_TRY(make_tmap_f16(&tmap_c, h->dns, (uint64_t)h->n_rows, (uint64_t)g.C_pad, (uint64_t)g.C_pad, box_rows));
+        DHR_TRY(make_tmap_f16(&tmap_c, rowmajor, (uint64_t)h->n_rows, (uint64_t)cols, (uint64_t)c_pitch, box_rows));
+    if (pair_mma) {
+        DHR_CUDA(cudaLaunchKernelEx(&cfg, dense_tile_ts2_kernel, tmap_c, tmap_q, a));
+        return DHR_OK;
+    }
     DHR_CUDA(cudaLaunchKernelEx(&cfg, dense_tile_ts_kernel, tmap_c, tmap_q, a));
     return DHR_OK;
 }
@@ -661,8 +914,9 @@ int launch_dense_tile(const dhr_index* h, const void* q_dns16, int n_queries, lo
     int stages = 0;
     if (!dense_tile_supported(g, &stages)) return DHR_ERR_UNSUPPORTED;
     if (row_end <= row_begin || n_queries <= 0) return DHR_OK;
-    if (h->opt_dense_variant == 1 && dense_tile_ts_supported(g))
-        return launch_dense_tile_ts(h, q_dns16, n_queries, tile_row0, row_begin, row_end, mode, scratch, scratch_slots, t, cap, st);
+    if (h->opt_dense_variant >= 1 && dense_tile_ts_supported(g))
+        return launch_dense_pass(h, h->dnst, h->dns, g.C_pad, g.C_pad, q_dns16, g.C_pad, n_queries, tile_row0, row_begin, row_end, mode, scratch,
+                                 scratch_slots, t, cap, st);
     CUtensorMap tmap_a, tmap_b;
     DHR_TRY(make_tmap_f16(&tmap_a, h->dns, (uint64_t)h->n_rows, (uint64_t)g.C_pad, (uint64_t)g.C_pad, kDT_M));
     DHR_TRY(make_tmap_f16(&tmap_b, q_dns16, (uint64_t)n_queries, (uint64_t)g.C_pad, (uint64_t)g.C_pad, kDT_N));

@@ -547,7 +547,7 @@ int dhr_index_set_option(dhr_index* h, const char* name, int64_t value) {
     if (!strcmp(name, "tile_mode")) { h->opt_tile_mode = value != 0; return DHR_OK; }
     if (!strcmp(name, "dense_multicast")) { if (value < 0 || value > 2) return DHR_ERR_INVALID; h->opt_dense_multicast = (int)value; return DHR_OK; }
     if (!strcmp(name, "overlap")) { h->opt_overlap = value != 0; return DHR_OK; }
-    if (!strcmp(name, "dense_variant")) { if (value < 0 || value > 1) return DHR_ERR_INVALID; h->opt_dense_variant = (int)value; return DHR_OK; }
+    if (!strcmp(name, "dense_variant")) { if (value < 0 || value > 2) return DHR_ERR_INVALID; h->opt_dense_variant = (int)value; return DHR_OK; }
     if (!strcmp(name, "profile")) { h->opt_profile = value != 0; return DHR_OK; }
     return DHR_ERR_INVALID;
 }

@@ -154,6 +154,12 @@ int launch_dense_tile(const dhr_index* h, const void* q_dns16, int n_queries, lo
                       long long row_end, int mode, float* scratch, long long scratch_slots, const TopkState& t, int cap,
                       cudaStream_t st);
 
+// one column pass of the tensor-core kernel over any fp16 column block (mode: 0 filter, 1 scratch =, 2 scratch +=, 3 (+ scratch) -> filter)
+int launch_dense_pass(const dhr_index* h, const __half* blocked, const __half* rowmajor, int c_pitch, int cols, const void* q16,
+                      int q_pitch, int n_queries, long long tile_row0, long long row_begin, long long row_end, int mode, float* scratch,
+                      long long scratch_slots, const TopkState& t, int cap, cudaStream_t st);
+constexpr int kDensePassMaxCols = 768;   // query operand of one pass must fit 384 TMEM columns
+
 int ensure_device_buffer(void** p, size_t* cur, size_t need);
 // row-major arrays (lexv / lexi / dns) serve the row scan K1, the rerank kernel K4 and the overflow fallback; they can be
 // dropped once the tiled copies exist (option "rowmajor" = 0) and are rebuilt from the tiled copies on first use

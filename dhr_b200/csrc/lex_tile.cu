@@ -300,6 +300,29 @@ __device__ __forceinline__ void sts_acc_pred(uint32_t addr, float v, uint32_t ac
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.f32 [%0], %1;\n\t}" :: "r"(addr), "f"(v), "r"(act) : "memory");
 }
 
+// ---- the same with the predicate `i < n` formed inside the asm block (no materialised 0/1 flag: ptxas merges the compares) ----
+template <int EW>
+__device__ __forceinline__ void lds_entry_lt(uint32_t addr, uint32_t i, uint32_t n, uint32_t (&ew)[EW]) {
+    static_assert(EW == 2 || EW == 4 || EW == 6, "entry words");
+    if constexpr (EW == 2)
+        asm("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %3, %4;\n\t@q ld.shared.v2.u32 {%0, %1}, [%2];\n\t}"
+            : "=r"(ew[0]), "=r"(ew[1]) : "r"(addr), "r"(i), "r"(n));
+    else if constexpr (EW == 4)
+        asm("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %5, %6;\n\t@q ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+            : "=r"(ew[0]), "=r"(ew[1]), "=r"(ew[2]), "=r"(ew[3]) : "r"(addr), "r"(i), "r"(n));
+    else
+        asm("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %7, %8;\n\t@q ld.shared.v2.u32 {%0, %1}, [%6];\n\t@q ld.shared.v2.u32 {%2, %3}, [%6+8];\n\t"
+            "@q ld.shared.v2.u32 {%4, %5}, [%6+16];\n\t}"
+            : "=r"(ew[0]), "=r"(ew[1]), "=r"(ew[2]), "=r"(ew[3]), "=r"(ew[4]), "=r"(ew[5]) : "r"(addr), "r"(i), "r"(n));
+}
+__device__ __forceinline__ float lds_acc_lt(uint32_t addr, uint32_t i, uint32_t n) {
+    float v;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %2, %3;\n\t@q ld.shared.f32 %0, [%1];\n\t}" : "=f"(v) : "r"(addr), "r"(i), "r"(n) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_acc_lt(uint32_t addr, float v, uint32_t i, uint32_t n) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %2, %3;\n\t@q st.shared.f32 [%0], %1;\n\t}" :: "r"(addr), "f"(v), "r"(i), "r"(n) : "memory");
+}
 template <int G>
 struct LexLevel {                       // operands of one match level of one thread
     uint32_t ew[lt_entry_words(G)];

@@ -201,7 +201,9 @@ static std::vector<long long> chunk_schedule(long long n_rows, int k, int cap, b
         growth = std::min(gmax, std::max(1.25, pow(ratio, 1.0 / std::max(1.0, n)) * 1.0001));
     }
     while (b.back() < n_rows) {
-        long long next = (long long)ceil((double)b.back() * growth) / align * align;
+        long long next = (long long)ceil((double)b.back() * growth);
+        if (next >= n_rows || (double)(n_rows - next) < 0.04 * (double)next) { b.push_back(n_rows); break; }   // no sliver chunk behind an aligned-down boundary
+        next = next / align * align;
         if (quantum > 0 && next - b.back() >= quantum) {                 // whole sub-launches: nearest multiple, never beyond gmax
             const long long len = next - b.back();
             long long q = (len + quantum / 2) / quantum * quantum;
@@ -502,6 +504,55 @@ static int validate_query_args(const dhr_index* h, int n_queries, int q_val_dtyp
     return DHR_OK;
 }
 
+// Unmasked (--IP, gip_retrieval.py:139) first stage of an index with a lexical part: a plain [Q, W] x [W, N] inner product over
+// ALL columns, i.e. a GEMM -> the tensor-core kernel K2, one column pass per <= 768 columns: the lexical value columns from the
+// row-major array (TMA 2-D over a column window), then the dense block from its K-blocked copy; partial sums travel between
+// the passes of a sub-chunk through the L2-resident scratch, the last pass adds them and applies the admission filter.
+static int run_batch_unmasked_tile(dhr_index* h, const QuerySet& qs, int base, int nq, int k, SelectOut so, cudaStream_t st) {
+    const Geometry& g = h->g;
+    TopkState t = h->topk;
+    so.base = base;
+    const std::vector<long long> bounds = chunk_schedule(h->n_rows, k, kCandCap, false, kDenseTileRows, kTileSubRows);
+    const size_t n_chunks = bounds.size() - 1;
+    struct Pass { const __half* blocked; const __half* rowmajor; int pitch, cols; const void* q; int q_pitch; };
+    std::vector<Pass> passes;
+    for (int c0 = 0; c0 < g.D_pad; c0 += kDensePassMaxCols)
+        passes.push_back({nullptr, h->lexv + c0, g.D_pad, std::min(kDensePassMaxCols, g.D_pad - c0),
+                          (const __half*)(qs.lex + (size_t)base * qs.lex_stride) + c0, g.D_pad});
+    if (g.C_pad > 0)
+        passes.push_back({h->dnst, h->dns, g.C_pad, g.C_pad, qs.dns + (size_t)base * qs.dns_stride, g.C_pad});
+    const int np = (int)passes.size();
+    for (size_t c = 0; c < n_chunks; ++c) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+        if (h->opt_profile) { e0 = h->events.get(); e1 = h->events.get(); e2 = h->events.get(); cudaEventRecord(e0, st); }
+        for (long long r0 = bounds[c]; r0 < bounds[c + 1]; r0 += kTileSubRows) {
+            const long long r1 = std::min(bounds[c + 1], r0 + kTileSubRows);
+            for (int p = 0; p < np; ++p) {
+                const int mode = np == 1 ? 0 : (p == 0 ? 1 : (p == np - 1 ? 3 : 2));
+                DHR_TRY(launch_dense_pass(h, passes[p].blocked, passes[p].rowmajor, passes[p].pitch, passes[p].cols, passes[p].q,
+                                          passes[p].q_pitch, nq, r0, r0, r1, mode, h->scratch, kMaxInflight, t, kCandCap, st));
+                h->stats.n_kernel_launches++;
+                h->stats.n_scan_launches++;
+                h->stats.alg_bytes += (double)(r1 - r0) * ((nq + 127) / 128) * (double)passes[p].cols * 2.0;
+            }
+        }
+        if (h->opt_profile) cudaEventRecord(e1, st);
+        DHR_TRY(launch_select(t, nq, k, kCandCap, c + 1 == n_chunks, so, st));
+        if (h->opt_profile) cudaEventRecord(e2, st);
+        h->stats.n_select_launches++;
+        h->stats.n_kernel_launches++;
+        h->stats.corpus_passes += (double)(bounds[c + 1] - bounds[c]) * ((nq + 127) / 128) / (double)std::max<int64_t>(1, h->n_rows);
+        h->stats.dense_flops += 2.0 * (double)(bounds[c + 1] - bounds[c]) * (double)nq * (double)(g.S * g.G + g.C);
+    }
+    if (n_chunks == 0) {
+        DHR_TRY(launch_select(t, nq, k, kCandCap, true, so, st));
+        h->stats.n_select_launches++;
+        h->stats.n_kernel_launches++;
+    }
+    h->stats.scan_variant = 4;
+    return DHR_OK;
+}
+
 // ---- the search proper: shared by dhr_search (synchronous, host or device outputs) and dhr_search_keys (stream-ordered,
 // device-resident packed keys, no host synchronisation on the common path) -------------------------------------------------
 struct SearchRequest {
@@ -583,8 +634,22 @@ static int enqueue_search(dhr_index* h, const SearchRequest& r, SelectOut so, bo
         h->stats.n_prep_launches++; h->stats.n_kernel_launches++;
         slots = kMaxInflight; qb = kLexTileQueries; groups = kMaxInflight / kLexTileQueries;
     }
+    // unmasked search of an index with a lexical part (--IP first stage): all columns through K2
+    const bool tile_unmasked = h->opt_tile_mode && g.S > 0 && !r.masked && !qs.f32 && h->opt_dense_variant >= 1 &&
+                               (g.C_pad == 0 || dense_tile_ts_supported(g));
+    if (tile_unmasked) {
+        DHR_TRY(ensure_rowmajor(h));                                      // the lexical columns are read from the row-major array
+        const size_t sc_need = (size_t)kMaxInflight * kTileSubRows * sizeof(float);
+        if (sc_need > h->scratch_bytes) {
+            if (h->scratch) cudaFree(h->scratch);
+            h->scratch = nullptr; h->scratch_bytes = 0;
+            DHR_CUDA(cudaMalloc(&h->scratch, sc_need));
+            h->scratch_bytes = sc_need;
+        }
+        slots = kMaxInflight; qb = 128; groups = kMaxInflight / 128;
+    }
     if (!tile_dense && !tile_hybrid) DHR_TRY(ensure_rowmajor(h));          // the row scan K1 reads the row-major arrays
-    else if (g.C_pad > 0 && (!h->dnst || h->opt_dense_variant != 1 || !dense_tile_ts_supported(g)))
+    else if (g.C_pad > 0 && (!h->dnst || h->opt_dense_variant < 1 || !dense_tile_ts_supported(g)))
         DHR_TRY(ensure_rowmajor(h));                                      // K2's SS variant streams the row-major dense block
     h->stats.query_block = qb;
     h->stats.query_groups = groups;
@@ -593,6 +658,7 @@ static int enqueue_search(dhr_index* h, const SearchRequest& r, SelectOut so, bo
     for (int base = 0; base < n_queries; base += slots, ++b) {
         const int nq = std::min(slots, n_queries - base);
         if (tile_dense) DHR_TRY(run_batch_dense_tile(h, qs, base, nq, k, so, st));
+        else if (tile_unmasked) DHR_TRY(run_batch_unmasked_tile(h, qs, base, nq, k, so, st));
         else if (tile_hybrid) DHR_TRY(run_batch_hybrid_tile(h, lt, qs, base, nq, k, so, st));
         else DHR_TRY(run_batch(h, qs, base, nq, k, r.masked, false, qb, so, st));
         if (record_batches) {

@@ -24,6 +24,12 @@ CONFIGS = {
     'bm25': dict(S=256, G=3, C=0, idx='uint16', recipe='bm25', R=3466),              # config 3 (literal)
     'bm25_ref': dict(S=768, G=1, C=0, idx='int16', recipe='bm25', R=3466),           # config 3'
     'dense': dict(S=0, G=1, C=768, idx='uint8', recipe='dense', R=1),                # config 4
+    # robustness variant of config 2: slice indices Zipf-distributed over the 39 values (p(r) ~ 1/(r+1)), like the argmax over
+    # vocabulary strides of a real encoder where a few strides win most often -> ~3.5x the matches of the uniform recipe
+    'delade_cls_zipf': dict(S=128, G=6, C=768, idx='uint16', recipe='delade', R=39, zipf=1.0),
+    # kernel-level variants (tools/k1t_bench.py): the lexical part of configs 2 / 2' alone
+    'delade_lex': dict(S=128, G=6, C=0, idx='uint16', recipe='delade', R=39),
+    'delade_ref_lex': dict(S=768, G=1, C=0, idx='uint8', recipe='delade', R=39),
 }
 N_MSMARCO = 8841823
 Q_MSMARCO = 6808
@@ -56,7 +62,11 @@ def _np_segment(cfg, seed, n, queries):
             else:
                 v = rng.random((n, S, G), dtype=np.float32) * 7.5 + 0.5
                 empty = rng.random((n, S)) >= 0.05
-        ii = rng.integers(0, R, size=(n, S))
+        if cfg.get('zipf'):
+            pr = 1.0 / np.arange(1, R + 1, dtype=np.float64) ** cfg['zipf']
+            ii = rng.choice(R, size=(n, S), p=pr / pr.sum())
+        else:
+            ii = rng.integers(0, R, size=(n, S))
         v[empty] = 0
         ii[empty] = 0
         parts.append(v.reshape(n, S * G).astype(np.float16))
@@ -108,7 +118,11 @@ def _torch_segment(torch, cfg, seed, n, queries, device):
             else:
                 v = torch.rand((n, S, G), generator=g, device=device) * 7.5 + 0.5
                 empty = torch.rand((n, S), generator=g, device=device) >= 0.05
-        ii = torch.randint(0, R, (n, S), generator=g, device=device, dtype=torch.int32)
+        if cfg.get('zipf'):
+            pr = 1.0 / torch.arange(1, R + 1, device=device, dtype=torch.float32) ** cfg['zipf']
+            ii = torch.multinomial(pr / pr.sum(), n * S, replacement=True, generator=g).reshape(n, S).to(torch.int32)
+        else:
+            ii = torch.randint(0, R, (n, S), generator=g, device=device, dtype=torch.int32)
         v[empty] = 0
         ii[empty] = 0
         parts.append(v.reshape(n, S * G).to(torch.float16))

@@ -377,6 +377,22 @@ def test_tile_path_bm25_like(shape):
     assert np.array_equal(s, s2) and np.array_equal(r, r2)
 
 
+def test_dense_only_cta_pair_variant():
+    """K2 as a CTA pair (cta_group::2): same answer as the single-CTA kernel on a dense-only index, > 128 queries in flight."""
+    case = make_case(77, 70000, 300, 0, 1, 768, 1, np.uint8, grid=True)
+    k = 100
+    with GipIndex.from_arrays(case['c_vals'], None) as ix:
+        s1, r1, c1 = ix.search(case['q_vals'], None, k)
+        ix.set_option('dense_variant', 2)
+        s2, r2, c2 = ix.search(case['q_vals'], None, k)
+        assert ix.stats()['scan_variant'] == 2
+    assert np.array_equal(s1, s2) and np.array_equal(r1, r2)
+    sub = dict(case)
+    sel = np.r_[0:4, 126:132, 296:300]
+    sub['q_vals'], sub['q_idx'] = case['q_vals'][sel], None
+    assert_matches_oracle(sub, s2[sel], r2[sel], c2[sel], k, exact=True)
+
+
 def test_tile_path_options_agree():
     """K2 variants (queries in TMEM / both operands in shared memory) and the stream plan (overlapped / in line) are
     implementation choices: on exact-arithmetic inputs every combination returns the identical answer."""
@@ -385,7 +401,7 @@ def test_tile_path_options_agree():
     outs = []
     with GipIndex.from_arrays(case['c_vals'], case['c_idx'], n_slices=32, group=6) as ix:
         configure(ix, 'tile')
-        for dv in (1, 0):
+        for dv in (1, 0, 2):                                           # 2 = CTA-pair form (tcgen05 cta_group::2, M = 256)
             for ov in (1, 0):
                 ix.set_option('dense_variant', dv)
                 ix.set_option('overlap', ov)
@@ -398,3 +414,47 @@ def test_tile_path_options_agree():
     assert_matches_oracle(sub, outs[0][0][sel], outs[0][1][sel], outs[0][2][sel], k, exact=True)
     for o in outs[1:]:
         assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])
+
+
+def test_skewed_index_distribution_zipf():
+    """K1t is O(matches); real argmax-over-39 indices are skewed.  Zipf-distributed slice indices
+    (big buckets for the hot values, ~3.5x the matches of the uniform recipe) on the tile path and on the row scan."""
+    from dhr_b200 import synth
+    cv, ci = synth.corpus_numpy('delade_cls_zipf', 0, 40000)
+    qv, qi = synth.queries_numpy('delade_cls_zipf', 70)
+    case = dict(S=128, G=6, C=768, c_vals=cv, c_idx=ci, q_vals=qv.astype(np.float32), q_idx=qi)
+    k = 100
+    with GipIndex.from_arrays(cv, ci, n_slices=128, group=6) as ix:
+        configure(ix, 'tile')
+        s, r, c = ix.search(case['q_vals'], qi, k)
+        assert ix.stats()['scan_variant'] == 3
+        configure(ix, 'scan1', 8)
+        s2, r2, c2 = ix.search(case['q_vals'], qi, k)
+    sub = dict(case)
+    sel = np.r_[0:5, 60:70]
+    sub['q_vals'], sub['q_idx'] = case['q_vals'][sel], qi[sel]
+    assert_matches_oracle(sub, s[sel], r[sel], c[sel], k)
+    assert_matches_oracle(sub, s2[sel], r2[sel], c2[sel], k)
+    assert np.abs(s - s2).max() < 1e-4 and np.mean(r == r2) > 0.99
+
+
+@pytest.mark.parametrize('shape', [(64, 1, 32), (128, 8, 64), (16, 7, 100), (768, 1, 128), (96, 3, 0), (160, 6, 0)])
+@pytest.mark.parametrize('dv', [1, 2])
+def test_unmasked_ip_stage_on_tensor_cores(shape, dv):
+    """--IP first stage (gip_retrieval.py:139) of a hybrid / lexical index: plain inner product over all columns, run as K2
+    column passes (lexical columns from the row-major array, then the dense block; > 768 columns = several passes through
+    the scratch).  Grid inputs: bit-exact against the oracle; 200 queries = two query groups (dv 2: CTA-pair form)."""
+    S, G, Cd = shape
+    case = make_case(300 + S + G, 50000, 200, S, G, Cd, 39, np.uint8, grid=True)
+    k = 64
+    with GipIndex.from_arrays(case['c_vals'], case['c_idx'], n_slices=S, group=G) as ix:
+        ix.set_option('dense_variant', dv)
+        s, r, c = ix.search(case['q_vals'], None, k, masked=False)
+        assert ix.stats()['scan_variant'] == 4, 'unmasked tile path not taken'
+        ix.set_option('tile_mode', 0)
+        s1, r1, c1 = ix.search(case['q_vals'][:16], None, k, masked=False)        # row scan K1, same rule
+    assert np.array_equal(s[:16], s1) and np.array_equal(r[:16], r1)
+    sub = dict(case)
+    sel = np.r_[0:5, 125:131, 195:200]
+    sub['q_vals'], sub['q_idx'] = case['q_vals'][sel], case['q_idx'][sel]
+    assert_matches_oracle(sub, s[sel], r[sel], c[sel], k, masked=False, exact=True)

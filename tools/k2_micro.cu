@@ -45,12 +45,13 @@ int main(int argc, char** argv) {
     float* scratch; CK(cudaMalloc(&scratch, (size_t)sub * 256 * 4));
     dhr::TopkState t; CK(cudaMalloc(&t.tau, 256 * 4)); CK(cudaMalloc(&t.cnt, 256 * 4));
     CK(cudaMemset(t.tau, 0x7f, 256 * 4)); CK(cudaMemset(t.cnt, 0, 256 * 4));
+    const float tau_arg = argc > 7 ? (float)atof(argv[7]) : 0.f;            // finite admission threshold for the dense-only (mode 0) runs
     CK(cudaMalloc(&t.cand_score, (size_t)256 * 16384 * 4)); CK(cudaMalloc(&t.cand_row, (size_t)256 * 16384 * 4));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    const int dbgs[] = {0, 0, 0, 4, 12};
-    const int mcast[] = {1, 0, 1, 1, 1};
-    for (int vi = 0; vi < 5; ++vi) {
-        const int variant = vi == 0 ? 0 : 1;
+    const int dbgs[] = {0, 0, 0, 4, 12, 0};
+    const int mcast[] = {1, 0, 1, 1, 1, 1};
+    for (int vi = 0; vi < 6; ++vi) {
+        const int variant = vi == 0 ? 0 : (vi == 5 ? 2 : 1);
         const int dbg = dbgs[vi];
         CK(cudaMemcpyToSymbol(dhr::g_k2_dbg, &dbg, sizeof(int)));
         h.opt_dense_variant = variant;
@@ -67,16 +68,18 @@ int main(int argc, char** argv) {
         }
         std::sort(ms.begin(), ms.end());
         const double flops = 2.0 * sub * nq * C;
-        printf("dbg %2d multicast %d variant %d (%s): median %.1f us  min %.1f us  -> %.0f TFLOP/s, corpus read %.0f GB/s\n", dbg, mcast[vi], variant, variant ? "TS" : "SS",
+        printf("dbg %2d multicast %d variant %d (%s): median %.1f us  min %.1f us  -> %.0f TFLOP/s, corpus read %.0f GB/s\n", dbg, mcast[vi], variant, variant == 2 ? "TS 2-CTA" : (variant ? "TS" : "SS"),
                ms[20] * 1e3, ms[0] * 1e3, flops / (ms[20] * 1e-3) / 1e12, sub * h.g.C_pad * 2.0 / (ms[20] * 1e-3) / 1e9);
     }
     // dense-only mode (filter + append, nothing passes tau): one launch over all rows, both variants
     { const int z = 0; CK(cudaMemcpyToSymbol(dhr::g_k2_dbg, &z, sizeof(int))); }
-    for (int variant = 1; variant < 3; ++variant) {
-        h.opt_dense_variant = 1;
-        h.opt_dense_multicast = variant - 1;
+    if (argc > 7) { std::vector<float> tv(256, tau_arg); CK(cudaMemcpy(t.tau, tv.data(), 256 * 4, cudaMemcpyHostToDevice)); }
+    for (int variant = 1; variant < 4; ++variant) {
+        h.opt_dense_variant = variant == 3 ? 2 : 1;
+        h.opt_dense_multicast = variant == 3 ? 1 : variant - 1;
         float best = 1e9f;
         for (int i = 0; i < 5; ++i) {
+            CK(cudaMemset(t.cnt, 0, 256 * 4));
             cudaEventRecord(e0);
             int rc = dhr::launch_dense_tile(&h, q, nq, 0, 0, n_rows, 0, nullptr, 0, t, 16384, 0);
             cudaEventRecord(e1);
@@ -84,7 +87,9 @@ int main(int argc, char** argv) {
             if (rc != 0) { fprintf(stderr, "launch rc %d\n", rc); return 1; }
             float m; cudaEventElapsedTime(&m, e0, e1); best = std::min(best, m);
         }
-        printf("mode 0 (filter) TS multicast %d: %lld rows x %d queries in %.1f us -> %.0f TFLOP/s, corpus read %.0f GB/s\n", variant - 1, n_rows, nq,
+        { std::vector<unsigned> cn(256); CK(cudaMemcpy(cn.data(), t.cnt, 256 * 4, cudaMemcpyDeviceToHost)); double tot = 0; for (unsigned x : cn) tot += x;
+          printf("  passes per query %.1f (tau %g) | ", tot / 256, tau_arg); }
+        printf("mode 0 (filter) %s multicast %d: %lld rows x %d queries in %.1f us -> %.0f TFLOP/s, corpus read %.0f GB/s\n", variant == 3 ? "TS 2-CTA" : "TS", h.opt_dense_multicast, n_rows, nq,
                best * 1e3, 2.0 * n_rows * nq * C / (best * 1e-3) / 1e12, n_rows * h.g.C_pad * 2.0 / (best * 1e-3) / 1e9);
     }
     long long tr[8][64];
