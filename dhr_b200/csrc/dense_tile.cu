@@ -861,7 +861,10 @@ int launch_dense_pass(const dhr_index* h, const __half* blocked, const __half* r
     // asked for (dense_multicast = 2).
     a.cluster = (a.n_qgroups == 2 && ((h->opt_dense_multicast == 1 && mode == 0) || h->opt_dense_multicast == 2)) ? 1 : 0;
     // cta_group::2 form (dense_variant 2): the two query groups of a batch as one CTA pair; needs exactly two groups in flight
-    const bool pair_mma = h->opt_dense_variant == 2 && a.n_qgroups == 2 && h->num_sms >= 2;
+    // (dense_variant 3 = automatic: the pair form for the long filter-mode launches of dense-only / --IP searches, the single-CTA
+    // form for the short scratch-mode launches of the hybrid path, where a cluster has to wait for both SMs of a TPC)
+    const bool want_pair = h->opt_dense_variant == 2 || (h->opt_dense_variant == 3 && (mode == 0 || mode == 3));
+    const bool pair_mma = want_pair && a.n_qgroups == 2 && h->num_sms >= 2;
     if (pair_mma) { a.cluster = 1; a.n_stages = kTS2_MaxStages; }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(per_q * a.n_qgroups));

@@ -486,17 +486,21 @@ int dhr_index_close(dhr_index* h) {
     if (!h) return DHR_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    void* bufs[] = {h->lexv, h->lexi, h->dns, h->dnst, h->lext, h->qblocks, h->qblock_bytes, h->scratch, h->d_flags, h->stage_a, h->stage_b, h->q_lex16, h->q_lex32, h->q_dns16, h->q_dns32,
+    void* bufs[] = {h->lexv, h->lexi, h->dns, h->dnst, h->lext, h->qblocks, h->qblock_bytes, h->lane[0].scratch, h->lane[1].scratch, h->d_flags, h->stage_a, h->stage_b, h->q_lex16, h->q_lex32, h->q_dns16, h->q_dns32,
                     h->q_code, h->topk.tau, h->topk.cnt, h->topk.overflow, h->topk.cand_score, h->topk.cand_row,
+                    h->topk1.tau, h->topk1.cnt, h->topk1.overflow, h->topk1.cand_score, h->topk1.cand_row,
                     h->d_out_scores, h->d_out_rows, h->d_out_counts, h->d_overflow, h->stage_c};
     for (void* b : bufs) if (b) cudaFree(b);
     for (cudaEvent_t e : h->batch_events) cudaEventDestroy(e);
-    for (int i = 0; i < 2; ++i) { if (h->ev_k2_done[i]) cudaEventDestroy(h->ev_k2_done[i]); if (h->ev_k1_done[i]) cudaEventDestroy(h->ev_k1_done[i]); }
-    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    if (h->ev_join) cudaEventDestroy(h->ev_join);
-    if (h->ev_sel) cudaEventDestroy(h->ev_sel);
-    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
-    if (h->aux2_stream) cudaStreamDestroy(h->aux2_stream);
+    for (int L = 0; L < 2; ++L) {
+        dhr_index::TileLane& ln = h->lane[L];
+        cudaEvent_t evs[] = {ln.ev_k2_done[0], ln.ev_k2_done[1], ln.ev_k1_done[0], ln.ev_k1_done[1], ln.ev_fork, ln.ev_join, ln.ev_sel, ln.ev_done};
+        for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+        if (ln.main) cudaStreamDestroy(ln.main);
+        if (ln.aux) cudaStreamDestroy(ln.aux);
+        if (ln.aux2) cudaStreamDestroy(ln.aux2);
+    }
+    if (h->ev_lanes_fork) cudaEventDestroy(h->ev_lanes_fork);
     h->events.destroy();
     cudaGetLastError();
     delete h;
@@ -523,9 +527,10 @@ int dhr_index_device_bytes(const dhr_index* h, int64_t* bytes) {
     if (h->lexv) b += rows * g.D_pad * 2;
     if (h->lexi) b += rows * g.S_pad * g.code_bytes;
     if (h->dns) b += rows * g.C_pad * 2;
-    b += h->lext_bytes + h->dnst_bytes + h->qblocks_bytes + h->qblock_bytes_cap + h->scratch_bytes + h->stage_a_bytes + h->stage_b_bytes +
+    b += h->lext_bytes + h->dnst_bytes + h->qblocks_bytes + h->qblock_bytes_cap + h->lane[0].scratch_bytes + h->lane[1].scratch_bytes + h->stage_a_bytes + h->stage_b_bytes +
          h->stage_c_bytes;
     if (h->topk.tau) b += (size_t)kMaxInflight * (12 + (size_t)kCandCap * 8);
+    if (h->topk1.tau) b += (size_t)kMaxInflight * (12 + (size_t)kCandCap * 8);
     if (h->q_capacity > 0) b += ((size_t)h->q_capacity + kMaxInflight) * ((size_t)g.D_pad * 6 + (size_t)g.S_pad * g.code_bytes + (size_t)g.C_pad * 6);
     b += h->out_capacity * 12 + h->out_q_capacity * 4 + h->overflow_capacity * 4;
     *bytes = (int64_t)b;
@@ -546,8 +551,9 @@ int dhr_index_set_option(dhr_index* h, const char* name, int64_t value) {
     if (!strcmp(name, "query_groups")) { if (value < 1 || value > kMaxScanInflight) return DHR_ERR_INVALID; h->opt_query_groups = (int)value; return DHR_OK; }
     if (!strcmp(name, "tile_mode")) { h->opt_tile_mode = value != 0; return DHR_OK; }
     if (!strcmp(name, "dense_multicast")) { if (value < 0 || value > 2) return DHR_ERR_INVALID; h->opt_dense_multicast = (int)value; return DHR_OK; }
+    if (!strcmp(name, "lanes")) { if (value < 1 || value > 2) return DHR_ERR_INVALID; h->opt_lanes = (int)value; return DHR_OK; }
     if (!strcmp(name, "overlap")) { h->opt_overlap = value != 0; return DHR_OK; }
-    if (!strcmp(name, "dense_variant")) { if (value < 0 || value > 2) return DHR_ERR_INVALID; h->opt_dense_variant = (int)value; return DHR_OK; }
+    if (!strcmp(name, "dense_variant")) { if (value < 0 || value > 3) return DHR_ERR_INVALID; h->opt_dense_variant = (int)value; return DHR_OK; }
     if (!strcmp(name, "profile")) { h->opt_profile = value != 0; return DHR_OK; }
     return DHR_ERR_INVALID;
 }

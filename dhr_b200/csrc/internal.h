@@ -67,10 +67,20 @@ struct dhr_index {
     // tile-mode workspace
     uint8_t* qblocks = nullptr; size_t qblocks_bytes = 0;
     uint32_t* qblock_bytes = nullptr; size_t qblock_bytes_cap = 0;
-    float* scratch = nullptr; size_t scratch_bytes = 0;   // two sub-chunk buffers (K2 of sub-chunk i+1 overlaps K1t of sub-chunk i)
-    cudaStream_t aux_stream = nullptr;   // K2 launches of the hybrid tile path
-    cudaStream_t aux2_stream = nullptr;  // every second K1t launch of a chunk (launches of one chunk are independent)
-    cudaEvent_t ev_k2_done[2] = {nullptr, nullptr}, ev_k1_done[2] = {nullptr, nullptr}, ev_fork = nullptr, ev_join = nullptr, ev_sel = nullptr;
+    // Two batch lanes: consecutive 256-query batches alternate between two independent sets of selection state, scratch, streams
+    // and events, so the select / drain at a chunk boundary of one batch is covered by scan launches of the other.
+    struct TileLane {
+        cudaStream_t main = nullptr;         // lane 1 only (lane 0 runs on the caller's stream)
+        cudaStream_t aux = nullptr;          // K2 launches of the hybrid tile path
+        cudaStream_t aux2 = nullptr;         // every second K1t launch of a chunk (launches of one chunk are independent)
+        float* scratch = nullptr; size_t scratch_bytes = 0;   // two sub-chunk buffers (K2 of sub-chunk i+1 overlaps K1t of sub-chunk i)
+        cudaEvent_t ev_k2_done[2] = {nullptr, nullptr}, ev_k1_done[2] = {nullptr, nullptr}, ev_fork = nullptr, ev_join = nullptr, ev_sel = nullptr;
+        cudaEvent_t ev_done = nullptr;       // lane 1: all its batches enqueued so far have finished
+    };
+    TileLane lane[2];
+    dhr::TopkState topk1;                    // selection state of lane 1 (lane 0 uses `topk`)
+    cudaEvent_t ev_lanes_fork = nullptr;
+    int opt_lanes = 2;                       // 1 = batches strictly one after the other
     float* d_out_scores = nullptr; int64_t* d_out_rows = nullptr; int32_t* d_out_counts = nullptr;
     size_t out_capacity = 0, out_q_capacity = 0;                   // [Q,k] elements / [Q] counts of the host-output staging
     uint32_t* d_overflow = nullptr; size_t overflow_capacity = 0;   // [Q] per-query overflow flags of the current search
@@ -88,7 +98,7 @@ struct dhr_index {
     int opt_tile_mode = 1;               // use the tensor-core tile kernels when the shape allows
     int opt_overlap = 1;                 // hybrid tile path: run K2 on a second stream, one sub-chunk ahead of K1t
     int opt_dense_multicast = 1;         // K2 (TS): the two query groups of a batch share corpus tiles as a cluster of two CTAs (0 off, 1 dense-only searches, 2 always)
-    int opt_dense_variant = 1;           // K2: 1 = queries in TMEM (TS) when C_pad <= 768, 0 = both operands in shared memory (SS)
+    int opt_dense_variant = 3;           // K2: 0 = both operands in shared memory (SS), 1 = queries in TMEM (TS), 2 = TS as a CTA pair (cta_group::2, M = 256), 3 = auto (2 for filter-mode launches, 1 for scratch-mode ones)
     int num_sms = 148;
     dhr_stats stats{};
     dhr::EventPool events;

@@ -136,8 +136,8 @@ static int ensure_query_workspace(dhr_index* h, int n) {
     return DHR_OK;
 }
 
-static int ensure_topk_state(dhr_index* h) {
-    TopkState& t = h->topk;
+static int ensure_topk_state(dhr_index* h, int lane = 0) {
+    TopkState& t = lane ? h->topk1 : h->topk;
     if (t.tau) return DHR_OK;
     DHR_CUDA(cudaMalloc(&t.tau, kMaxInflight * sizeof(float)));
     DHR_CUDA(cudaMalloc(&t.cnt, kMaxInflight * sizeof(uint32_t)));
@@ -290,8 +290,8 @@ static int run_batch(dhr_index* h, const QuerySet& qs, int base, int nq, int k, 
 }
 
 // dense-only index on the tensor-core tile kernel (K2): same chunk schedule, 128-row aligned
-static int run_batch_dense_tile(dhr_index* h, const QuerySet& qs, int base, int nq, int k, SelectOut so, cudaStream_t st) {
-    TopkState t = h->topk;
+static int run_batch_dense_tile(dhr_index* h, const QuerySet& qs, int base, int nq, int k, SelectOut so, cudaStream_t st, int L) {
+    TopkState t = L ? h->topk1 : h->topk;
     so.base = base;
     const std::vector<long long> bounds = chunk_schedule(h->n_rows, k, kCandCap, false, 128);
     const size_t n_chunks = bounds.size() - 1;
@@ -339,31 +339,41 @@ static int ensure_tile_workspace(dhr_index* h, const LexTileGeom& t, int n_queri
         DHR_CUDA(cudaMalloc(&h->qblock_bytes, nb_need));
         h->qblock_bytes_cap = nb_need;
     }
-    const size_t sc_need = h->g.C_pad > 0 ? (size_t)2 * kMaxInflight * kTileSubRows * sizeof(float) : 0;
-    if (sc_need > h->scratch_bytes) {
-        if (h->scratch) cudaFree(h->scratch);
-        h->scratch = nullptr; h->scratch_bytes = 0;
-        DHR_CUDA(cudaMalloc(&h->scratch, sc_need));
-        h->scratch_bytes = sc_need;
+    return DHR_OK;
+}
+
+// streams, events and (hybrid index) the two scratch buffers of a batch lane
+static int ensure_lane(dhr_index* h, int L, bool need_scratch) {
+    dhr_index::TileLane& ln = h->lane[L];
+    const size_t sc_need = need_scratch ? (size_t)2 * kMaxInflight * kTileSubRows * sizeof(float) : 0;
+    if (sc_need > ln.scratch_bytes) {
+        if (ln.scratch) cudaFree(ln.scratch);
+        ln.scratch = nullptr; ln.scratch_bytes = 0;
+        DHR_CUDA(cudaMalloc(&ln.scratch, sc_need));
+        ln.scratch_bytes = sc_need;
     }
-    if (!h->aux_stream) {
-        DHR_CUDA(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
-        DHR_CUDA(cudaStreamCreateWithFlags(&h->aux2_stream, cudaStreamNonBlocking));
-        DHR_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-        DHR_CUDA(cudaEventCreateWithFlags(&h->ev_sel, cudaEventDisableTiming));
+    if (!ln.aux) {
+        if (L == 1) DHR_CUDA(cudaStreamCreateWithFlags(&ln.main, cudaStreamNonBlocking));
+        DHR_CUDA(cudaStreamCreateWithFlags(&ln.aux, cudaStreamNonBlocking));
+        DHR_CUDA(cudaStreamCreateWithFlags(&ln.aux2, cudaStreamNonBlocking));
+        DHR_CUDA(cudaEventCreateWithFlags(&ln.ev_join, cudaEventDisableTiming));
+        DHR_CUDA(cudaEventCreateWithFlags(&ln.ev_sel, cudaEventDisableTiming));
         for (int i = 0; i < 2; ++i) {
-            DHR_CUDA(cudaEventCreateWithFlags(&h->ev_k2_done[i], cudaEventDisableTiming));
-            DHR_CUDA(cudaEventCreateWithFlags(&h->ev_k1_done[i], cudaEventDisableTiming));
+            DHR_CUDA(cudaEventCreateWithFlags(&ln.ev_k2_done[i], cudaEventDisableTiming));
+            DHR_CUDA(cudaEventCreateWithFlags(&ln.ev_k1_done[i], cudaEventDisableTiming));
         }
-        DHR_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        DHR_CUDA(cudaEventCreateWithFlags(&ln.ev_fork, cudaEventDisableTiming));
+        DHR_CUDA(cudaEventCreateWithFlags(&ln.ev_done, cudaEventDisableTiming));
     }
+    if (!h->ev_lanes_fork) DHR_CUDA(cudaEventCreateWithFlags(&h->ev_lanes_fork, cudaEventDisableTiming));
     return DHR_OK;
 }
 
 static int run_batch_hybrid_tile(dhr_index* h, const LexTileGeom& lt, const QuerySet& qs, int base, int nq, int k,
-                                 SelectOut so, cudaStream_t st) {
+                                 SelectOut so, cudaStream_t st, int L) {
     const Geometry& g = h->g;
-    TopkState t = h->topk;
+    TopkState t = L ? h->topk1 : h->topk;
+    dhr_index::TileLane& ln = h->lane[L];
     so.base = base;
     const std::vector<long long> bounds = chunk_schedule(h->n_rows, k, kCandCap, false, kLexTileRows, kTileSubRows);
     const size_t n_chunks = bounds.size() - 1;
@@ -387,19 +397,19 @@ static int run_batch_hybrid_tile(dhr_index* h, const LexTileGeom& lt, const Quer
             subs.emplace_back(r0, std::min(bounds[c + 1], r0 + kTileSubRows));
             sub_chunk.push_back(c);
         }
-    cudaStream_t k2s = k2_overlap ? h->aux_stream : st;
-    cudaStream_t k1s[2] = {st, overlap ? h->aux2_stream : st};
+    cudaStream_t k2s = k2_overlap ? ln.aux : st;
+    cudaStream_t k1s[2] = {st, overlap ? ln.aux2 : st};
     if (overlap) {
-        DHR_CUDA(cudaEventRecord(h->ev_fork, st));                   // queries prepared, slots initialised, previous batch done
-        if (k2_overlap) DHR_CUDA(cudaStreamWaitEvent(k2s, h->ev_fork, 0));
-        DHR_CUDA(cudaStreamWaitEvent(k1s[1], h->ev_fork, 0));
+        DHR_CUDA(cudaEventRecord(ln.ev_fork, st));                   // queries prepared, slots initialised, previous batch done
+        if (k2_overlap) DHR_CUDA(cudaStreamWaitEvent(k2s, ln.ev_fork, 0));
+        DHR_CUDA(cudaStreamWaitEvent(k1s[1], ln.ev_fork, 0));
     }
     auto launch_k2 = [&](size_t i) -> int {
         const int b = (int)(i & 1);
-        if (k2_overlap && i >= 2) DHR_CUDA(cudaStreamWaitEvent(k2s, h->ev_k1_done[b], 0));     // K1t(i-2) has read this buffer
-        DHR_TRY(launch_dense_tile(h, q16, nq, subs[i].first, subs[i].first, subs[i].second, 1, h->scratch + (k2_overlap ? b * sc_half : 0),
+        if (k2_overlap && i >= 2) DHR_CUDA(cudaStreamWaitEvent(k2s, ln.ev_k1_done[b], 0));     // K1t(i-2) has read this buffer
+        DHR_TRY(launch_dense_tile(h, q16, nq, subs[i].first, subs[i].first, subs[i].second, 1, ln.scratch + (k2_overlap ? b * sc_half : 0),
                                   kMaxInflight, t, kCandCap, k2s));
-        if (k2_overlap) DHR_CUDA(cudaEventRecord(h->ev_k2_done[b], k2s));
+        if (k2_overlap) DHR_CUDA(cudaEventRecord(ln.ev_k2_done[b], k2s));
         h->stats.n_kernel_launches++;
         return DHR_OK;
     };
@@ -416,22 +426,22 @@ static int run_batch_hybrid_tile(dhr_index* h, const LexTileGeom& lt, const Quer
             if (dense) {
                 if (k2_overlap) {
                     if (si + 1 < subs.size()) DHR_TRY(launch_k2(si + 1));
-                    DHR_CUDA(cudaStreamWaitEvent(ks, h->ev_k2_done[b], 0));
+                    DHR_CUDA(cudaStreamWaitEvent(ks, ln.ev_k2_done[b], 0));
                 } else {
                     DHR_TRY(launch_k2(si));
-                    if (ks != st) { DHR_CUDA(cudaEventRecord(h->ev_k2_done[b], st)); DHR_CUDA(cudaStreamWaitEvent(ks, h->ev_k2_done[b], 0)); }
+                    if (ks != st) { DHR_CUDA(cudaEventRecord(ln.ev_k2_done[b], st)); DHR_CUDA(cudaStreamWaitEvent(ks, ln.ev_k2_done[b], 0)); }
                 }
             }
-            DHR_TRY(launch_lex_tile(h, lt, qblocks, qbytes, nq, r0, r1, dense ? h->scratch + (k2_overlap ? b * sc_half : 0) : nullptr, kMaxInflight,
+            DHR_TRY(launch_lex_tile(h, lt, qblocks, qbytes, nq, r0, r1, dense ? ln.scratch + (k2_overlap ? b * sc_half : 0) : nullptr, kMaxInflight,
                                     r0, t, kCandCap, ks));
-            if (overlap) DHR_CUDA(cudaEventRecord(h->ev_k1_done[b], ks));
+            if (overlap) DHR_CUDA(cudaEventRecord(ln.ev_k1_done[b], ks));
             if (ks != st) used_aux2 = true;
             h->stats.n_kernel_launches++;
             h->stats.n_scan_launches++;
         }
         if (used_aux2) {                                             // the select needs every K1t launch of the chunk
-            DHR_CUDA(cudaEventRecord(h->ev_join, k1s[1]));
-            DHR_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+            DHR_CUDA(cudaEventRecord(ln.ev_join, k1s[1]));
+            DHR_CUDA(cudaStreamWaitEvent(st, ln.ev_join, 0));
         }
         if (h->opt_profile) cudaEventRecord(e1, st);
         DHR_TRY(launch_select(t, nq, k, kCandCap, c + 1 == n_chunks, so, st));
@@ -445,8 +455,8 @@ static int run_batch_hybrid_tile(dhr_index* h, const LexTileGeom& lt, const Quer
                               (((nq + kLexTileQueries - 1) / kLexTileQueries) * ((double)g.D_pad * 2.0 + (double)g.S_pad * lt.tcode_bytes) +
                                ((nq + 127) / 128) * (double)g.C_pad * 2.0);
         if (overlap && c + 1 < n_chunks) {                           // the next chunk's K1t launches read the new tau
-            DHR_CUDA(cudaEventRecord(h->ev_sel, st));
-            DHR_CUDA(cudaStreamWaitEvent(k1s[1], h->ev_sel, 0));
+            DHR_CUDA(cudaEventRecord(ln.ev_sel, st));
+            DHR_CUDA(cudaStreamWaitEvent(k1s[1], ln.ev_sel, 0));
         }
     }
     if (n_chunks == 0) {
@@ -530,7 +540,7 @@ static int run_batch_unmasked_tile(dhr_index* h, const QuerySet& qs, int base, i
             for (int p = 0; p < np; ++p) {
                 const int mode = np == 1 ? 0 : (p == 0 ? 1 : (p == np - 1 ? 3 : 2));
                 DHR_TRY(launch_dense_pass(h, passes[p].blocked, passes[p].rowmajor, passes[p].pitch, passes[p].cols, passes[p].q,
-                                          passes[p].q_pitch, nq, r0, r0, r1, mode, h->scratch, kMaxInflight, t, kCandCap, st));
+                                          passes[p].q_pitch, nq, r0, r0, r1, mode, h->lane[0].scratch, kMaxInflight, t, kCandCap, st));
                 h->stats.n_kernel_launches++;
                 h->stats.n_scan_launches++;
                 h->stats.alg_bytes += (double)(r1 - r0) * ((nq + 127) / 128) * (double)passes[p].cols * 2.0;
@@ -630,6 +640,7 @@ static int enqueue_search(dhr_index* h, const SearchRequest& r, SelectOut so, bo
     if (tile_hybrid) {
         lt = lex_tile_geom(g, rt);
         DHR_TRY(ensure_tile_workspace(h, lt, n_queries));
+        DHR_TRY(ensure_lane(h, 0, g.C_pad > 0));
         DHR_TRY(launch_lex_tile_prep(h, lt, h->q_lex16, h->q_code, n_queries, h->qblocks, h->qblock_bytes, st));
         h->stats.n_prep_launches++; h->stats.n_kernel_launches++;
         slots = kMaxInflight; qb = kLexTileQueries; groups = kMaxInflight / kLexTileQueries;
@@ -639,13 +650,7 @@ static int enqueue_search(dhr_index* h, const SearchRequest& r, SelectOut so, bo
                                (g.C_pad == 0 || dense_tile_ts_supported(g));
     if (tile_unmasked) {
         DHR_TRY(ensure_rowmajor(h));                                      // the lexical columns are read from the row-major array
-        const size_t sc_need = (size_t)kMaxInflight * kTileSubRows * sizeof(float);
-        if (sc_need > h->scratch_bytes) {
-            if (h->scratch) cudaFree(h->scratch);
-            h->scratch = nullptr; h->scratch_bytes = 0;
-            DHR_CUDA(cudaMalloc(&h->scratch, sc_need));
-            h->scratch_bytes = sc_need;
-        }
+        DHR_TRY(ensure_lane(h, 0, true));
         slots = kMaxInflight; qb = 128; groups = kMaxInflight / 128;
     }
     if (!tile_dense && !tile_hybrid) DHR_TRY(ensure_rowmajor(h));          // the row scan K1 reads the row-major arrays
@@ -654,12 +659,26 @@ static int enqueue_search(dhr_index* h, const SearchRequest& r, SelectOut so, bo
     h->stats.query_block = qb;
     h->stats.query_groups = groups;
     h->batch_size = slots;
+    // two batch lanes (tile paths): odd batches run on lane 1's streams with lane 1's selection state and scratch
+    const bool two_lanes = (tile_hybrid || tile_dense) && h->opt_lanes >= 2 && n_queries > slots;
+    if (two_lanes) {
+        DHR_TRY(ensure_lane(h, 0, tile_hybrid && g.C_pad > 0));
+        DHR_TRY(ensure_lane(h, 1, tile_hybrid && g.C_pad > 0));
+        DHR_TRY(ensure_topk_state(h, 1));
+        launch_init_slots(h->topk1, st);
+        DHR_CUDA(cudaGetLastError());
+        h->stats.n_kernel_launches++;
+        DHR_CUDA(cudaEventRecord(h->ev_lanes_fork, st));                  // queries prepared, both lanes' slots initialised
+        DHR_CUDA(cudaStreamWaitEvent(h->lane[1].main, h->ev_lanes_fork, 0));
+    }
     int b = 0;
     for (int base = 0; base < n_queries; base += slots, ++b) {
         const int nq = std::min(slots, n_queries - base);
-        if (tile_dense) DHR_TRY(run_batch_dense_tile(h, qs, base, nq, k, so, st));
+        const int L = two_lanes ? (b & 1) : 0;
+        cudaStream_t ms = L ? h->lane[1].main : st;
+        if (tile_dense) DHR_TRY(run_batch_dense_tile(h, qs, base, nq, k, so, ms, L));
         else if (tile_unmasked) DHR_TRY(run_batch_unmasked_tile(h, qs, base, nq, k, so, st));
-        else if (tile_hybrid) DHR_TRY(run_batch_hybrid_tile(h, lt, qs, base, nq, k, so, st));
+        else if (tile_hybrid) DHR_TRY(run_batch_hybrid_tile(h, lt, qs, base, nq, k, so, ms, L));
         else DHR_TRY(run_batch(h, qs, base, nq, k, r.masked, false, qb, so, st));
         if (record_batches) {
             while ((int)h->batch_events.size() <= b) {
@@ -667,8 +686,12 @@ static int enqueue_search(dhr_index* h, const SearchRequest& r, SelectOut so, bo
                 DHR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
                 h->batch_events.push_back(e);
             }
-            DHR_CUDA(cudaEventRecord(h->batch_events[(size_t)b], st));
+            DHR_CUDA(cudaEventRecord(h->batch_events[(size_t)b], ms));
         }
+    }
+    if (two_lanes) {                                                       // the caller's stream continues after both lanes
+        DHR_CUDA(cudaEventRecord(h->lane[1].ev_done, h->lane[1].main));
+        DHR_CUDA(cudaStreamWaitEvent(st, h->lane[1].ev_done, 0));
     }
     h->n_batches = b;
     if (h->opt_profile) cudaEventRecord(h->ev_end, st);
