@@ -32,7 +32,7 @@ def load(path):
 
 def main():
     traffic = {'_comment': 'per workload: DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch of the scan kernels of one '
-                           'steady-state sub-chunk of the tile path (rows_per_launch rows x queries_in_flight queries), from ncu --set full '
+                           'steady-state sub-chunk of the tile path at full size (rows_per_launch rows x queries_in_flight queries; last chunk, tight threshold), from ncu --set full '
                            '(tools/ncu_workloads.sh, summaries in profiles/r2_ncu_<workload>.txt); utilisation figures are those of the dominant kernel'}
     for w in ['delade_cls', 'delade_cls_ref', 'bm25', 'bm25_ref', 'dense', 'delade_cls_zipf']:
         rep = os.path.join(ROOT, 'gpurun_out', 'r2_ncu_%s.ncu-rep' % w)
@@ -52,8 +52,8 @@ def main():
                 return v * TIME.get(u, 1.0)
             return v
         kernels = {}
-        lines = ['# ncu --set full --clock-control none --import-source on, one steady-state sub-chunk of `python tools/k1t_bench.py --workload %s` '
-                 '(37,888 rows x 256 queries in flight); source: %s' % (w, os.path.relpath(rep, ROOT))]
+        lines = ['# ncu --set full --clock-control none --import-source on, steady-state launches of the last chunk of `python bench.py --workload %s --queries 256` '
+                 '(8,841,823 rows; 37,888 rows x 256 queries per tile-path launch, the 7.78 M-row last chunk for the dense-only index); source: %s' % (w, os.path.relpath(rep, ROOT))]
         for r in rows:
             name = r[col['Kernel Name']].split('(')[0].replace('void ', '').replace('dhr::', '')
             kind = 'K1t' if 'lex_tile' in name else 'K2'
@@ -78,7 +78,7 @@ def main():
                 if x is not None:
                     k[key].append(x)
             k['lsu_wavefronts_shared'] += val(r, 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum') or 0.0
-        out = {'rows_per_launch': 37888, 'queries_in_flight': 256, 'source': 'profiles/r2_ncu_%s.txt' % w, 'kernels': {}}
+        out = {'rows_per_launch': 37888 if w != 'dense' else 8841823 - 1062656, 'queries_in_flight': 256, 'source': 'profiles/r2_ncu_%s.txt' % w, 'kernels': {}}
         total = 0.0
         for kind, k in kernels.items():
             n = k['launches']
