@@ -61,6 +61,7 @@ def parse():
     ap.add_argument('--cpu-queries', type=int, default=12)
     ap.add_argument('--cpu-full', action='store_true', help='--impl reference: the full SURVEY 8(d) procedure (16 shards, 1 thread and all cores)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--lex-postings', action='store_true', help='experimental postings lexical layout (kernel K1p) instead of the tiled one (K1t)')
     ap.add_argument('--no-verify', action='store_true')
     ap.add_argument('--verify-queries', type=int, default=16)
     return ap.parse_args()
@@ -361,7 +362,7 @@ def main():
 
     # ---- build the resident shard (not timed: index load is outside the metric) ----
     t_build = time.perf_counter()
-    ix = GipIndex(cfg['S'], cfg['C'], cfg['G'], capacity=hi - lo, idx_dtype=np.dtype(cfg['idx']), device=local_rank, row_offset=lo)
+    ix = GipIndex(cfg['S'], cfg['C'], cfg['G'], capacity=hi - lo, idx_dtype=np.dtype(cfg['idx']), device=local_rank, row_offset=lo, lex_postings=args.lex_postings)
     for vals, idx in synth.corpus_torch_segments(args.workload, lo, hi, dev):
         ix.append(vals, idx)
     ix.finalize()
@@ -506,7 +507,9 @@ def main():
         tensor_achieved = dense_flops / scan_s / 1e12 if scan_s > 0 else 0.0
         tensor_peak = peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops'))
         kernel_names = {1: 'gip_scan_tma (K1)', 0: 'gip_scan_direct (K1)', 2: 'dense_tile_ts (K2, tcgen05, queries in TMEM)',
-                        3: 'lex_tile (K1t) + dense_tile_ts (K2, tcgen05, queries in TMEM)'}
+                        3: ('lex_post (K1p, postings walk)' if stats[0].get('lex_layout') else 'lex_tile (K1t)') +
+                           (' + dense_tile_ts (K2, tcgen05, queries in TMEM)' if cfg['C'] > 0 else ''),
+                        4: 'dense_tile_ts column passes (K2, tcgen05): unmasked --IP stage'}
         if variant == 2:      # dense-only: a GEMM -> tensor ceiling (sustained: timed inside a long step)
             roof = {'bound': 'tensor', 'achieved': tensor_achieved, 'peak': tensor_peak, 'unit': 'TFLOP/s',
                     'frac': tensor_achieved / tensor_peak, 'peak_kind': 'bf16 sustained (fp16 runs at the same rate)',

@@ -19,6 +19,7 @@ VAL_F16, VAL_F32 = 0, 1
 SEARCH_UNMASKED = 1
 INDEX_NARROW_CODES = 1
 INDEX_KEEP_ROWMAJOR = 2
+INDEX_LEX_POSTINGS = 4
 MAX_K = 12288
 MAX_GROUP = 8
 
@@ -39,7 +40,7 @@ class DhrStats(ctypes.Structure):
         ('n_prep_launches', ctypes.c_int32), ('n_fallback_queries', ctypes.c_int32),
         ('n_kernel_launches', ctypes.c_int32), ('rowmajor_rebuilds', ctypes.c_int32),
         ('scan_ms', ctypes.c_double), ('select_ms', ctypes.c_double), ('total_ms', ctypes.c_double),
-        ('corpus_passes', ctypes.c_double), ('bytes_per_pass', ctypes.c_double), ('dense_flops', ctypes.c_double), ('alg_bytes', ctypes.c_double),
+        ('corpus_passes', ctypes.c_double), ('bytes_per_pass', ctypes.c_double), ('dense_flops', ctypes.c_double), ('lex_layout', ctypes.c_double), ('alg_bytes', ctypes.c_double),
     ]
 
     def as_dict(self):

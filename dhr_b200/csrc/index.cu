@@ -159,6 +159,90 @@ __global__ void build_lext_kernel(long long n_rows, long long n_rows_pad, int S_
     for (int g = 0; g < G; ++g) tv[g] = src[g];
 }
 
+// Postings copy for K1p, built once at finalize: one CTA per (tile of 512 rows, chunk of 4 slices), thread = row.  Per slice a
+// counting sort by code over the non-empty rows; item = {row-in-tile | code << 16, G fp16 values} of EW words.  The order of
+// items with the same code is the order of the atomic ranks (arbitrary); a slice holds each row once, so the scores do not
+// depend on it.
+template <typename CodeT>
+__global__ void __launch_bounds__(kLexTileRows)
+build_lexp_kernel(long long n_rows, int S_pad, int G, int EW, int rt, int block_stride, const __half* __restrict__ lexv,
+                  const CodeT* __restrict__ lexi, uint8_t* __restrict__ lexp, uint32_t* __restrict__ nbytes) {
+    __shared__ uint32_t cnt[256], start[256];
+    __shared__ uint32_t slice_n;
+    const int chunk = blockIdx.x, n_chunks = gridDim.x;
+    const long long tile = blockIdx.y;
+    const int p = threadIdx.x;
+    const long long row = tile * kLexTileRows + p;
+    uint8_t* blk = lexp + ((size_t)tile * n_chunks + chunk) * (size_t)block_stride;
+    uint32_t* hdr = (uint32_t*)blk;
+    uint32_t* items = (uint32_t*)(blk + 16);
+    uint32_t base = 0;
+    for (int j = 0; j < kLexTileSlices; ++j) {
+        const int s = chunk * kLexTileSlices + j;
+        uint32_t code = 0xFFFFFFFFu;
+        if (row < n_rows) code = lexi[(size_t)row * S_pad + s];
+        const bool valid = code < (uint32_t)rt;                           // CODE_EMPTY / CODE_NOMATCH are above every stored code
+        if (p < 256) cnt[p] = 0u;
+        __syncthreads();
+        uint32_t rank = 0;
+        if (valid) rank = atomicAdd(&cnt[code], 1u);
+        __syncthreads();
+        if (p == 0) {
+            uint32_t run = 0;
+            for (int c = 0; c < rt; ++c) { start[c] = run; run += cnt[c]; }
+            slice_n = run;
+            hdr[j] = (base << 16) | run;
+        }
+        __syncthreads();
+        if (valid) {
+            uint32_t* it = items + (size_t)(base + start[code] + rank) * EW;
+            const __half* v = lexv + ((size_t)row * S_pad + s) * G;
+            it[0] = (uint32_t)p | (code << 16);
+            for (int w = 1; w < EW; ++w) {
+                const int g0 = 2 * (w - 1), g1 = g0 + 1;
+                const uint32_t lo = g0 < G ? __half_as_ushort(v[g0]) : 0u;
+                const uint32_t hi = g1 < G ? __half_as_ushort(v[g1]) : 0u;
+                it[w] = lo | (hi << 16);
+            }
+        }
+        base += slice_n;
+        __syncthreads();
+    }
+    if (p == 0) nbytes[(size_t)tile * n_chunks + chunk] = (16u + base * (uint32_t)EW * 4u + 15u) & ~15u;
+}
+
+// inverse: rebuild the row-major arrays from the postings (rows of empty slices were pre-filled with value 0 / CODE_EMPTY)
+template <typename CodeT>
+__global__ void __launch_bounds__(kLexTileRows)
+unbuild_lexp_kernel(long long n_rows, int S_pad, int G, int EW, int block_stride, const uint8_t* __restrict__ lexp, __half* __restrict__ lexv,
+                    CodeT* __restrict__ lexi) {
+    const int chunk = blockIdx.x, n_chunks = gridDim.x;
+    const long long tile = blockIdx.y;
+    const uint8_t* blk = lexp + ((size_t)tile * n_chunks + chunk) * (size_t)block_stride;
+    const uint32_t* hdr = (const uint32_t*)blk;
+    const uint32_t* items = (const uint32_t*)(blk + 16);
+    for (int j = 0; j < kLexTileSlices; ++j) {
+        const uint32_t n = hdr[j] & 0xFFFFu, first = hdr[j] >> 16;
+        const int s = chunk * kLexTileSlices + j;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t* it = items + (size_t)(first + i) * EW;
+            const long long row = tile * kLexTileRows + (it[0] & 0xFFFFu);
+            if (row >= n_rows) continue;
+            lexi[(size_t)row * S_pad + s] = (CodeT)((it[0] >> 16) & 0xFFu);
+            __half* dst = lexv + ((size_t)row * S_pad + s) * G;
+            for (int g = 0; g < G; ++g) dst[g] = __ushort_as_half((unsigned short)((it[1 + (g >> 1)] >> (16 * (g & 1))) & 0xFFFFu));
+        }
+    }
+}
+
+template <typename CodeT>
+__global__ void fill_empty_lexical_kernel(long long total_slices, int G, __half* __restrict__ lexv, CodeT* __restrict__ lexi) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total_slices) return;
+    lexi[i] = (CodeT)CodeTraits<CodeT>::kEmpty;
+    for (int g = 0; g < G; ++g) lexv[(size_t)i * G + g] = __float2half_rn(0.f);
+}
+
 // K-blocked copy of the dense block for K2 (TS variant): [tile of 128 rows][k-block][128 rows][64 cols], so that one
 // 16 KiB TMA stage is one contiguous piece of HBM (the row-major block would be read as 128-byte pieces 2*C_pad apart,
 // which measured ~2.2 TB/s).  One thread moves one 16-byte vector; rows >= n_rows and columns >= C_pad are zero.
@@ -213,7 +297,7 @@ __global__ void unbuild_dnst_kernel(long long n_rows, int C_pad, int n_kblocks, 
 
 static bool tiled_copies_complete(const dhr_index* h) {
     const Geometry& g = h->g;
-    return (g.D_pad == 0 || h->lext) && (g.C_pad == 0 || h->dnst);
+    return (g.D_pad == 0 || h->lext || h->lexp) && (g.C_pad == 0 || h->dnst);
 }
 
 static int drop_rowmajor_unchecked(dhr_index* h);
@@ -244,7 +328,18 @@ int ensure_rowmajor(dhr_index* h) {
         const long long total = h->n_rows * g.S_pad;
         const unsigned blocks = (unsigned)((total + 255) / 256);
         const bool wide = std::max(1, h->max_code + 1) > 254;
-        if (wide) unbuild_lext_kernel<uint16_t, uint16_t><<<blocks, 256>>>(h->n_rows, g.S_pad, g.G, h->lext, h->lexv, (uint16_t*)h->lexi);
+        if (!h->lext) {                                                   // postings layout: pre-fill, then scatter the items
+            const LexTileGeom lp = lex_post_geom(g, std::max(1, h->max_code + 1));
+            const int EW = lex_post_entry_words(g.G);
+            dim3 grid((unsigned)(g.S_pad / kLexTileSlices), (unsigned)((h->n_rows + kLexTileRows - 1) / kLexTileRows));
+            if (g.code_bytes == 1) {
+                fill_empty_lexical_kernel<uint8_t><<<blocks, 256>>>(total, g.G, h->lexv, (uint8_t*)h->lexi);
+                unbuild_lexp_kernel<uint8_t><<<grid, kLexTileRows>>>(h->n_rows, g.S_pad, g.G, EW, lp.pblock_bytes, h->lexp, h->lexv, (uint8_t*)h->lexi);
+            } else {
+                fill_empty_lexical_kernel<uint16_t><<<blocks, 256>>>(total, g.G, h->lexv, (uint16_t*)h->lexi);
+                unbuild_lexp_kernel<uint16_t><<<grid, kLexTileRows>>>(h->n_rows, g.S_pad, g.G, EW, lp.pblock_bytes, h->lexp, h->lexv, (uint16_t*)h->lexi);
+            }
+        } else if (wide) unbuild_lext_kernel<uint16_t, uint16_t><<<blocks, 256>>>(h->n_rows, g.S_pad, g.G, h->lext, h->lexv, (uint16_t*)h->lexi);
         else if (g.code_bytes == 1) unbuild_lext_kernel<uint8_t, uint8_t><<<blocks, 256>>>(h->n_rows, g.S_pad, g.G, h->lext, h->lexv, (uint8_t*)h->lexi);
         else unbuild_lext_kernel<uint16_t, uint8_t><<<blocks, 256>>>(h->n_rows, g.S_pad, g.G, h->lext, h->lexv, (uint16_t*)h->lexi);
         DHR_CUDA(cudaGetLastError());
@@ -344,6 +439,7 @@ int dhr_index_create(dhr_index** out, int device, int64_t cap_rows, int n_slices
     g.C_pad = (int)round_up(n_dense, 8);
     const bool narrow = (flags & DHR_INDEX_NARROW_CODES) != 0;
     h->keep_rowmajor = (flags & DHR_INDEX_KEEP_ROWMAJOR) != 0;
+    h->use_postings = (flags & DHR_INDEX_LEX_POSTINGS) != 0;
     g.code_bytes = (idx_dtype_size(h->idx_dtype) == 1 || narrow || n_slices == 0) ? 1 : 2;
     g.unit_halves = (group % 8 == 0) ? group : (group % 4 == 0) ? 2 * group : (group % 2 == 0) ? 4 * group : 8 * group;
     g.unit_slices = g.unit_halves / group;
@@ -427,9 +523,33 @@ int dhr_index_finalize(dhr_index* h) {
     if (flags[0]) return DHR_ERR_LOSSY;
     if (flags[1]) return DHR_ERR_IDX_RANGE;
     h->max_code = flags[3] - 1;
-    if (h->g.S_pad > 0 && h->n_rows > 0 && lex_tile_supported(h->g, std::max(1, h->max_code + 1))) {
+    const int rt_fin = std::max(1, h->max_code + 1);
+    if (h->g.S_pad > 0 && h->n_rows > 0 && h->use_postings && lex_post_supported(h->g, rt_fin)) {
+        // postings layout (K1p): non-empty passages of every (tile, slice) sorted by code
         const Geometry& g = h->g;
-        const LexTileGeom lt = lex_tile_geom(g, std::max(1, h->max_code + 1));
+        const LexTileGeom lp = lex_post_geom(g, rt_fin);
+        const long long n_tiles = (h->n_rows + kLexTileRows - 1) / kLexTileRows;
+        const int n_chunks = g.S_pad / kLexTileSlices;
+        h->lexp_bytes = (size_t)n_tiles * n_chunks * (size_t)lp.pblock_bytes;
+        if (cudaMalloc(&h->lexp, h->lexp_bytes) != cudaSuccess) { cudaGetLastError(); h->lexp = nullptr; h->lexp_bytes = 0; }
+        if (h->lexp && cudaMalloc(&h->lexp_nbytes, (size_t)n_tiles * n_chunks * sizeof(uint32_t)) != cudaSuccess) {
+            cudaGetLastError(); cudaFree(h->lexp); h->lexp = nullptr; h->lexp_bytes = 0; h->lexp_nbytes = nullptr;
+        }
+        if (h->lexp) {
+            dim3 grid((unsigned)n_chunks, (unsigned)n_tiles);
+            const int EW = lex_post_entry_words(g.G);
+            if (g.code_bytes == 1)
+                build_lexp_kernel<uint8_t><<<grid, kLexTileRows>>>(h->n_rows, g.S_pad, g.G, EW, rt_fin, lp.pblock_bytes, h->lexv, (const uint8_t*)h->lexi, h->lexp, h->lexp_nbytes);
+            else
+                build_lexp_kernel<uint16_t><<<grid, kLexTileRows>>>(h->n_rows, g.S_pad, g.G, EW, rt_fin, lp.pblock_bytes, h->lexv, (const uint16_t*)h->lexi, h->lexp, h->lexp_nbytes);
+            DHR_CUDA(cudaGetLastError());
+            DHR_CUDA(cudaDeviceSynchronize());
+            h->lex_layout = 1;
+        }
+    }
+    if (h->g.S_pad > 0 && h->n_rows > 0 && !h->lexp && lex_tile_supported(h->g, rt_fin)) {
+        const Geometry& g = h->g;
+        const LexTileGeom lt = lex_tile_geom(g, rt_fin);
         const long long rows_pad = round_up(h->n_rows, kLexTileRows);
         h->lext_bytes = (size_t)rows_pad * g.S_pad * (lt.tcode_bytes + 2 * (size_t)g.G);
         if (cudaMalloc(&h->lext, h->lext_bytes) != cudaSuccess) { cudaGetLastError(); h->lext = nullptr; h->lext_bytes = 0; }   // tile path simply stays off
@@ -486,7 +606,7 @@ int dhr_index_close(dhr_index* h) {
     if (!h) return DHR_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    void* bufs[] = {h->lexv, h->lexi, h->dns, h->dnst, h->lext, h->qblocks, h->qblock_bytes, h->lane[0].scratch, h->lane[1].scratch, h->d_flags, h->stage_a, h->stage_b, h->q_lex16, h->q_lex32, h->q_dns16, h->q_dns32,
+    void* bufs[] = {h->lexv, h->lexi, h->dns, h->dnst, h->lext, h->qblocks, h->qblock_bytes, h->lane[0].scratch, h->lane[1].scratch, h->lexp, h->lexp_nbytes, h->d_flags, h->stage_a, h->stage_b, h->q_lex16, h->q_lex32, h->q_dns16, h->q_dns32,
                     h->q_code, h->topk.tau, h->topk.cnt, h->topk.overflow, h->topk.cand_score, h->topk.cand_row,
                     h->topk1.tau, h->topk1.cnt, h->topk1.overflow, h->topk1.cand_score, h->topk1.cand_row,
                     h->d_out_scores, h->d_out_rows, h->d_out_counts, h->d_overflow, h->stage_c};
@@ -527,7 +647,7 @@ int dhr_index_device_bytes(const dhr_index* h, int64_t* bytes) {
     if (h->lexv) b += rows * g.D_pad * 2;
     if (h->lexi) b += rows * g.S_pad * g.code_bytes;
     if (h->dns) b += rows * g.C_pad * 2;
-    b += h->lext_bytes + h->dnst_bytes + h->qblocks_bytes + h->qblock_bytes_cap + h->lane[0].scratch_bytes + h->lane[1].scratch_bytes + h->stage_a_bytes + h->stage_b_bytes +
+    b += h->lext_bytes + h->lexp_bytes + h->dnst_bytes + h->qblocks_bytes + h->qblock_bytes_cap + h->lane[0].scratch_bytes + h->lane[1].scratch_bytes + h->stage_a_bytes + h->stage_b_bytes +
          h->stage_c_bytes;
     if (h->topk.tau) b += (size_t)kMaxInflight * (12 + (size_t)kCandCap * 8);
     if (h->topk1.tau) b += (size_t)kMaxInflight * (12 + (size_t)kCandCap * 8);

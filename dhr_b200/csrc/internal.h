@@ -46,6 +46,7 @@ struct dhr_index {
     dhr::Geometry g;
     int idx_dtype = DHR_IDX_NONE;
     bool finalized = false;
+    bool use_postings = false;           // DHR_INDEX_LEX_POSTINGS: lexical copy as postings (K1p, experimental) instead of the tiled layout (K1t)
     bool keep_rowmajor = false;          // DHR_INDEX_KEEP_ROWMAJOR: never drop lexv / lexi / dns at finalize
     // resident arrays (device)
     __half* lexv = nullptr;              // [capacity][D_pad]
@@ -55,6 +56,10 @@ struct dhr_index {
     size_t dnst_bytes = 0;
     uint8_t* lext = nullptr;             // tiled lexical copy for K1t: [tile of 512 rows][4-slice chunk]{codes u8|u16 [512][4] | vals [4][512][G]}
     size_t lext_bytes = 0;
+    uint8_t* lexp = nullptr;             // postings copy for K1p: [tile][chunk] fixed-stride blocks (see lex_post_geom)
+    size_t lexp_bytes = 0;
+    uint32_t* lexp_nbytes = nullptr;     // [tiles * chunks] bytes actually used by each block (what the producer copies)
+    int lex_layout = 0;                  // 0 = tiled copy (K1t), 1 = postings (K1p)
     int max_code = -1;                   // largest slice code stored (known after finalize)
     int* d_flags = nullptr;              // [4] device-side validation flags (lossy, idx range, query needs fp32, spare)
     // staging for host -> device appends / queries
@@ -149,6 +154,14 @@ constexpr int kLexTileRows = 512;        // passages per K1t tile (= consumer th
 constexpr int kLexTileQueries = 64;      // queries per K1t tile (acc[64][512] fp32 = 128 KiB, 16 consumer warps per SM)
 constexpr int kLexTileSlices = 4;        // slices per chunk
 LexTileGeom lex_tile_geom(const Geometry& g, int rt);
+// postings layout of the corpus tile (K1p, lex_tile.cu): per (tile of 512 rows, chunk of 4 slices) a fixed-stride block holding a
+// 16-byte header and the NON-EMPTY passages of each slice sorted by code, item = {passage | code << 16, G fp16}
+LexTileGeom lex_post_geom(const Geometry& g, int rt);
+bool lex_post_supported(const Geometry& g, int rt);
+int lex_post_entry_words(int G);
+int launch_lex_post(const dhr_index* h, const LexTileGeom& t, const uint8_t* qblocks, const uint32_t* qblock_bytes, int n_queries,
+                    long long row_begin, long long row_end, const float* scratch, long long scratch_slots, long long scratch_row0,
+                    const TopkState& tk, int cap, cudaStream_t st);
 bool lex_tile_supported(const Geometry& g, int rt);
 int launch_lex_tile_prep(const dhr_index* h, const LexTileGeom& t, const void* q_lex16, const void* q_code, int n_queries,
                          uint8_t* qblocks, uint32_t* qblock_bytes, cudaStream_t st);

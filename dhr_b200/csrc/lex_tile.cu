@@ -234,6 +234,7 @@ struct LexTileArgs {
     const uint8_t* lext;               // tiled corpus blocks [tile][chunk]
     const uint8_t* qblocks;            // query blocks [qtile][chunk] (stride qblock_stride)
     const uint32_t* qblock_bytes;      // bytes to copy per query block
+    const uint32_t* pblock_nbytes;     // postings layout: bytes to copy per (tile, chunk) block
     long long row_begin, row_end;      // rows handled by this launch (row_begin multiple of the tile size)
     long long n_rows;
     int n_tiles;                       // tiles in [row_begin, row_end)
@@ -508,7 +509,277 @@ __global__ void __launch_bounds__(kLT_Threads, kLT_CtasPerSm) lex_tile_kernel(co
     }
 }
 
+// =====================================================================================================
+// K1p: the same tile (64 queries x 512 passages) walked from a POSTINGS layout of the corpus tile.
+//
+// K1t gives every passage a thread and lets it walk the queries of its bucket; per-thread match counts are
+// Poisson, so ~40 % of the lanes of a level work, and every thread pays the lookup of 4 slices (~100
+// instructions per chunk) whether they match or not.  Here the index stores, per (tile, slice), only the
+// NON-EMPTY passages, sorted by their slice code: item = {passage u16 | code u8, G fp16 values}.  A warp takes
+// 32 consecutive items of the slice's list: its lanes hold the same or neighbouring codes, so they read the
+// SAME bucket (broadcast loads of table word and entries), run the same number of levels (bucket size), and no
+// lane is spent on an empty slice.  Every level is: entry (broadcast) -> acc[q][passage] += dot.  Within a slice
+// the passages of all items are distinct, so the warps of the CTA never touch the same accumulator; between
+// slices a CTA barrier orders the read-modify-writes of one (query, passage) pair (fixed summation order: by
+// slice).  The table word and the item of the next slice are loaded before the barrier (stage data is
+// read-only), which takes their latency off the per-slice critical path.
+// =====================================================================================================
+
+// ---- K1p pipeline stages (force-inlined; every slice of a chunk has its own PItem / PRun registers) ----------------------------
+template <int EW> struct PItem { uint32_t it[EW]; uint32_t tw; };
+struct PRun { uint32_t cnt, eb, accp, M; };
+constexpr int kLP_Group = 4;               // bucket entries handled as one group of independent accumulator updates
+
+template <int EW>
+__device__ __forceinline__ void k1p_item(uint32_t st_s, uint32_t hdr, uint32_t p, PItem<EW>& o) {         // S1
+    lds_entry_lt<EW>(st_s + 16u + ((hdr >> 16) + p) * (uint32_t)(EW * 4), p, hdr & 0xFFFFu, o.it);
+}
+template <int EW>
+__device__ __forceinline__ void k1p_table(uint32_t tab_s, uint32_t slice_off, uint32_t hdr, uint32_t p, PItem<EW>& o) {   // S2
+    const uint32_t code = (o.it[0] >> 16) & 0xFFu;
+    o.tw = 0u;                                                              // slots beyond the item count: empty bucket
+    asm("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %2, %3;\n\t@q ld.shared.u32 %0, [%1];\n\t}"
+        : "+r"(o.tw) : "r"(tab_s + (slice_off + code) * 4u), "r"(p), "r"(hdr & 0xFFFFu));
+}
+template <int EW>
+__device__ __forceinline__ void k1p_load_group(const PRun& r, uint32_t i0, uint32_t (&e)[kLP_Group][EW]) {
+#pragma unroll
+    for (int u = 0; u < kLP_Group; ++u) lds_entry_lt<EW>(r.eb + (i0 + u) * (uint32_t)(EW * 4), i0 + u, r.cnt, e[u]);
+}
+template <int G, int EW>
+__device__ __forceinline__ void k1p_apply_group(const PRun& r, const PItem<EW>& item, uint32_t i0, const uint32_t (&e)[kLP_Group][EW]) {
+    uint32_t ad[kLP_Group]; float cur[kLP_Group], res[kLP_Group];
+#pragma unroll
+    for (int u = 0; u < kLP_Group; ++u) { ad[u] = r.accp + e[u][0]; cur[u] = lds_acc_lt(ad[u], i0 + u, r.cnt); }
+#pragma unroll
+    for (int u = 0; u < kLP_Group; ++u) res[u] = entry_chain<G, 0>(e[u], item.it + 1, cur[u]) + entry_chain<G, 1>(e[u], item.it + 1, 0.f);
+#pragma unroll
+    for (int u = 0; u < kLP_Group; ++u) sts_acc_lt(ad[u], res[u], i0 + u, r.cnt);
+}
+template <int EW>
+__device__ __forceinline__ void k1p_bucket(uint32_t ent_s, uint32_t acc_s, const PItem<EW>& item, PRun& r, uint32_t (&e)[kLP_Group][EW]) {   // S3
+    r.cnt = item.tw >> 16;
+    r.eb = ent_s + (item.tw & 0xFFFFu);
+    r.accp = acc_s + (item.it[0] & 0xFFFFu) * 4u;                          // acc[0][passage of the item]
+    r.M = __reduce_max_sync(0xFFFFFFFFu, r.cnt);
+    k1p_load_group<EW>(r, 0u, e);
+}
+template <int G, int EW>
+__device__ __forceinline__ void k1p_update(const PRun& r, const PItem<EW>& item, const uint32_t (&e)[kLP_Group][EW]) {      // S4
+    k1p_apply_group<G, EW>(r, item, 0u, e);
+#pragma unroll 1
+    for (uint32_t i = kLP_Group; i < r.M; ++i) {                          // larger buckets (warp-uniform trip count, rare): one entry at a time
+        uint32_t e1[EW];
+        lds_entry_lt<EW>(r.eb + i * (uint32_t)(EW * 4), i, r.cnt, e1);
+        const uint32_t ad = r.accp + e1[0];
+        const float cur = lds_acc_lt(ad, i, r.cnt);
+        sts_acc_lt(ad, entry_chain<G, 0>(e1, item.it + 1, cur) + entry_chain<G, 1>(e1, item.it + 1, 0.f), i, r.cnt);
+    }
+}
+
+constexpr int kLP_Threads = kLT_PT;     // 512: no separate producer warp (a 544-thread CTA is capped at 96 registers per thread, 512 at 128)
+
+template <int G>
+__global__ void __launch_bounds__(kLP_Threads, 1) lex_post_kernel(const __grid_constant__ LexTileArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[kLT_MaxStages];
+    __shared__ __align__(16) float tau_s[kLT_QT];
+
+    constexpr int EW = lt_entry_words(G);                                  // entry and item share the format {word 0, G fp16}
+    float* acc = (float*)smem;                                            // [QT][PT]
+    uint8_t* stages = smem + (size_t)kLT_QT * kLT_PT * 4;
+
+    const int qt = blockIdx.x % a.n_qtiles;
+    const int cta_in_q = blockIdx.x / a.n_qtiles;
+    const int ctas_per_q = gridDim.x / a.n_qtiles;
+    const int q0 = qt * kLT_QT;
+    const int nq = min(kLT_QT, a.n_queries - q0);
+    const int p = threadIdx.x;                                             // passage of this thread for init / filter; item slot for the walk
+    const uint32_t up = (uint32_t)p;
+
+    if (p == 0) {
+        for (int s = 0; s < a.n_stages; ++s) mbar_init(&full_bar[s], 1);
+        mbar_fence_init();
+    }
+    if (p < kLT_QT) tau_s[p] = p < nq ? a.tau[q0 + p] : INFINITY;
+    __syncthreads();
+
+    const long long tile0 = a.row_begin / kLT_PT;
+    const int my_tiles = cta_in_q < a.n_tiles ? (a.n_tiles - cta_in_q + ctas_per_q - 1) / ctas_per_q : 0;
+    const int n_work = my_tiles * a.n_chunks;                               // work item w = (tile w / n_chunks of this CTA, chunk w % n_chunks)
+    // The CTA is its own producer: all warps pass a CTA barrier after every slice, so when a chunk is done nobody reads its
+    // stage any more and thread 0 refills it with the chunk n_stages ahead (TMA bulk copies, completion on the stage's mbarrier).
+    auto issue = [&](int w) {
+        const int t = cta_in_q + (w / a.n_chunks) * ctas_per_q, c = w % a.n_chunks, s = w % a.n_stages;
+        const size_t blk = (size_t)(tile0 + t) * a.n_chunks + c;
+        const uint32_t qb = __ldg(a.qblock_bytes + (size_t)qt * a.n_chunks + c);
+        const uint32_t pb = __ldg(a.pblock_nbytes + blk);
+        uint8_t* dst = stages + (size_t)s * a.stage_bytes;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the stage's generic-proxy reads are done (barrier) before TMA rewrites it
+        mbar_arrive_expect_tx(&full_bar[s], pb + qb);
+        bulk_g2s(dst, a.lext + blk * (size_t)a.pblock_bytes, pb, &full_bar[s]);
+        bulk_g2s(dst + a.pblock_smem, a.qblocks + ((size_t)qt * a.n_chunks + c) * a.qblock_stride, qb, &full_bar[s]);
+    };
+    if (p == 0)
+        for (int w = 0; w < a.n_stages && w < n_work; ++w) issue(w);
+
+    const uint32_t per = (uint32_t)a.rt + 1u;
+    const uint32_t acc_s = smem_u32(acc);
+    const uint32_t stages_s = smem_u32(stages);
+    int w = 0;
+    for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q) {
+        const long long row = (tile0 + t) * kLT_PT + p;
+        const bool row_ok = row >= a.row_begin && row < a.row_end && row < a.n_rows;
+        if (a.scratch && row_ok) {
+            const float4* src = (const float4*)(a.scratch + (size_t)(row - a.scratch_row0) * a.scratch_slots + q0);
+#pragma unroll 1
+            for (int qb = 0; qb < kLT_QT / 4; qb += 8) {
+                float4 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = __ldcs(src + qb + i);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float* d = acc + (size_t)(4 * (qb + i)) * kLT_PT + p;
+                    d[0] = v[i].x; d[kLT_PT] = v[i].y; d[2 * kLT_PT] = v[i].z; d[3 * kLT_PT] = v[i].w;
+                }
+            }
+        } else {
+#pragma unroll 16
+            for (int q = 0; q < kLT_QT; ++q) acc[q * kLT_PT + p] = 0.f;
+        }
+        __syncthreads();                                                   // the walk touches every column of acc
+        for (int c = 0; c < a.n_chunks; ++c, ++w) {
+            const int s = w % a.n_stages;
+            mbar_wait(&full_bar[s], (uint32_t)(w / a.n_stages) & 1u);
+            const uint32_t st_s = stages_s + (uint32_t)s * (uint32_t)a.stage_bytes;
+            const uint32_t tab_s = st_s + (uint32_t)a.pblock_smem;
+            const uint32_t ent_s = tab_s + (uint32_t)a.qoff_bytes;
+            uint32_t hdr[kLT_SC];                                          // per slice: (first item << 16) | item count
+            {   // a C++ load: ordered behind the barrier wait by its memory clobber (every later stage read depends on it)
+                const uint4 hv = *(const uint4*)(stages + (size_t)s * a.stage_bytes);
+                hdr[0] = hv.x; hdr[1] = hv.y; hdr[2] = hv.z; hdr[3] = hv.w;
+            }
+            // Software pipeline over the four slices of the chunk.  Per slice: S1 item load -> S2 table word of its code -> S3 bucket
+            // size, warp maximum, first group of entries -> S4 accumulator read-modify-writes.  Only S4 touches acc and has to wait
+            // for the barrier that ends the previous slice; S1..S3 read stage data only and are issued ahead of their consumer (S3 of
+            // the next slice right before the barrier, so its entry loads fly across it): after a barrier the critical path is
+            // LDS acc -> FMA chain -> STS.
+            PItem<EW> i0, i1, i2, i3;
+            PRun r0, r1, r2, r3;
+            uint32_t en[kLP_Group][EW];
+            k1p_item<EW>(st_s, hdr[0], up, i0);
+            k1p_item<EW>(st_s, hdr[1], up, i1);
+            k1p_table<EW>(tab_s, 0u, hdr[0], up, i0);
+            k1p_bucket<EW>(ent_s, acc_s, i0, r0, en);
+            // slice 0
+            k1p_item<EW>(st_s, hdr[2], up, i2);
+            k1p_table<EW>(tab_s, per, hdr[1], up, i1);
+            k1p_update<G, EW>(r0, i0, en);
+            k1p_bucket<EW>(ent_s, acc_s, i1, r1, en);
+            __syncthreads();
+            // slice 1
+            k1p_item<EW>(st_s, hdr[3], up, i3);
+            k1p_table<EW>(tab_s, 2u * per, hdr[2], up, i2);
+            k1p_update<G, EW>(r1, i1, en);
+            k1p_bucket<EW>(ent_s, acc_s, i2, r2, en);
+            __syncthreads();
+            // slice 2
+            k1p_table<EW>(tab_s, 3u * per, hdr[3], up, i3);
+            k1p_update<G, EW>(r2, i2, en);
+            k1p_bucket<EW>(ent_s, acc_s, i3, r3, en);
+            __syncthreads();
+            // slice 3
+            k1p_update<G, EW>(r3, i3, en);
+            __syncthreads();                                               // chunk done by every warp: its stage may be refilled
+            if (p == 0 && w + a.n_stages < n_work) issue(w + a.n_stages);
+        }
+        // admission filter (thread p = passage p again; the barrier above ordered all accumulator writes)
+        if (row_ok) {
+#pragma unroll 1
+            for (int qb = 0; qb < nq; qb += 4) {
+                const float4 tq = *(const float4*)(tau_s + qb);
+                const float tv[4] = {tq.x, tq.y, tq.z, tq.w};
+                float sv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) sv[i] = acc[(qb + i) * kLT_PT + p] + 0.0f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (sv[i] > tv[i]) {
+                        const int slot = q0 + qb + i;
+                        const uint32_t pos = atomicAdd(a.cnt + slot, 1u);
+                        if (pos < (uint32_t)a.cap) {
+                            a.cand_score[(size_t)slot * a.cap + pos] = sv[i];
+                            a.cand_row[(size_t)slot * a.cap + pos] = (int32_t)row;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
+// postings layout: block = 16-byte header (4 x {first item << 16 | count}) + up to 4 x 512 items of lt_entry_words(G) words
+LexTileGeom lex_post_geom(const Geometry& g, int rt) {
+    LexTileGeom t = lex_tile_geom(g, rt);
+    t.pblock_bytes = (int)round_up(16 + (int64_t)kLT_PT * kLT_SC * lt_entry_words(g.G) * 4, 128);
+    t.stage_bytes = t.pblock_bytes + (int)round_up(t.qblock_stride, 128);
+    const size_t fixed = (size_t)kLT_QT * kLT_PT * 4 + 128 + kLT_StaticSmem;
+    t.n_stages = kLT_MaxStages;
+    while (t.n_stages > 1 && fixed + (size_t)t.n_stages * t.stage_bytes > kLT_SmemBudget) --t.n_stages;
+    return t;
+}
+
+bool lex_post_supported(const Geometry& g, int rt) {
+    if (g.S_pad <= 0 || g.S_pad % kLT_SC != 0 || rt < 1 || rt > 254 || g.G > 8) return false;   // 8-bit codes only
+    const LexTileGeom t = lex_post_geom(g, rt);
+    return t.n_stages >= 2;
+}
+
+template <int G>
+static int launch_lex_post_t(const dhr_index* h, const LexTileArgs& a, size_t smem, cudaStream_t st) {
+    auto kern = lex_post_kernel<G>;
+    DHR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_q = h->num_sms / a.n_qtiles;
+    if (per_q < 1) per_q = 1;
+    if (per_q > a.n_tiles) per_q = a.n_tiles;
+    kern<<<(unsigned)(per_q * a.n_qtiles), kLP_Threads, smem, st>>>(a);
+    DHR_CUDA(cudaGetLastError());
+    return DHR_OK;
+}
+
+int launch_lex_post(const dhr_index* h, const LexTileGeom& t, const uint8_t* qblocks, const uint32_t* qblock_bytes, int n_queries,
+                    long long row_begin, long long row_end, const float* scratch, long long scratch_slots, long long scratch_row0,
+                    const TopkState& tk, int cap, cudaStream_t st) {
+    if (row_end <= row_begin || n_queries <= 0) return DHR_OK;
+    if (!h->lexp) return DHR_ERR_STATE;
+    LexTileArgs a{};
+    a.lext = h->lexp; a.qblocks = qblocks; a.qblock_bytes = qblock_bytes; a.pblock_nbytes = h->lexp_nbytes;
+    a.row_begin = row_begin; a.row_end = row_end; a.n_rows = h->n_rows;
+    a.n_tiles = (int)((row_end - row_begin / kLT_PT * kLT_PT + kLT_PT - 1) / kLT_PT);
+    a.n_chunks = t.n_chunks; a.rt = t.rt; a.n_stages = t.n_stages;
+    a.pblock_bytes = t.pblock_bytes; a.qoff_bytes = t.qoff_bytes; a.qblock_stride = t.qblock_stride;
+    a.stage_bytes = t.stage_bytes; a.pblock_smem = t.pblock_bytes;
+    a.n_qtiles = (n_queries + kLT_QT - 1) / kLT_QT;
+    a.n_queries = n_queries;
+    a.scratch = scratch; a.scratch_slots = scratch_slots; a.scratch_row0 = scratch_row0;
+    a.tau = tk.tau; a.cnt = tk.cnt; a.cand_score = tk.cand_score; a.cand_row = tk.cand_row; a.cap = cap;
+    const size_t smem = (size_t)kLT_QT * kLT_PT * 4 + (size_t)t.n_stages * t.stage_bytes + 128;
+    switch (h->g.G) {
+        case 1: return launch_lex_post_t<1>(h, a, smem, st);
+        case 2: return launch_lex_post_t<2>(h, a, smem, st);
+        case 3: return launch_lex_post_t<3>(h, a, smem, st);
+        case 4: return launch_lex_post_t<4>(h, a, smem, st);
+        case 5: return launch_lex_post_t<5>(h, a, smem, st);
+        case 6: return launch_lex_post_t<6>(h, a, smem, st);
+        case 7: return launch_lex_post_t<7>(h, a, smem, st);
+        case 8: return launch_lex_post_t<8>(h, a, smem, st);
+        default: return DHR_ERR_UNSUPPORTED;
+    }
+}
+
+int lex_post_entry_words(int G) { return lt_entry_words(G); }
+
 int launch_lex_tile_prep(const dhr_index* h, const LexTileGeom& t, const void* q_lex16, const void* q_code, int n_queries,
                          uint8_t* qblocks, uint32_t* qblock_bytes, cudaStream_t st) {
     const Geometry& g = h->g;

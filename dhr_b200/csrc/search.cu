@@ -432,8 +432,12 @@ static int run_batch_hybrid_tile(dhr_index* h, const LexTileGeom& lt, const Quer
                     if (ks != st) { DHR_CUDA(cudaEventRecord(ln.ev_k2_done[b], st)); DHR_CUDA(cudaStreamWaitEvent(ks, ln.ev_k2_done[b], 0)); }
                 }
             }
-            DHR_TRY(launch_lex_tile(h, lt, qblocks, qbytes, nq, r0, r1, dense ? ln.scratch + (k2_overlap ? b * sc_half : 0) : nullptr, kMaxInflight,
-                                    r0, t, kCandCap, ks));
+            if (h->lexp)
+                DHR_TRY(launch_lex_post(h, lt, qblocks, qbytes, nq, r0, r1, dense ? ln.scratch + (k2_overlap ? b * sc_half : 0) : nullptr, kMaxInflight,
+                                        r0, t, kCandCap, ks));
+            else
+                DHR_TRY(launch_lex_tile(h, lt, qblocks, qbytes, nq, r0, r1, dense ? ln.scratch + (k2_overlap ? b * sc_half : 0) : nullptr, kMaxInflight,
+                                        r0, t, kCandCap, ks));
             if (overlap) DHR_CUDA(cudaEventRecord(ln.ev_k1_done[b], ks));
             if (ks != st) used_aux2 = true;
             h->stats.n_kernel_launches++;
@@ -465,6 +469,7 @@ static int run_batch_hybrid_tile(dhr_index* h, const LexTileGeom& lt, const Quer
         h->stats.n_kernel_launches++;
     }
     h->stats.scan_variant = 3;
+    h->stats.lex_layout = h->lexp ? 1.0 : 0.0;
     return DHR_OK;
 }
 
@@ -634,11 +639,12 @@ static int enqueue_search(dhr_index* h, const SearchRequest& r, SelectOut so, bo
     const bool tile_dense = h->opt_tile_mode && g.S == 0 && !qs.f32 && dense_tile_supported(g, nullptr);
     if (tile_dense) { slots = kMaxInflight; qb = 64; groups = kMaxInflight / 64; }
     const int rt = std::max(1, h->max_code + 1);
-    const bool tile_hybrid = h->opt_tile_mode && g.S > 0 && r.masked && !qs.f32 && h->lext && lex_tile_supported(g, rt) &&
+    const bool post = h->lexp && lex_post_supported(g, rt);                // postings layout -> K1p, tiled layout -> K1t
+    const bool tile_hybrid = h->opt_tile_mode && g.S > 0 && r.masked && !qs.f32 && (post || (h->lext && lex_tile_supported(g, rt))) &&
                              (g.C_pad == 0 || dense_tile_supported(g, nullptr));
     LexTileGeom lt{};
     if (tile_hybrid) {
-        lt = lex_tile_geom(g, rt);
+        lt = post ? lex_post_geom(g, rt) : lex_tile_geom(g, rt);
         DHR_TRY(ensure_tile_workspace(h, lt, n_queries));
         DHR_TRY(ensure_lane(h, 0, g.C_pad > 0));
         DHR_TRY(launch_lex_tile_prep(h, lt, h->q_lex16, h->q_code, n_queries, h->qblocks, h->qblock_bytes, st));

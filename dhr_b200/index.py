@@ -72,19 +72,19 @@ class GipIndex:
     """One corpus shard resident in the HBM of one GPU."""
 
     def __init__(self, n_slices, n_dense, group=1, capacity=0, idx_dtype=np.uint8, device=0, row_offset=0,
-                 narrow_codes=False, keep_rowmajor=False):
+                 narrow_codes=False, keep_rowmajor=False, lex_postings=False):
         self._h = ctypes.c_void_p()
         self.n_slices, self.n_dense, self.group = int(n_slices), int(n_dense), int(group)
         self.device, self.row_offset = int(device), int(row_offset)
         self.width = self.n_slices * self.group + self.n_dense
         code = C.IDX_NONE if n_slices == 0 else _NP_IDX[np.dtype(idx_dtype)]
-        flags = (C.INDEX_NARROW_CODES if narrow_codes else 0) | (C.INDEX_KEEP_ROWMAJOR if keep_rowmajor else 0)
+        flags = (C.INDEX_NARROW_CODES if narrow_codes else 0) | (C.INDEX_KEEP_ROWMAJOR if keep_rowmajor else 0) | (C.INDEX_LEX_POSTINGS if lex_postings else 0)
         C.check(C.lib().dhr_index_create(ctypes.byref(self._h), self.device, int(capacity), self.n_slices, self.group,
                                          self.n_dense, code, self.row_offset, flags), 'dhr_index_create')
 
     # ---- construction --------------------------------------------------------------------------
     @classmethod
-    def from_arrays(cls, vals, idx, n_slices=None, group=1, device=0, row_offset=0, narrow_codes=False, keep_rowmajor=False):
+    def from_arrays(cls, vals, idx, n_slices=None, group=1, device=0, row_offset=0, narrow_codes=False, keep_rowmajor=False, lex_postings=False):
         """vals [N, S*G + C] fp16/fp32, idx [N, S] integer array or None / 0 (dense-only index,
         the reference stores None or 0 there: encode.py:149-153, index.py:40-43)."""
         v = _Arr(vals, 'val')
@@ -99,7 +99,7 @@ class GipIndex:
         if C_ < 0:
             raise ValueError('values have %d columns but n_slices*group = %d' % (v.shape[1], S * group))
         self = cls(S, C_, group, capacity=v.shape[0], idx_dtype=np_dtype, device=device, row_offset=row_offset,
-                   narrow_codes=narrow_codes, keep_rowmajor=keep_rowmajor)
+                   narrow_codes=narrow_codes, keep_rowmajor=keep_rowmajor, lex_postings=lex_postings)
         self.append(vals, idx if has_idx else None)
         self.finalize()
         return self

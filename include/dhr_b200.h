@@ -55,6 +55,9 @@ extern "C" {
 
 /* dhr_index_create flags */
 #define DHR_INDEX_NARROW_CODES 1u /* store 16-bit slice indices as 8-bit codes (all values must be < 254) */
+#define DHR_INDEX_LEX_POSTINGS 4u  /* experimental: keep the lexical part as per-(tile, slice) postings sorted by code (kernel K1p)
+                                      instead of the tiled layout of the passage-per-thread kernel K1t; 8-bit codes only.
+                                      Parity-tested, measured slower than K1t, hence opt-in */
 #define DHR_INDEX_KEEP_ROWMAJOR 2u /* keep the row-major arrays resident after finalize (default: only the tiled copies stay;
                                       the row-major ones are rebuilt on the first call that needs them) */
 
@@ -81,6 +84,7 @@ typedef struct dhr_stats {
     double   corpus_passes;      /* logical corpus passes made by the scan launches (sum rows*groups / N) */
     double   bytes_per_pass;     /* N * row_bytes of the HBM-resident layout                         */
     double   dense_flops;        /* 2 * Q * N * C issued to the tensor-core kernel K2 by the call        */
+    double   lex_layout;         /* tile path: 0 = tiled lexical copy (K1t), 1 = postings (K1p)                           */
     double   alg_bytes;          /* algorithmic bytes of the scan launches: K1 rows*row_bytes per group of QB queries, K1t
                                     rows*(lexical value + code bytes) per tile of 64 queries, K2 rows*C_pad*2 per 128 queries */
 } dhr_stats;

@@ -19,7 +19,7 @@ if has_cuda():
 def configure(ix, mode, qb=None):
     """mode: 'scan0' / 'scan1' = row-scan kernel K1 (direct loads / TMA bulk staging), 'tile' = tensor-core +
     bucketed tile kernels (K2 + K1t) when the shape allows (falls back to K1 otherwise)."""
-    if mode == 'tile':
+    if mode in ('tile', 'tile_p'):
         ix.set_option('tile_mode', 1)
     else:
         ix.set_option('tile_mode', 0)
@@ -28,7 +28,11 @@ def configure(ix, mode, qb=None):
         ix.set_option('query_block', qb)
 
 
-MODES = ['scan0', 'scan1', 'tile']
+MODES = ['scan0', 'scan1', 'tile', 'tile_p']     # tile = tiled lexical layout (K1t), tile_p = experimental postings layout (K1p)
+
+
+def postings(variant):
+    return variant == 'tile_p'
 
 
 def _golden_queries(g):
@@ -48,7 +52,7 @@ def test_golden_grid_bit_exact(name, variant):
     g = load_golden(name)
     S, G, k = int(g['S']), int(g['G']), int(g['topk'])
     lam = float(g['lamda']) if 'lamda' in g else 1.0
-    with GipIndex.from_arrays(g['c_vals'], g['c_idx'], n_slices=S, group=G) as ix:
+    with GipIndex.from_arrays(g['c_vals'], g['c_idx'], n_slices=S, group=G, lex_postings=postings(variant)) as ix:
         configure(ix, variant)
         scores, rows, counts = ix.search(_golden_queries(g), g['q_idx'], k, lamda=lam)
     assert np.array_equal(scores.astype(np.float64), g['ref_scores'])
@@ -62,7 +66,7 @@ def test_golden_grid_bit_exact(name, variant):
 def test_golden_gauss_within_tolerance(variant):
     g = load_golden('delade_g1_u8_gauss')
     S, G, k = int(g['S']), int(g['G']), int(g['topk'])
-    with GipIndex.from_arrays(g['c_vals'], g['c_idx'], n_slices=S, group=G) as ix:
+    with GipIndex.from_arrays(g['c_vals'], g['c_idx'], n_slices=S, group=G, lex_postings=postings(variant)) as ix:
         configure(ix, variant)
         scores, rows, counts = ix.search(_golden_queries(g), g['q_idx'], k)
     assert np.abs(scores - g['ref_scores']).max() < 1e-3          # north_star tolerance
@@ -106,11 +110,11 @@ SHAPES = [
 @pytest.mark.parametrize('shape', SHAPES)
 def test_oracle_parity_shapes(shape, qb, variant):
     S, G, Cd, R, cdt, qdt = shape
-    if variant == 'tile' and qb != 1:
+    if variant in ('tile', 'tile_p') and qb != 1:
         pytest.skip('query_block only applies to the row scan')
     case = make_case(100 + S + G + Cd, 3000, 11, S, G, Cd, R, cdt, qdt)
     k = 100
-    with GipIndex.from_arrays(case['c_vals'], case['c_idx'] if S else None, n_slices=S, group=G) as ix:
+    with GipIndex.from_arrays(case['c_vals'], case['c_idx'] if S else None, n_slices=S, group=G, lex_postings=postings(variant)) as ix:
         configure(ix, variant, qb)
         scores, rows, counts = ix.search(case['q_vals'], case['q_idx'] if S else None, k)
     assert_matches_oracle(case, scores, rows, counts, k)
@@ -121,7 +125,7 @@ def test_oracle_parity_shapes(shape, qb, variant):
 def test_fp32_queries_lamda_and_unmasked(qb, variant):
     case = make_case(7, 4000, 9, 64, 3, 40, 39, np.uint8, np.int16, q_fp32_noise=True)
     k = 50
-    with GipIndex.from_arrays(case['c_vals'], case['c_idx'], n_slices=64, group=3) as ix:
+    with GipIndex.from_arrays(case['c_vals'], case['c_idx'], n_slices=64, group=3, lex_postings=postings(variant)) as ix:
         configure(ix, variant, qb)
         s1, r1, c1 = ix.search(case['q_vals'], case['q_idx'], k, lamda=0.37)
         s2, r2, c2 = ix.search(case['q_vals'], None, k, masked=False)
@@ -142,7 +146,10 @@ def test_grid_many_shapes_bit_exact():
                     outs.append(ix.search(case['q_vals'], case['q_idx'], k))
             configure(ix, 'tile')
             outs.append(ix.search(case['q_vals'], case['q_idx'], k))
-            assert ix.stats()['scan_variant'] == 3, 'tile path not taken'
+            assert ix.stats()['scan_variant'] == 3 and ix.stats()['lex_layout'] == 0, 'tiled tile path not taken'
+        with GipIndex.from_arrays(case['c_vals'], case['c_idx'], n_slices=S, group=G, lex_postings=True) as ix:
+            outs.append(ix.search(case['q_vals'], case['q_idx'], k))
+            assert ix.stats()['scan_variant'] == 3 and ix.stats()['lex_layout'] == 1, 'postings tile path not taken'
         assert_matches_oracle(case, *outs[0], k, exact=True)
         for o in outs[1:]:
             assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])
@@ -329,12 +336,13 @@ def test_dense_tile_grid_bit_exact_and_ties():
                                    # index range > 254: 16-bit codes in the tiled copy, distinct-code lookup ("wide" layout)
                                    (64, 3, 0, 3466, np.uint16), (32, 6, 64, 300, np.int16), (128, 1, 0, 1000, np.int16),
                                    (20, 2, 24, 40000, np.int32), (16, 5, 16, 500, np.uint16)])
-def test_tile_path_many_queries(shape):
+@pytest.mark.parametrize('layout', ['postings', 'tiled'])
+def test_tile_path_many_queries(shape, layout):
     """Tile kernels with several query tiles in flight (300 queries -> 5 tiles of 64, two super-batches of 256)."""
     S, G, Cd, R, cdt = shape
     case = make_case(900 + S + G, 60000, 300, S, G, Cd, R, cdt, cdt)
     k = 100
-    with GipIndex.from_arrays(case['c_vals'], case['c_idx'], n_slices=S, group=G) as ix:
+    with GipIndex.from_arrays(case['c_vals'], case['c_idx'], n_slices=S, group=G, lex_postings=layout == 'postings') as ix:
         configure(ix, 'tile')
         s, r, c = ix.search(case['q_vals'], case['q_idx'], k)
         # shapes whose stage does not fit the K1t shared-memory budget (large G) fall back to the row scan

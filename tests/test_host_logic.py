@@ -34,7 +34,7 @@ def test_constants_match_header():
                       ('DHR_IDX_I32', C.IDX_I32), ('DHR_IDX_I64', C.IDX_I64), ('DHR_VAL_F16', C.VAL_F16), ('DHR_VAL_F32', C.VAL_F32),
                       ('DHR_ERR_LOSSY', C.ERR_LOSSY), ('DHR_ERR_IDX_RANGE', C.ERR_IDX_RANGE), ('DHR_ERR_NO_DEVICE', C.ERR_NO_DEVICE)]:
         assert int(defs[name]) == val
-    assert ctypes.sizeof(C.DhrStats) == 10 * 4 + 7 * 8
+    assert ctypes.sizeof(C.DhrStats) == 10 * 4 + 8 * 8
     assert int(defs['DHR_INDEX_KEEP_ROWMAJOR']) == C.INDEX_KEEP_ROWMAJOR and int(defs['DHR_INDEX_NARROW_CODES']) == C.INDEX_NARROW_CODES
 
 

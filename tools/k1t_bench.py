@@ -23,11 +23,12 @@ ap.add_argument('--topk', type=int, default=1000)
 ap.add_argument('--reps', type=int, default=5)
 ap.add_argument('--option', action='append', default=[])
 ap.add_argument('--no-check', action='store_true')
+ap.add_argument('--lex-postings', action='store_true', help='experimental postings lexical layout (K1p) instead of the tiled one (K1t)')
 a = ap.parse_args()
 
 cfg = synth.CONFIGS[a.workload]
 dev = torch.device('cuda', 0)
-ix = GipIndex(cfg['S'], cfg['C'], cfg['G'], capacity=a.rows, idx_dtype=np.dtype(cfg['idx']), device=0)
+ix = GipIndex(cfg['S'], cfg['C'], cfg['G'], capacity=a.rows, idx_dtype=np.dtype(cfg['idx']), device=0, lex_postings=a.lex_postings)
 for v, i in synth.corpus_torch_segments(a.workload, 0, a.rows, dev):
     ix.append(v, i)
 ix.finalize()
@@ -45,7 +46,7 @@ for r in range(a.reps + 2):
         best = st
 res = {'workload': a.workload, 'rows': a.rows, 'queries': a.queries, 'scan_ms': best['scan_ms'], 'select_ms': best['select_ms'],
        'total_ms': best['total_ms'], 'scan_launches': best['n_scan_launches'], 'us_per_scan_launch': 1e3 * best['scan_ms'] / max(1, best['n_scan_launches']),
-       'scan_variant': best['scan_variant'], 'q_per_s_at_8p8M': a.queries / (best['total_ms'] / 1e3) * a.rows / synth.N_MSMARCO}
+       'scan_variant': best['scan_variant'], 'lex_layout': best['lex_layout'], 'q_per_s_at_8p8M': a.queries / (best['total_ms'] / 1e3) * a.rows / synth.N_MSMARCO}
 if not a.no_check:
     n = min(16, a.queries)
     ix.set_option('tile_mode', 0)
