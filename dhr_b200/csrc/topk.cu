@@ -52,7 +52,8 @@ topk_select_kernel(TopkState t, int k, int cap, int final_pass, const SelectOut 
     __shared__ uint32_t whist[kSelectThreads / 32][256];              // one histogram per warp
     __shared__ uint32_t hist[256];
     __shared__ uint32_t wtot[kSelectThreads / 32];
-    __shared__ uint32_t sh_digit, sh_need;
+    __shared__ uint32_t sh_digit, sh_need, sh_bin;
+    __shared__ unsigned long long wmin[kSelectThreads / 32];
     const int slot = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t raw = t.cnt[slot];
@@ -107,7 +108,7 @@ topk_select_kernel(TopkState t, int k, int cap, int final_pass, const SelectOut 
 #pragma unroll
                     for (int b = 7; b >= 0; --b) {
                         if (rem != 0u) {
-                            if (c[b] >= rem) { d = lane * 8 + b; sh_need = rem; rem = 0u; }
+                            if (c[b] >= rem) { d = lane * 8 + b; sh_need = rem; sh_bin = c[b]; rem = 0u; }
                             else rem -= c[b];
                         }
                     }
@@ -117,6 +118,10 @@ topk_select_kernel(TopkState t, int k, int cap, int final_pass, const SelectOut 
             __syncthreads();
             prefix = (prefix << 8) | (unsigned long long)sh_digit;
             need = sh_need;
+            if (sh_bin == need) {                                        // the whole bin is kept: every key >= prefix followed by zeros is
+                prefix <<= shift;                                        // in the top k, the remaining digits need not be resolved
+                break;                                                   // (block-uniform: sh_bin / sh_need are shared)
+            }
         }
         kth = prefix;
     }
@@ -153,7 +158,23 @@ topk_select_kernel(TopkState t, int k, int cap, int final_pass, const SelectOut 
             if (pos < (uint32_t)m) keys[pos] = r[j];                       // keys are unique for scans; duplicated rerank candidates must not run past m
             ++pos;
         }
-    bitonic_sort_desc(keys, m, tid, kSelectThreads);
+    // Intermediate passes only need the SET of kept candidates and the k-th best score: no sort.  The k-th key is the minimum
+    // of the kept keys (the radix select may have stopped early, so `kth` itself need not be a key).
+    unsigned long long kmin = ~0ull;
+    if (!final_pass) {
+#pragma unroll
+        for (int j = 0; j < kSelectKeysPerThread; ++j)
+            if (tid + j * kSelectThreads < n && r[j] >= kth) kmin = r[j] < kmin ? r[j] : kmin;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned long long o2 = __shfl_xor_sync(0xFFFFFFFFu, kmin, off);
+            kmin = o2 < kmin ? o2 : kmin;
+        }
+        if (lane == 0) wmin[warp] = kmin;
+        __syncthreads();
+    } else {
+        bitonic_sort_desc(keys, m, tid, kSelectThreads);
+    }
     for (int i = tid; i < keep; i += kSelectThreads) {
         const unsigned long long key = keys[i];
         cs[i] = key_score(key);
@@ -166,8 +187,10 @@ topk_select_kernel(TopkState t, int k, int cap, int final_pass, const SelectOut 
             t.cnt[slot] = 0u; t.tau[slot] = -INFINITY; t.overflow[slot] = 0u;
             if (o.overflow && overflowed) o.overflow[out_base + slot] = 1u;
         } else {
+            unsigned long long km = wmin[0];
+            for (int w = 1; w < kSelectThreads / 32; ++w) km = wmin[w] < km ? wmin[w] : km;
             t.cnt[slot] = (uint32_t)keep;
-            t.tau[slot] = (n >= k) ? key_score(keys[k - 1]) : -INFINITY;
+            t.tau[slot] = (n >= k) ? key_score(km) : -INFINITY;
             t.overflow[slot] = overflowed ? 1u : 0u;
         }
     }
