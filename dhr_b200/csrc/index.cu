@@ -135,7 +135,7 @@ __global__ void ingest_dense_kernel(long long n, int D, int C, int C_pad, int va
 //   [tile of 512 rows][chunk of 4 slices]{ codes TCode [512][4] | vals fp16 [4][512][G] }
 // TCode is uint8 when the largest stored code is <= 253 (CODE_EMPTY/NOMATCH map to 0xFF), else uint16 (0xFFFF).
 template <typename CodeT, typename TCode>
-__global__ void build_lext_kernel(long long n_rows, long long n_rows_pad, int S_pad, int G, const __half* __restrict__ lexv,
+__global__ void build_lext_kernel(long long n_rows, long long n_rows_pad, int S_pad, int G, uint32_t empty_code, const __half* __restrict__ lexv,
                                   const CodeT* __restrict__ lexi, uint8_t* __restrict__ lext) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_rows_pad * S_pad) return;
@@ -147,7 +147,9 @@ __global__ void build_lext_kernel(long long n_rows, long long n_rows_pad, int S_
     uint8_t* blk = lext + ((size_t)tile * (S_pad / kLexTileSlices) + chunk) * pblock;
     TCode* tc = (TCode*)blk + (size_t)tp * kLexTileSlices + tj;
     __half* tv = (__half*)(blk + (size_t)kLexTileRows * kLexTileSlices * sizeof(TCode)) + ((size_t)tj * kLexTileRows + tp) * G;
-    constexpr uint32_t kTEmpty = sizeof(TCode) == 1 ? 0xFFu : 0xFFFFu;
+    // empty slices store `empty_code`: the narrow layout uses rt (= largest code + 1), the index of the always-empty bucket of the
+    // query tables, so K1t needs no clamp; the wide layout uses 0xFFFF, which no query code equals
+    const uint32_t kTEmpty = empty_code;
     if (r >= n_rows) {
         *tc = (TCode)kTEmpty;
         for (int g = 0; g < G; ++g) tv[g] = __float2half_rn(0.f);
@@ -264,7 +266,7 @@ __global__ void build_dnst_kernel(long long n_rows, long long n_rows_pad, int C_
 
 // inverse of build_lext_kernel / build_dnst_kernel: rebuild the row-major arrays from the tiled copies (option "rowmajor")
 template <typename CodeT, typename TCode>
-__global__ void unbuild_lext_kernel(long long n_rows, int S_pad, int G, const uint8_t* __restrict__ lext, __half* __restrict__ lexv,
+__global__ void unbuild_lext_kernel(long long n_rows, int S_pad, int G, uint32_t empty_code, const uint8_t* __restrict__ lext, __half* __restrict__ lexv,
                                     CodeT* __restrict__ lexi) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_rows * S_pad) return;
@@ -276,7 +278,7 @@ __global__ void unbuild_lext_kernel(long long n_rows, int S_pad, int G, const ui
     const uint8_t* blk = lext + ((size_t)tile * (S_pad / kLexTileSlices) + chunk) * pblock;
     const TCode tc = ((const TCode*)blk)[(size_t)tp * kLexTileSlices + tj];
     const __half* tv = (const __half*)(blk + (size_t)kLexTileRows * kLexTileSlices * sizeof(TCode)) + ((size_t)tj * kLexTileRows + tp) * G;
-    constexpr uint32_t kTEmpty = sizeof(TCode) == 1 ? 0xFFu : 0xFFFFu;
+    const uint32_t kTEmpty = empty_code;
     lexi[(size_t)r * S_pad + s] = (uint32_t)tc == kTEmpty ? (CodeT)CodeTraits<CodeT>::kEmpty : (CodeT)tc;
     __half* dst = lexv + ((size_t)r * S_pad + s) * G;
     for (int g = 0; g < G; ++g) dst[g] = tv[g];
@@ -339,9 +341,9 @@ int ensure_rowmajor(dhr_index* h) {
                 fill_empty_lexical_kernel<uint16_t><<<blocks, 256>>>(total, g.G, h->lexv, (uint16_t*)h->lexi);
                 unbuild_lexp_kernel<uint16_t><<<grid, kLexTileRows>>>(h->n_rows, g.S_pad, g.G, EW, lp.pblock_bytes, h->lexp, h->lexv, (uint16_t*)h->lexi);
             }
-        } else if (wide) unbuild_lext_kernel<uint16_t, uint16_t><<<blocks, 256>>>(h->n_rows, g.S_pad, g.G, h->lext, h->lexv, (uint16_t*)h->lexi);
-        else if (g.code_bytes == 1) unbuild_lext_kernel<uint8_t, uint8_t><<<blocks, 256>>>(h->n_rows, g.S_pad, g.G, h->lext, h->lexv, (uint8_t*)h->lexi);
-        else unbuild_lext_kernel<uint16_t, uint8_t><<<blocks, 256>>>(h->n_rows, g.S_pad, g.G, h->lext, h->lexv, (uint16_t*)h->lexi);
+        } else if (wide) unbuild_lext_kernel<uint16_t, uint16_t><<<blocks, 256>>>(h->n_rows, g.S_pad, g.G, 0xFFFFu, h->lext, h->lexv, (uint16_t*)h->lexi);
+        else if (g.code_bytes == 1) unbuild_lext_kernel<uint8_t, uint8_t><<<blocks, 256>>>(h->n_rows, g.S_pad, g.G, (uint32_t)std::max(1, h->max_code + 1), h->lext, h->lexv, (uint8_t*)h->lexi);
+        else unbuild_lext_kernel<uint16_t, uint8_t><<<blocks, 256>>>(h->n_rows, g.S_pad, g.G, (uint32_t)std::max(1, h->max_code + 1), h->lext, h->lexv, (uint16_t*)h->lexi);
         DHR_CUDA(cudaGetLastError());
     }
     if (g.C_pad > 0 && !h->dns) {
@@ -557,11 +559,11 @@ int dhr_index_finalize(dhr_index* h) {
             const long long total = rows_pad * g.S_pad;
             const unsigned blocks = (unsigned)((total + 255) / 256);
             if (lt.wide)
-                build_lext_kernel<uint16_t, uint16_t><<<blocks, 256>>>(h->n_rows, rows_pad, g.S_pad, g.G, h->lexv, (const uint16_t*)h->lexi, h->lext);
+                build_lext_kernel<uint16_t, uint16_t><<<blocks, 256>>>(h->n_rows, rows_pad, g.S_pad, g.G, 0xFFFFu, h->lexv, (const uint16_t*)h->lexi, h->lext);
             else if (g.code_bytes == 1)
-                build_lext_kernel<uint8_t, uint8_t><<<blocks, 256>>>(h->n_rows, rows_pad, g.S_pad, g.G, h->lexv, (const uint8_t*)h->lexi, h->lext);
+                build_lext_kernel<uint8_t, uint8_t><<<blocks, 256>>>(h->n_rows, rows_pad, g.S_pad, g.G, (uint32_t)rt_fin, h->lexv, (const uint8_t*)h->lexi, h->lext);
             else
-                build_lext_kernel<uint16_t, uint8_t><<<blocks, 256>>>(h->n_rows, rows_pad, g.S_pad, g.G, h->lexv, (const uint16_t*)h->lexi, h->lext);
+                build_lext_kernel<uint16_t, uint8_t><<<blocks, 256>>>(h->n_rows, rows_pad, g.S_pad, g.G, (uint32_t)rt_fin, h->lexv, (const uint16_t*)h->lexi, h->lext);
             DHR_CUDA(cudaGetLastError());
             DHR_CUDA(cudaDeviceSynchronize());
         }

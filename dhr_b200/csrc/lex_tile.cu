@@ -438,8 +438,8 @@ __global__ void __launch_bounds__(kLT_Threads, kLT_CtasPerSm) lex_tile_kernel(co
                 const uint32_t* tab = (const uint32_t*)(st + a.pblock_smem);
                 const uint32_t cw = *(const uint32_t*)(st + (size_t)p * kLT_SC);       // my four slice codes (one byte each)
 #pragma unroll
-                for (int j = 0; j < kLT_SC; ++j) {
-                    const uint32_t code = min((cw >> (8 * j)) & 0xFFu, (uint32_t)a.rt);
+                for (int j = 0; j < kLT_SC; ++j) {                           // empty slices store code rt = the always-empty bucket (no clamp)
+                    const uint32_t code = __byte_perm(cw, 0u, 0x4440u + j);
                     tw[j] = tab[j * per + code];
                 }
             }

@@ -1,4 +1,3 @@
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-timeout 200 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_sel.json 2>gpurun_out/r2_bench_sel.err
-python -c "
-import json; d=json.load(open('gpurun_out/r2_bench_sel.json')); print('n1', d['value'], d['ms_per_step'], d['verified']['ok'], d['roofline']['select_stream_ms_per_step'])"
+for w in delade_lex delade_ref_lex delade_cls; do
+timeout 120 python tools/k1t_bench.py --workload $w 2>&1 | tail -1 | cut -c1-200
+done
