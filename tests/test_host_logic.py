@@ -306,3 +306,28 @@ def test_packed_keys_roundtrip_and_order():
     assert np.array_equal(order, expect)
     pad = pack_keys(np.float32([1.0]), np.int64([-1]))
     assert pad[0] == 0 and unpack_keys(pad)[1][0] == -1 and np.isneginf(unpack_keys(pad)[0][0])
+
+
+def test_trec_writer_longest_admitted_ids_and_limits(tmp_path):
+    """a 500-character query id, a 399-character docid and a 250-character run name used to overrun the line
+    buffer of dhr_write_trec.  The admitted maxima (512 / 400 / 256) format correctly; anything longer is rejected."""
+    from dhr_b200.gip_retrieval import write_trec_arrays
+    from dhr_b200 import _cabi as C
+    qids = ['q' * 500, 'short']
+    docids = ['d' * 399, 'e' * 400, 'x']
+    rows = np.array([[0, 1, 2], [2, 1, -1]], np.int64)
+    scores = np.array([[3.5, 2.25, -1.0], [0.1, 1e-5, 0.0]], np.float32)
+    out = str(tmp_path / 'long.trec')
+    run = 'r' * 256
+    n = write_trec_arrays(out, qids, scores, rows, None, docids, run)
+    assert n == 5
+    lines = open(out).read().splitlines()
+    exp = ['{} Q0 {} {} {} {}'.format(qids[q], docids[rows[q, r]], r + 1, float(scores[q, r]), run)
+           for q in range(2) for r in range(3) if rows[q, r] >= 0]
+    assert lines == exp
+    with pytest.raises(C.DhrError):
+        write_trec_arrays(out, qids, scores, rows, None, docids, 'r' * 257)
+    with pytest.raises(C.DhrError):
+        write_trec_arrays(out, ['q' * 513, 'short'], scores, rows, None, docids, 'run')
+    with pytest.raises(C.DhrError):
+        write_trec_arrays(out, qids, scores, rows, None, ['d' * 401, 'e', 'x'], 'run')
