@@ -317,6 +317,7 @@ struct DenseTsArgs {
     float* scratch;                    // [row - scratch_row0][scratch_slots]  (modes 1-3)
     long long scratch_slots;
     float* tau; uint32_t* cnt; float* cand_score; int32_t* cand_row; int cap;
+    float* seg_score; int32_t* seg_row; uint32_t* seg_cnt;   // segmented candidate lists (filter modes) or nullptr: append with atomics
 };
 
 // ---- epilogue bodies shared by the cta_group::1 and cta_group::2 kernels: thread = one query, v = its 128 passage scores ----
@@ -403,6 +404,47 @@ __device__ __forceinline__ void dense_ts_filter_append(const DenseTsArgs& a, uin
             }
         }
     }
+}
+
+// The same filter appending to this CTA's own segment of the query's candidate list: the thread is the only writer of
+// (slot, segment), so its running count lives in a register (`my_cnt`, stored once when the kernel ends): no atomics, no round trip.
+__device__ __forceinline__ void dense_ts_filter_append_seg(const DenseTsArgs& a, uint32_t (&v)[kTS_N / 32][32], long long row0, float tau_q,
+                                                           float* seg_s, int32_t* seg_r, uint32_t& my_cnt) {
+    if (!(row0 >= a.row_begin && row0 + kTS_N <= a.row_end)) {            // edge tile: rows outside the launch range never pass
+#pragma unroll
+        for (int c = 0; c < kTS_N; ++c) {
+            const long long row = row0 + c;
+            if (row < a.row_begin || row >= a.row_end) v[c >> 5][c & 31] = 0xFF800000u;      // -inf
+        }
+    }
+    float gm[kTS_N / 8];
+#pragma unroll
+    for (int j = 0; j < kTS_N / 8; ++j) {
+        float m = __uint_as_float(v[j >> 2][(j & 3) * 8]);
+#pragma unroll
+        for (int c = 1; c < 8; ++c) m = fmaxf(m, __uint_as_float(v[j >> 2][(j & 3) * 8 + c]));
+        gm[j] = m;
+    }
+    float m = gm[0];
+#pragma unroll
+    for (int j = 1; j < kTS_N / 8; ++j) m = fmaxf(m, gm[j]);
+    if (!(m > tau_q)) return;                                              // the common exit of (almost) every lane
+    const int32_t r0 = (int32_t)row0;
+    uint32_t pos = my_cnt;
+#pragma unroll
+    for (int j = 0; j < kTS_N / 8; ++j) {
+        if (gm[j] > tau_q) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float sc = __uint_as_float(v[j >> 2][(j & 3) * 8 + c]);
+                if (sc > tau_q) {
+                    if (pos < (uint32_t)kSegCap) { seg_s[pos] = sc + 0.0f; seg_r[pos] = r0 + 8 * j + c; }
+                    ++pos;
+                }
+            }
+        }
+    }
+    my_cnt = pos;
 }
 
 __global__ void __launch_bounds__(kTS_Threads, 1)
@@ -553,6 +595,9 @@ dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
         const bool q_ok = slot < a.n_queries;
         const float tau_q = (q_ok && (a.mode == 0 || a.mode == 3)) ? a.tau[slot] : INFINITY;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a_cols;
+        const bool use_seg = a.seg_cnt != nullptr && q_ok && (a.mode == 0 || a.mode == 3);
+        const size_t seg0 = ((size_t)(q_ok ? slot : 0) * kSegCount + (size_t)cta_in_q) * kSegCap;
+        uint32_t my_cnt = 0;
         int i = 0;
         for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q, ++i) {
             mbar_wait(&tfull_bar[0], (uint32_t)i & 1u);
@@ -570,8 +615,10 @@ dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
             if (a.mode >= 2) dense_ts_add_scratch(a, v, slot, row0);
             if (K2_DBG() & 4) {
             } else if (a.mode == 1 || a.mode == 2) dense_ts_store_scratch(a, v, slot, row0);
+            else if (use_seg) dense_ts_filter_append_seg(a, v, row0, tau_q, a.seg_score + seg0, a.seg_row + seg0, my_cnt);
             else dense_ts_filter_append(a, v, slot, row0, tau_q);
         }
+        if (use_seg) a.seg_cnt[(size_t)slot * kSegCount + cta_in_q] = my_cnt;
     }
     if (threadIdx.x == 64) K2_TRACE(0, 3);
     tc_fence_before();
@@ -752,6 +799,9 @@ dense_tile_ts2_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_c
         const float tau_q = (q_ok && (a.mode == 0 || a.mode == 3)) ? a.tau[slot] : INFINITY;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a_cols;
         const uint32_t tempty_leader = mapa_shared(smem_u32(&tempty_bar), 0u);
+        const bool use_seg = a.seg_cnt != nullptr && q_ok && (a.mode == 0 || a.mode == 3);
+        const size_t seg0 = ((size_t)(q_ok ? slot : 0) * kSegCount + (size_t)pair) * kSegCap;
+        uint32_t my_cnt = 0;
         int i = 0;
         for (int t = pair; t < a.n_tiles; t += n_pairs, ++i) {
             mbar_wait(&tfull_bar, (uint32_t)i & 1u);
@@ -766,8 +816,10 @@ dense_tile_ts2_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_c
             const long long row0 = a.tile_row0 + (long long)t * kTS_N;
             if (a.mode >= 2) dense_ts_add_scratch(a, v, slot, row0);
             if (a.mode == 1 || a.mode == 2) dense_ts_store_scratch(a, v, slot, row0);
+            else if (use_seg) dense_ts_filter_append_seg(a, v, row0, tau_q, a.seg_score + seg0, a.seg_row + seg0, my_cnt);
             else dense_ts_filter_append(a, v, slot, row0, tau_q);
         }
+        if (use_seg) a.seg_cnt[(size_t)slot * kSegCount + pair] = my_cnt;
     }
     tc_fence_before();
     cluster_sync_all();                          // no CTA of the pair exits (or frees TMEM) while the other may still signal it
@@ -850,6 +902,7 @@ int launch_dense_pass(const dhr_index* h, const __half* blocked, const __half* r
     a.mode = mode;
     a.scratch = scratch; a.scratch_slots = scratch_slots;
     a.tau = t.tau; a.cnt = t.cnt; a.cand_score = t.cand_score; a.cand_row = t.cand_row; a.cap = cap;
+    a.seg_score = t.seg_score; a.seg_row = t.seg_row; a.seg_cnt = t.seg_cnt;
     const size_t smem = (size_t)a.n_stages * kTS_BBytes + 1024;
     DHR_CUDA(cudaFuncSetAttribute(dense_tile_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DHR_CUDA(cudaFuncSetAttribute(dense_tile_ts2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTS2_MaxStages * kTS2_StageBytes + 1024));

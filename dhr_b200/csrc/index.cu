@@ -611,6 +611,7 @@ int dhr_index_close(dhr_index* h) {
     void* bufs[] = {h->lexv, h->lexi, h->dns, h->dnst, h->lext, h->qblocks, h->qblock_bytes, h->lane[0].scratch, h->lane[1].scratch, h->lexp, h->lexp_nbytes, h->d_flags, h->stage_a, h->stage_b, h->q_lex16, h->q_lex32, h->q_dns16, h->q_dns32,
                     h->q_code, h->topk.tau, h->topk.cnt, h->topk.overflow, h->topk.cand_score, h->topk.cand_row,
                     h->topk1.tau, h->topk1.cnt, h->topk1.overflow, h->topk1.cand_score, h->topk1.cand_row,
+                    h->topk.seg_score, h->topk.seg_row, h->topk.seg_cnt, h->topk1.seg_score, h->topk1.seg_row, h->topk1.seg_cnt,
                     h->d_out_scores, h->d_out_rows, h->d_out_counts, h->d_overflow, h->stage_c};
     for (void* b : bufs) if (b) cudaFree(b);
     for (cudaEvent_t e : h->batch_events) cudaEventDestroy(e);
@@ -653,6 +654,8 @@ int dhr_index_device_bytes(const dhr_index* h, int64_t* bytes) {
          h->stage_c_bytes;
     if (h->topk.tau) b += (size_t)kMaxInflight * (12 + (size_t)kCandCap * 8);
     if (h->topk1.tau) b += (size_t)kMaxInflight * (12 + (size_t)kCandCap * 8);
+    if (h->topk.seg_cnt) b += (size_t)kMaxInflight * kSegCount * (4 + (size_t)kSegCap * 8);
+    if (h->topk1.seg_cnt) b += (size_t)kMaxInflight * kSegCount * (4 + (size_t)kSegCap * 8);
     if (h->q_capacity > 0) b += ((size_t)h->q_capacity + kMaxInflight) * ((size_t)g.D_pad * 6 + (size_t)g.S_pad * g.code_bytes + (size_t)g.C_pad * 6);
     b += h->out_capacity * 12 + h->out_q_capacity * 4 + h->overflow_capacity * 4;
     *bytes = (int64_t)b;

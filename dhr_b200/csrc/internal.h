@@ -28,7 +28,14 @@ struct TopkState {
     uint32_t* overflow = nullptr;        // [slots] sticky overflow flag
     float*    cand_score = nullptr;      // [slots][cap]
     int32_t*  cand_row = nullptr;        // [slots][cap]
+    // Segmented candidate lists of the tensor-core filter epilogue (K2, thread = query): every CTA appends to its OWN segment of a
+    // slot with a register counter -- no atomics, no round trips -- and K3 gathers the segments behind the kept candidates.
+    float*    seg_score = nullptr;       // [slots][kSegCount][kSegCap]
+    int32_t*  seg_row = nullptr;
+    uint32_t* seg_cnt = nullptr;         // [slots][kSegCount] appended per segment (may exceed kSegCap -> overflow); zeroed before a scan launch
 };
+constexpr int kSegCount = 160;           // >= CTAs that can work on one query group in one launch (SMs of the device)
+constexpr int kSegCap = 512;             // per (slot, CTA) and chunk: the first chunk hands a CTA <= 2 tiles of 128 rows, later chunks ~100 rows
 
 struct EventPool {
     std::vector<cudaEvent_t> ev;

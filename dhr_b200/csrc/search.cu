@@ -168,6 +168,24 @@ static int ensure_out_buffers(dhr_index* h, size_t n_queries, int k) {
     return DHR_OK;
 }
 
+// the paths that append with atomics (K1, K1t, the multi-launch --IP passes, rerank) must not hand K3 the segment pointers
+static TopkState without_segments(TopkState t) {
+    t.seg_score = nullptr; t.seg_row = nullptr; t.seg_cnt = nullptr;
+    return t;
+}
+
+// segmented candidate lists of the tensor-core filter epilogue (one set per batch lane), attached to a copy of the lane's TopkState
+static int ensure_segments(dhr_index* h, int lane) {
+    TopkState& t = lane ? h->topk1 : h->topk;
+    if (t.seg_cnt) return DHR_OK;
+    const size_t n = (size_t)kMaxInflight * kSegCount * kSegCap;
+    DHR_CUDA(cudaMalloc(&t.seg_score, n * sizeof(float)));
+    DHR_CUDA(cudaMalloc(&t.seg_row, n * sizeof(int32_t)));
+    DHR_CUDA(cudaMalloc(&t.seg_cnt, (size_t)kMaxInflight * kSegCount * sizeof(uint32_t)));
+    DHR_CUDA(cudaMemset(t.seg_cnt, 0, (size_t)kMaxInflight * kSegCount * sizeof(uint32_t)));
+    return DHR_OK;
+}
+
 static int ensure_overflow_flags(dhr_index* h, size_t n_queries) {
     if (n_queries <= h->overflow_capacity && h->d_overflow) return DHR_OK;
     if (h->d_overflow) cudaFree(h->d_overflow);
@@ -239,7 +257,7 @@ static QuerySet query_set(const dhr_index* h, bool f32) {
 static int run_batch(dhr_index* h, const QuerySet& qs, int base, int nq, int k, bool masked, bool safe, int qb,
                      SelectOut so, cudaStream_t st) {
     const Geometry& g = h->g;
-    TopkState t = h->topk;
+    TopkState t = without_segments(h->topk);
     so.base = base;
     const std::vector<long long> bounds = chunk_schedule(h->n_rows, k, kCandCap, safe);
     ScanArgs a{};
@@ -291,6 +309,7 @@ static int run_batch(dhr_index* h, const QuerySet& qs, int base, int nq, int k, 
 
 // dense-only index on the tensor-core tile kernel (K2): same chunk schedule, 128-row aligned
 static int run_batch_dense_tile(dhr_index* h, const QuerySet& qs, int base, int nq, int k, SelectOut so, cudaStream_t st, int L) {
+    DHR_TRY(ensure_segments(h, L));
     TopkState t = L ? h->topk1 : h->topk;
     so.base = base;
     const std::vector<long long> bounds = chunk_schedule(h->n_rows, k, kCandCap, false, 128);
@@ -299,6 +318,7 @@ static int run_batch_dense_tile(dhr_index* h, const QuerySet& qs, int base, int 
     for (size_t c = 0; c < n_chunks; ++c) {
         cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
         if (h->opt_profile) { e0 = h->events.get(); e1 = h->events.get(); e2 = h->events.get(); cudaEventRecord(e0, st); }
+        if (t.seg_cnt) DHR_CUDA(cudaMemsetAsync(t.seg_cnt, 0, (size_t)kMaxInflight * kSegCount * sizeof(uint32_t), st));
         DHR_TRY(launch_dense_tile(h, q16, nq, 0, bounds[c], bounds[c + 1], 0, nullptr, 0, t, kCandCap, st));
         if (h->opt_profile) cudaEventRecord(e1, st);
         DHR_TRY(launch_select(t, nq, k, kCandCap, c + 1 == n_chunks, so, st));
@@ -372,7 +392,7 @@ static int ensure_lane(dhr_index* h, int L, bool need_scratch) {
 static int run_batch_hybrid_tile(dhr_index* h, const LexTileGeom& lt, const QuerySet& qs, int base, int nq, int k,
                                  SelectOut so, cudaStream_t st, int L) {
     const Geometry& g = h->g;
-    TopkState t = L ? h->topk1 : h->topk;
+    TopkState t = without_segments(L ? h->topk1 : h->topk);
     dhr_index::TileLane& ln = h->lane[L];
     so.base = base;
     const std::vector<long long> bounds = chunk_schedule(h->n_rows, k, kCandCap, false, kLexTileRows, kTileSubRows);
@@ -525,7 +545,7 @@ static int validate_query_args(const dhr_index* h, int n_queries, int q_val_dtyp
 // the passes of a sub-chunk through the L2-resident scratch, the last pass adds them and applies the admission filter.
 static int run_batch_unmasked_tile(dhr_index* h, const QuerySet& qs, int base, int nq, int k, SelectOut so, cudaStream_t st) {
     const Geometry& g = h->g;
-    TopkState t = h->topk;
+    TopkState t = without_segments(h->topk);
     so.base = base;
     const std::vector<long long> bounds = chunk_schedule(h->n_rows, k, kCandCap, false, kDenseTileRows, kTileSubRows);
     const size_t n_chunks = bounds.size() - 1;
@@ -879,7 +899,7 @@ extern "C" int dhr_rerank(dhr_index* h, int n_queries, int q_val_dtype, const vo
     h->stats.n_kernel_launches++;
     for (int base = 0; base < n_queries && status == DHR_OK; base += kMaxInflight) {
         const int nq = std::min(kMaxInflight, n_queries - base);
-        TopkState t = h->topk;
+        TopkState t = without_segments(h->topk);
         h->stats.n_kernel_launches += 2;
         ScanArgs a{};
         a.lexv = h->lexv; a.lexi = h->lexi; a.dns = h->dns;

@@ -56,11 +56,50 @@ topk_select_kernel(TopkState t, int k, int cap, int final_pass, const SelectOut 
     __shared__ unsigned long long wmin[kSelectThreads / 32];
     const int slot = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t raw = t.cnt[slot];
-    const int n = (int)min(raw, (uint32_t)cap);
-    const bool overflowed = raw > (uint32_t)cap || t.overflow[slot] != 0u;   // sticky over the chunks of a batch
     float* cs = t.cand_score + (size_t)slot * cap;
     int32_t* cr = t.cand_row + (size_t)slot * cap;
+    uint32_t raw = t.cnt[slot];
+    bool seg_over = false;
+    if (t.seg_cnt) {
+        // gather the per-CTA segments of the tensor-core filter epilogue behind the kept candidates: exclusive scan of the segment
+        // counts (warp 0), then one warp per segment copies its entries (coalesced) into the flat list
+        __shared__ uint32_t seg_off[kSegCount + 1];
+        __shared__ uint32_t seg_flag;
+        if (tid == 0) seg_flag = 0u;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t carry = 0;
+            for (int r0 = 0; r0 < kSegCount; r0 += 32) {
+                const uint32_t c = t.seg_cnt[(size_t)slot * kSegCount + r0 + lane];
+                if (c > (uint32_t)kSegCap) seg_flag = 1u;
+                const uint32_t v = min(c, (uint32_t)kSegCap);
+                uint32_t inc = v;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, off);
+                    if (lane >= off) inc += y;
+                }
+                seg_off[r0 + lane] = carry + inc - v;
+                carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
+            }
+            if (lane == 0) seg_off[kSegCount] = carry;
+        }
+        __syncthreads();
+        for (int sg = warp; sg < kSegCount; sg += kSelectThreads / 32) {
+            const uint32_t o0 = seg_off[sg], ns = seg_off[sg + 1] - o0;
+            const float* ss = t.seg_score + ((size_t)slot * kSegCount + sg) * kSegCap;
+            const int32_t* sr = t.seg_row + ((size_t)slot * kSegCount + sg) * kSegCap;
+            for (uint32_t i = lane; i < ns; i += 32) {
+                const uint32_t dst = raw + o0 + i;
+                if (dst < (uint32_t)cap) { cs[dst] = ss[i]; cr[dst] = sr[i]; }
+            }
+        }
+        __syncthreads();
+        raw += seg_off[kSegCount];
+        seg_over = seg_flag != 0u;
+    }
+    const int n = (int)min(raw, (uint32_t)cap);
+    const bool overflowed = raw > (uint32_t)cap || seg_over || t.overflow[slot] != 0u;   // sticky over the chunks of a batch
     unsigned long long r[kSelectKeysPerThread];
 #pragma unroll
     for (int j = 0; j < kSelectKeysPerThread; ++j) {
