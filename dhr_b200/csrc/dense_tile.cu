@@ -273,6 +273,45 @@ dense_tile_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 }
 
 
+// ---- 32-bit shared-address forms of the barrier / TMA / commit wrappers ------------------------------------------------------
+// The per-stage loops of the TMA producer and of the MMA issuer run in ONE warp each and are latency chains of uniform-datapath
+// instructions; converting generic pointers (cvta: an S2UR of the CTA id per call) and rebuilding descriptors per stage made
+// them ~75 dependent instructions (~560 cycles) per stage -- more than the 256 tensor cycles of the stage's four MMAs, so the
+// issuing warp, not the tensor pipe, set the pace.  With the addresses precomputed a stage is a handful of integer adds.
+__device__ __forceinline__ bool mbar_try_wait_u32(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_u32(bar, parity)) {
+        if (++spins > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_u32(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_multicast_u32(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_u32(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_multicast_u32(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(cta_mask) : "memory");
+}
+// descriptor of the K-major 128B-swizzled operand tile at shared address `addr` (< 256 KiB, 16-byte aligned): the address field is
+// additive, so desc(addr + d) = desc(addr) + (d >> 4)
+__device__ __forceinline__ uint64_t umma_smem_desc_base(uint32_t addr) { return umma_smem_desc(addr); }
+
 // ---- TS variant: queries in TMEM (M = 128), corpus streamed as the N operand -----------------------------
 constexpr int kTS_M = 128;             // queries per CTA (UMMA M, one TMEM lane each)
 constexpr int kTS_N = 128;             // passages per tile (UMMA N)
@@ -522,30 +561,33 @@ dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
     if (warp == 0) {
         // ===== TMA producer: corpus tiles (whole warp, one elected lane issues) =====
         int s = 0; uint32_t ph = 0; int i = 0;
+        const uint32_t ring_s = smem_u32(ring), full_s = smem_u32(full_bar), empty_s = smem_u32(empty_bar);
+        const uint32_t half_off = a.cluster ? crank * (uint32_t)(kTS_BBytes / 2) : 0u;
+        const int half_rows = a.cluster ? (int)crank * (kTS_N / 2) : 0;
+        const int pf_tiles = kTS_Prefetch * ctas_per_q;
         for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q, ++i) {
             if (lane == 0) K2_TRACE(1, i);
             const int row0 = (int)(a.tile_row0 + (long long)t * kTS_N);
+            const int blk0 = row0 / kTS_N * a.n_kblocks * kTS_N;                  // first row of the tile's k-block 0 in the blocked copy
+            const bool do_pf = qg == 0 && t + pf_tiles < a.n_tiles;
             for (int kb = 0; kb < a.n_kblocks; ++kb) {
                 if (K2_DBG() & 8) continue;
-                mbar_wait(&empty_bar[s], ph ^ 1u);
+                mbar_wait_u32(empty_s + 8u * s, ph ^ 1u);
                 if (elect_one()) {
                     // the ring holds exactly one corpus tile, so the demand load is issued only one tile-time ahead of its use:
                     // pull the same k-block of the tile `kTS_Prefetch` iterations further on into L2 now (HBM latency off the
                     // critical path); the two query groups share tiles, group 0 prefetches
-                    const int tp = t + kTS_Prefetch * ctas_per_q;
-                    if (qg == 0 && tp < a.n_tiles) {
-                        const int rowp = row0 + kTS_Prefetch * ctas_per_q * kTS_N;
-                        if (a.blocked) tma_prefetch_l2_2d(&tmap_c, 0, (rowp / kTS_N * a.n_kblocks + kb) * kTS_N);
-                        else tma_prefetch_l2_2d(&tmap_c, kb * kDT_KB, rowp);
+                    if (do_pf) {
+                        if (a.blocked) tma_prefetch_l2_2d(&tmap_c, 0, blk0 + (pf_tiles * a.n_kblocks + kb) * kTS_N);
+                        else tma_prefetch_l2_2d(&tmap_c, kb * kDT_KB, row0 + pf_tiles * kTS_N);
                     }
-                    mbar_arrive_expect_tx(&full_bar[s], kTS_BBytes);              // both halves (own + peer's multicast)
-                    if (a.cluster) {
-                        const int half = (int)crank * (kTS_N / 2);
-                        uint8_t* dst = ring + (size_t)s * kTS_BBytes + (size_t)crank * (kTS_BBytes / 2);
-                        if (a.blocked) tma_load_2d_multicast(dst, &tmap_c, &full_bar[s], 0, (row0 / kTS_N * a.n_kblocks + kb) * kTS_N + half, 3);
-                        else tma_load_2d_multicast(dst, &tmap_c, &full_bar[s], kb * kDT_KB, row0 + half, 3);
-                    } else if (a.blocked) tma_load_2d(ring + (size_t)s * kTS_BBytes, &tmap_c, &full_bar[s], 0, (row0 / kTS_N * a.n_kblocks + kb) * kTS_N);
-                    else tma_load_2d(ring + (size_t)s * kTS_BBytes, &tmap_c, &full_bar[s], kb * kDT_KB, row0);
+                    const uint32_t bar = full_s + 8u * s;
+                    const uint32_t dst = ring_s + (uint32_t)s * kTS_BBytes + half_off;
+                    mbar_arrive_expect_tx_u32(bar, kTS_BBytes);                   // both halves (own + peer's multicast)
+                    const int c0 = a.blocked ? 0 : kb * kDT_KB;
+                    const int c1 = (a.blocked ? blk0 + kb * kTS_N : row0) + half_rows;
+                    if (a.cluster) tma_load_2d_multicast_u32(dst, &tmap_c, bar, c0, c1, 3);
+                    else tma_load_2d_u32(dst, &tmap_c, bar, c0, c1);
                 }
                 __syncwarp();
                 if (++s == a.n_stages) { s = 0; ph ^= 1u; }
@@ -559,31 +601,33 @@ dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
         constexpr uint32_t idesc = umma_idesc_f16(kTS_M, kTS_N);
         const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);
         const uint32_t d_tmem = tmem_u + a_cols;
+        const uint32_t full_s = smem_u32(full_bar), empty_s = smem_u32(empty_bar), tempty_s = smem_u32(&tempty_bar[0]), tfull_s = smem_u32(&tfull_bar[0]);
+        const uint64_t desc0 = umma_smem_desc_base(smem_u32(ring));              // stage s, k-step k: desc0 + s * (16 KiB >> 4) + k * (32 B >> 4)
         int s = 0; uint32_t ph = 0;
         int i = 0;
         for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q, ++i) {
             if (lane == 0) K2_TRACE(2, i);
-            mbar_wait(&tempty_bar[0], ((uint32_t)i & 1u) ^ 1u);
+            mbar_wait_u32(tempty_s, ((uint32_t)i & 1u) ^ 1u);
             tc_fence_after();
             if (lane == 0) K2_TRACE(3, i);
             for (int kb = 0; kb < a.n_kblocks; ++kb) {
-                if (!(K2_DBG() & 8)) mbar_wait(&full_bar[s], ph);
+                if (!(K2_DBG() & 8)) mbar_wait_u32(full_s + 8u * s, ph);
                 tc_fence_after();
-                const uint32_t b_addr = smem_u32(ring + (size_t)s * kTS_BBytes);
                 if (elect_one()) {
+                    const uint64_t bd = desc0 + (uint64_t)((uint32_t)s * (kTS_BBytes >> 4));
+                    const uint32_t at = tmem_u + (uint32_t)kb * 32u;
 #pragma unroll
                     for (int k = 0; k < kDT_KB / 16; ++k)
-                        umma_f16_ts(d_tmem, tmem_u + (uint32_t)kb * 32u + (uint32_t)k * 8u, umma_smem_desc(b_addr + k * 32), idesc,
-                                    (kb | k) != 0 ? 1u : 0u);
+                        umma_f16_ts(d_tmem, at + (uint32_t)k * 8u, bd + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
                     if (!(K2_DBG() & 8)) {                                // frees the corpus stage once these MMAs have read it
-                        if (a.cluster) umma_commit_multicast(&empty_bar[s], 3);
-                        else umma_commit(&empty_bar[s]);
+                        if (a.cluster) umma_commit_multicast_u32(empty_s + 8u * s, 3);
+                        else umma_commit_u32(empty_s + 8u * s);
                     }
                 }
                 __syncwarp();
                 if (++s == a.n_stages) { s = 0; ph ^= 1u; }
             }
-            if (elect_one()) umma_commit(&tfull_bar[0]);                  // accumulator tile complete
+            if (elect_one()) umma_commit_u32(tfull_s);                    // accumulator tile complete
             __syncwarp();
             if (lane == 0) K2_TRACE(4, i);
         }
@@ -738,24 +782,28 @@ dense_tile_ts2_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_c
     if (warp == 0) {
         // ===== TMA producer: this CTA's half (64 passages) of every corpus stage =====
         int s = 0; uint32_t ph = 0;
-        const uint32_t full0 = mapa_shared(smem_u32(&full_bar[0]), 0u);          // the leader's full barriers
+        const uint32_t full0 = mapa_shared(smem_u32(&full_bar[0]), 0u);          // the leader's full barriers (cluster address)
+        const uint32_t full_local = smem_u32(full_bar), empty_s = smem_u32(empty_bar), ring_s = smem_u32(ring);
+        const int half = (int)crank * kTS2_HalfN;
+        const int pf_tiles = kTS_Prefetch * n_pairs;
         for (int t = pair; t < a.n_tiles; t += n_pairs) {
             const int row0 = (int)(a.tile_row0 + (long long)t * kTS_N);
+            const int blk0 = row0 / kTS_N * a.n_kblocks * kTS_N;
+            const bool do_pf = leader && t + pf_tiles < a.n_tiles;
             for (int kb = 0; kb < a.n_kblocks; ++kb) {
-                mbar_wait(&empty_bar[s], ph ^ 1u);
+                mbar_wait_u32(empty_s + 8u * s, ph ^ 1u);
                 if (elect_one()) {
-                    const int tp = t + kTS_Prefetch * n_pairs;
-                    if (leader && tp < a.n_tiles) {
-                        const int rowp = row0 + kTS_Prefetch * n_pairs * kTS_N;
-                        if (a.blocked) tma_prefetch_l2_2d(&tmap_c, 0, (rowp / kTS_N * a.n_kblocks + kb) * kTS_N);
-                        else tma_prefetch_l2_2d(&tmap_c, kb * kDT_KB, rowp);
+                    if (do_pf) {
+                        if (a.blocked) tma_prefetch_l2_2d(&tmap_c, 0, blk0 + (pf_tiles * a.n_kblocks + kb) * kTS_N);
+                        else tma_prefetch_l2_2d(&tmap_c, kb * kDT_KB, row0 + pf_tiles * kTS_N);
                     }
-                    if (leader) mbar_arrive_expect_tx(&full_bar[s], 2u * kTS2_StageBytes);
-                    const int half = (int)crank * kTS2_HalfN;
-                    uint8_t* dst = ring + (size_t)s * kTS2_StageBytes;
+                    if (leader) mbar_arrive_expect_tx_u32(full_local + 8u * s, 2u * kTS2_StageBytes);
+                    const uint32_t dst = ring_s + (uint32_t)s * kTS2_StageBytes;
                     const uint32_t bar = full0 + (uint32_t)s * 8u;
-                    if (a.blocked) tma_load_2d_2sm(dst, &tmap_c, bar, 0, (row0 / kTS_N * a.n_kblocks + kb) * kTS_N + half);
-                    else tma_load_2d_2sm(dst, &tmap_c, bar, kb * kDT_KB, row0 + half);
+                    const int c0 = a.blocked ? 0 : kb * kDT_KB;
+                    const int c1 = (a.blocked ? blk0 + kb * kTS_N : row0) + half;
+                    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                                 ::"r"(dst), "l"(&tmap_c), "r"(bar), "r"(c0), "r"(c1) : "memory");
                 }
                 __syncwarp();
                 if (++s == a.n_stages) { s = 0; ph ^= 1u; }
@@ -767,26 +815,31 @@ dense_tile_ts2_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_c
             constexpr uint32_t idesc = umma_idesc_f16(2 * kTS_M, kTS_N);
             const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);
             const uint32_t d_tmem = tmem_u + a_cols;
+            const uint32_t full_s = smem_u32(full_bar), empty_s = smem_u32(empty_bar), tempty_s = smem_u32(&tempty_bar), tfull_s = smem_u32(&tfull_bar);
+            const uint64_t desc0 = umma_smem_desc_base(smem_u32(ring));          // stage s, k-step k: desc0 + s * (8 KiB >> 4) + k * (32 B >> 4)
             int s = 0; uint32_t ph = 0;
             int i = 0;
             for (int t = pair; t < a.n_tiles; t += n_pairs, ++i) {
-                mbar_wait(&tempty_bar, ((uint32_t)i & 1u) ^ 1u);
+                mbar_wait_u32(tempty_s, ((uint32_t)i & 1u) ^ 1u);
                 tc_fence_after();
                 for (int kb = 0; kb < a.n_kblocks; ++kb) {
-                    mbar_wait(&full_bar[s], ph);
+                    mbar_wait_u32(full_s + 8u * s, ph);
                     tc_fence_after();
-                    const uint32_t b_addr = smem_u32(ring + (size_t)s * kTS2_StageBytes);
                     if (elect_one()) {
+                        const uint64_t bd = desc0 + (uint64_t)((uint32_t)s * (kTS2_StageBytes >> 4));
+                        const uint32_t at = tmem_u + (uint32_t)kb * 32u;
 #pragma unroll
                         for (int k = 0; k < kDT_KB / 16; ++k)
-                            umma_f16_ts_2sm(d_tmem, tmem_u + (uint32_t)kb * 32u + (uint32_t)k * 8u, umma_smem_desc(b_addr + k * 32), idesc,
-                                            (kb | k) != 0 ? 1u : 0u);
-                        umma_commit_2sm(&empty_bar[s], 3);                 // both CTAs may refill the stage
+                            umma_f16_ts_2sm(d_tmem, at + (uint32_t)k * 8u, bd + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                     ::"r"(empty_s + 8u * s), "h"((uint16_t)3) : "memory");     // both CTAs may refill the stage
                     }
                     __syncwarp();
                     if (++s == a.n_stages) { s = 0; ph ^= 1u; }
                 }
-                if (elect_one()) umma_commit_2sm(&tfull_bar, 3);           // accumulator tile complete in both CTAs
+                if (elect_one())                                           // accumulator tile complete in both CTAs
+                    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                 ::"r"(tfull_s), "h"((uint16_t)3) : "memory");
                 __syncwarp();
             }
         }

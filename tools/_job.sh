@@ -1,4 +1,6 @@
-timeout 300 python bench.py --unmasked --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_n1_unmasked_ip.json 2>gpurun_out/r2_bench_n1_unmasked_ip.err
-python -c "
-import json; d=json.load(open('gpurun_out/r2_bench_n1_unmasked_ip.json')); print('unmasked', d['value'], d['ms_per_step'], d['roofline']['bound'], d['roofline']['achieved'], d['roofline']['frac'], d['verified']['ok'], d['verified']['max_abs_score_err'], d['config']['scan_variant'], d['config']['index_bytes'])"
-tail -2 gpurun_out/r2_bench_n1_unmasked_ip.err
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -DDHR_K2_TRACE -o gpurun_out/k2_micro tools/k2_micro.cu -lcuda > gpurun_out/k2_probe_b.txt 2>&1
+for tau in 1e30 0.06; do
+  echo "== k2_micro 221045 256 768 1 0 1 $tau" >> gpurun_out/k2_probe_b.txt
+  timeout 120 ./gpurun_out/k2_micro 221045 256 768 1 0 1 $tau >> gpurun_out/k2_probe_b.txt 2>&1
+done
+head -40 gpurun_out/k2_probe_b.txt
