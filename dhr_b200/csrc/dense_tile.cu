@@ -318,7 +318,9 @@ constexpr int kTS_N = 128;             // passages per tile (UMMA N)
 constexpr int kTS_BBytes = kTS_N * kDT_KB * 2;   // 16 KiB per corpus stage
 constexpr int kTS_MaxStages = 12;
 constexpr int kTS_MaxACols = 384;      // TMEM columns holding the query operand (C_pad <= 768)
-constexpr int kTS_Threads = 192;
+constexpr int kTS_EpiWarps = 8;        // two warps per TMEM lane quadrant, each with half of the tile's passages
+constexpr int kTS_EpiCols = kTS_N / (kTS_EpiWarps / 4);   // accumulator columns (passages) per epilogue thread
+constexpr int kTS_Threads = 64 + 32 * kTS_EpiWarps;
 constexpr int kTS_Prefetch = 2;         // L2 prefetch distance in tiles of one CTA
 static_assert(kTS_N == kDenseTileRows && kDT_KB == kDenseTileCols, "K-blocked dense copy layout");
 
@@ -359,13 +361,13 @@ struct DenseTsArgs {
     float* seg_score; int32_t* seg_row; uint32_t* seg_cnt;   // segmented candidate lists (filter modes) or nullptr: append with atomics
 };
 
-// ---- epilogue bodies shared by the cta_group::1 and cta_group::2 kernels: thread = one query, v = its 128 passage scores ----
+// ---- epilogue bodies shared by the cta_group::1 and cta_group::2 kernels: thread = one query, v = the scores of its kTS_EpiCols passages starting at row0 ----
 // v += scratch (modes 2 and 3: partial sums of an earlier column pass, written by mode 1 / 2)
-__device__ __forceinline__ void dense_ts_add_scratch(const DenseTsArgs& a, uint32_t (&v)[kTS_N / 32][32], int slot, long long row0) {
+__device__ __forceinline__ void dense_ts_add_scratch(const DenseTsArgs& a, uint32_t (&v)[kTS_EpiCols / 32][32], int slot, long long row0) {
     if ((long long)slot < a.scratch_slots) {
         const float* src = a.scratch + (size_t)(row0 - a.scratch_row0) * a.scratch_slots + slot;
 #pragma unroll
-        for (int c = 0; c < kTS_N; ++c) {
+        for (int c = 0; c < kTS_EpiCols; ++c) {
             const long long row = row0 + c;
             if (row >= a.row_begin && row < a.row_end)
                 v[c >> 5][c & 31] = __float_as_uint(__uint_as_float(v[c >> 5][c & 31]) + src[(size_t)c * a.scratch_slots]);
@@ -373,17 +375,17 @@ __device__ __forceinline__ void dense_ts_add_scratch(const DenseTsArgs& a, uint3
     }
 }
 
-__device__ __forceinline__ void dense_ts_store_scratch(const DenseTsArgs& a, const uint32_t (&v)[kTS_N / 32][32], int slot, long long row0) {
+__device__ __forceinline__ void dense_ts_store_scratch(const DenseTsArgs& a, const uint32_t (&v)[kTS_EpiCols / 32][32], int slot, long long row0) {
     // scratch[row][slot]: for a fixed passage the 32 lanes of a warp write 32 consecutive slots (one 128-byte line)
     if ((long long)slot < a.scratch_slots) {
         float* dst = a.scratch + (size_t)(row0 - a.scratch_row0) * a.scratch_slots + slot;
-        if (a.scratch_slots == kMaxInflight && row0 >= a.row_begin && row0 + kTS_N <= a.row_end) {
+        if (a.scratch_slots == kMaxInflight && row0 >= a.row_begin && row0 + kTS_EpiCols <= a.row_end) {
             // whole tile in range, compile-time row pitch: one store instruction per passage
 #pragma unroll
-            for (int c = 0; c < kTS_N; ++c) dst[(size_t)c * kMaxInflight] = __uint_as_float(v[c >> 5][c & 31]);
+            for (int c = 0; c < kTS_EpiCols; ++c) dst[(size_t)c * kMaxInflight] = __uint_as_float(v[c >> 5][c & 31]);
         } else {
 #pragma unroll
-            for (int c = 0; c < kTS_N; ++c) {
+            for (int c = 0; c < kTS_EpiCols; ++c) {
                 const long long row = row0 + c;
                 if (row >= a.row_begin && row < a.row_end)
                     dst[(size_t)c * a.scratch_slots] = __uint_as_float(v[c >> 5][c & 31]);
@@ -392,7 +394,7 @@ __device__ __forceinline__ void dense_ts_store_scratch(const DenseTsArgs& a, con
     }
 }
 
-__device__ __forceinline__ void dense_ts_filter_append(const DenseTsArgs& a, uint32_t (&v)[kTS_N / 32][32], int slot, long long row0, float tau_q) {
+__device__ __forceinline__ void dense_ts_filter_append(const DenseTsArgs& a, uint32_t (&v)[kTS_EpiCols / 32][32], int slot, long long row0, float tau_q) {
     // dense-only index: strict admission threshold.  Lanes without a valid query carry tau = +inf and never pass.  Rows pass
     // rarely once tau is set (about one (query, row) pair per warp and tile in the last chunk), so the work is kept O(passes)
     // and the code small: the lane's 128 scores are reduced to 16 group maxima and their maximum; only a lane that can pass
@@ -402,16 +404,16 @@ __device__ __forceinline__ void dense_ts_filter_append(const DenseTsArgs& a, uin
     // flat count / write passes over all 128 registers 8.3 ms (3,500 dependent instructions per warp and tile: the epilogue,
     // not the tensor pipe, was the bottleneck); whole-warp scan of one flagged lane at a time through shared memory 4.65 ms but
     // 2.3x slower in the middle chunks where many lanes pass; this form 4.9 ms and the fastest over a whole batch.
-    if (!(row0 >= a.row_begin && row0 + kTS_N <= a.row_end)) {            // edge tile: rows outside the launch range never pass
+    if (!(row0 >= a.row_begin && row0 + kTS_EpiCols <= a.row_end)) {            // edge tile: rows outside the launch range never pass
 #pragma unroll
-        for (int c = 0; c < kTS_N; ++c) {
+        for (int c = 0; c < kTS_EpiCols; ++c) {
             const long long row = row0 + c;
             if (row < a.row_begin || row >= a.row_end) v[c >> 5][c & 31] = 0xFF800000u;      // -inf
         }
     }
-    float gm[kTS_N / 8];
+    float gm[kTS_EpiCols / 8];
 #pragma unroll
-    for (int j = 0; j < kTS_N / 8; ++j) {
+    for (int j = 0; j < kTS_EpiCols / 8; ++j) {
         float m = __uint_as_float(v[j >> 2][(j & 3) * 8]);
 #pragma unroll
         for (int c = 1; c < 8; ++c) m = fmaxf(m, __uint_as_float(v[j >> 2][(j & 3) * 8 + c]));
@@ -419,7 +421,7 @@ __device__ __forceinline__ void dense_ts_filter_append(const DenseTsArgs& a, uin
     }
     float m = gm[0];
 #pragma unroll
-    for (int j = 1; j < kTS_N / 8; ++j) m = fmaxf(m, gm[j]);
+    for (int j = 1; j < kTS_EpiCols / 8; ++j) m = fmaxf(m, gm[j]);
     if (!(m > tau_q)) return;                                              // the common exit of (almost) every lane
     uint32_t* cnt = a.cnt + slot;
     float* cs = a.cand_score + (size_t)slot * a.cap;
@@ -427,7 +429,7 @@ __device__ __forceinline__ void dense_ts_filter_append(const DenseTsArgs& a, uin
     const int32_t r0 = (int32_t)row0;
     const uint32_t cap = (uint32_t)a.cap;
 #pragma unroll
-    for (int j = 0; j < kTS_N / 8; ++j) {
+    for (int j = 0; j < kTS_EpiCols / 8; ++j) {
         if (gm[j] > tau_q) {
             uint32_t n = 0;
 #pragma unroll
@@ -447,18 +449,18 @@ __device__ __forceinline__ void dense_ts_filter_append(const DenseTsArgs& a, uin
 
 // The same filter appending to this CTA's own segment of the query's candidate list: the thread is the only writer of
 // (slot, segment), so its running count lives in a register (`my_cnt`, stored once when the kernel ends): no atomics, no round trip.
-__device__ __forceinline__ void dense_ts_filter_append_seg(const DenseTsArgs& a, uint32_t (&v)[kTS_N / 32][32], long long row0, float tau_q,
+__device__ __forceinline__ void dense_ts_filter_append_seg(const DenseTsArgs& a, uint32_t (&v)[kTS_EpiCols / 32][32], long long row0, float tau_q,
                                                            float* seg_s, int32_t* seg_r, uint32_t& my_cnt) {
-    if (!(row0 >= a.row_begin && row0 + kTS_N <= a.row_end)) {            // edge tile: rows outside the launch range never pass
+    if (!(row0 >= a.row_begin && row0 + kTS_EpiCols <= a.row_end)) {            // edge tile: rows outside the launch range never pass
 #pragma unroll
-        for (int c = 0; c < kTS_N; ++c) {
+        for (int c = 0; c < kTS_EpiCols; ++c) {
             const long long row = row0 + c;
             if (row < a.row_begin || row >= a.row_end) v[c >> 5][c & 31] = 0xFF800000u;      // -inf
         }
     }
-    float gm[kTS_N / 8];
+    float gm[kTS_EpiCols / 8];
 #pragma unroll
-    for (int j = 0; j < kTS_N / 8; ++j) {
+    for (int j = 0; j < kTS_EpiCols / 8; ++j) {
         float m = __uint_as_float(v[j >> 2][(j & 3) * 8]);
 #pragma unroll
         for (int c = 1; c < 8; ++c) m = fmaxf(m, __uint_as_float(v[j >> 2][(j & 3) * 8 + c]));
@@ -466,12 +468,12 @@ __device__ __forceinline__ void dense_ts_filter_append_seg(const DenseTsArgs& a,
     }
     float m = gm[0];
 #pragma unroll
-    for (int j = 1; j < kTS_N / 8; ++j) m = fmaxf(m, gm[j]);
+    for (int j = 1; j < kTS_EpiCols / 8; ++j) m = fmaxf(m, gm[j]);
     if (!(m > tau_q)) return;                                              // the common exit of (almost) every lane
     const int32_t r0 = (int32_t)row0;
     uint32_t pos = my_cnt;
 #pragma unroll
-    for (int j = 0; j < kTS_N / 8; ++j) {
+    for (int j = 0; j < kTS_EpiCols / 8; ++j) {
         if (gm[j] > tau_q) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -510,7 +512,7 @@ dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], a.cluster ? 2 : 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }   // only [0] is used (one accumulator)
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kTS_EpiWarps); }   // only [0] is used (one accumulator)
         mbar_init(&q_bar, 1);
         mbar_fence_init();
     }
@@ -537,7 +539,7 @@ dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
         const int quarter = warp & 3;
         const int qi = quarter * 32 + lane;
         mbar_wait(&q_bar, 0);
-        for (int kb = 0; kb < a.n_kblocks; ++kb) {
+        for (int kb = (warp - 2) >> 2; kb < a.n_kblocks; kb += kTS_EpiWarps / 4) {
             const uint8_t* row = ring + (size_t)kb * (kTS_M * kDT_KB * 2) + (size_t)qi * 128;
             uint32_t r[32];
 #pragma unroll
@@ -632,37 +634,37 @@ dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
             if (lane == 0) K2_TRACE(4, i);
         }
     } else {
-        // ===== epilogue warps: TMEM lane quarter = warp % 4; thread = one query, registers = 128 passages =====
-        const int quarter = warp & 3;
+        // ===== epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4; thread = one query x 64 passages =====
+        const int quarter = warp & 3, chalf = (warp - 2) >> 2;
         const int qi = quarter * 32 + lane;
         const int slot = qg * kTS_M + qi;
         const bool q_ok = slot < a.n_queries;
         const float tau_q = (q_ok && (a.mode == 0 || a.mode == 3)) ? a.tau[slot] : INFINITY;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a_cols;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a_cols + (uint32_t)(chalf * kTS_EpiCols);
         const bool use_seg = a.seg_cnt != nullptr && q_ok && (a.mode == 0 || a.mode == 3);
-        const size_t seg0 = ((size_t)(q_ok ? slot : 0) * kSegCount + (size_t)cta_in_q) * kSegCap;
+        const size_t seg_id = (size_t)(q_ok ? slot : 0) * kSegCount + (size_t)(cta_in_q * (kTS_EpiWarps / 4) + chalf);   // this thread's own list segment
         uint32_t my_cnt = 0;
         int i = 0;
         for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q, ++i) {
             mbar_wait(&tfull_bar[0], (uint32_t)i & 1u);
             tc_fence_after();
             if (threadIdx.x == 64) K2_TRACE(5, i);
-            uint32_t v[kTS_N / 32][32];
+            uint32_t v[kTS_EpiCols / 32][32];
 #pragma unroll
-            for (int j = 0; j < kTS_N / 32; ++j) tmem_ld_32x32(taddr + 32u * j, v[j]);
+            for (int j = 0; j < kTS_EpiCols / 32; ++j) tmem_ld_32x32(taddr + 32u * j, v[j]);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[0]);                  // D is free again: the next tile's MMAs may start
             if (threadIdx.x == 64) K2_TRACE(6, i);
-            const long long row0 = a.tile_row0 + (long long)t * kTS_N;
+            const long long row0 = a.tile_row0 + (long long)t * kTS_N + chalf * kTS_EpiCols;
             if (a.mode >= 2) dense_ts_add_scratch(a, v, slot, row0);
             if (K2_DBG() & 4) {
             } else if (a.mode == 1 || a.mode == 2) dense_ts_store_scratch(a, v, slot, row0);
-            else if (use_seg) dense_ts_filter_append_seg(a, v, row0, tau_q, a.seg_score + seg0, a.seg_row + seg0, my_cnt);
+            else if (use_seg) dense_ts_filter_append_seg(a, v, row0, tau_q, a.seg_score + seg_id * kSegCap, a.seg_row + seg_id * kSegCap, my_cnt);
             else dense_ts_filter_append(a, v, slot, row0, tau_q);
         }
-        if (use_seg) a.seg_cnt[(size_t)slot * kSegCount + cta_in_q] = my_cnt;
+        if (use_seg) a.seg_cnt[seg_id] = my_cnt;
     }
     if (threadIdx.x == 64) K2_TRACE(0, 3);
     tc_fence_before();
@@ -740,7 +742,7 @@ dense_tile_ts2_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_c
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&tfull_bar, 1);
-        mbar_init(&tempty_bar, 8);
+        mbar_init(&tempty_bar, 2 * kTS_EpiWarps);
         mbar_init(&q_bar, 1);
         mbar_fence_init();
     }
@@ -762,7 +764,7 @@ dense_tile_ts2_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_c
         const int quarter = warp & 3;
         const int qi = quarter * 32 + lane;
         mbar_wait(&q_bar, 0);
-        for (int kb = 0; kb < a.n_kblocks; ++kb) {
+        for (int kb = (warp - 2) >> 2; kb < a.n_kblocks; kb += kTS_EpiWarps / 4) {
             const uint8_t* row = ring + (size_t)kb * (kTS_M * kDT_KB * 2) + (size_t)qi * 128;
             uint32_t r[32];
 #pragma unroll
@@ -844,35 +846,35 @@ dense_tile_ts2_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_c
             }
         }
     } else {
-        // ===== epilogue warps (both CTAs): thread = one query of this CTA's group, registers = 128 passages =====
-        const int quarter = warp & 3;
+        // ===== epilogue warps (both CTAs): thread = one query of this CTA's group x 64 passages (column half = (warp - 2) / 4) =====
+        const int quarter = warp & 3, chalf = (warp - 2) >> 2;
         const int qi = quarter * 32 + lane;
         const int slot = qg * kTS_M + qi;
         const bool q_ok = slot < a.n_queries;
         const float tau_q = (q_ok && (a.mode == 0 || a.mode == 3)) ? a.tau[slot] : INFINITY;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a_cols;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a_cols + (uint32_t)(chalf * kTS_EpiCols);
         const uint32_t tempty_leader = mapa_shared(smem_u32(&tempty_bar), 0u);
         const bool use_seg = a.seg_cnt != nullptr && q_ok && (a.mode == 0 || a.mode == 3);
-        const size_t seg0 = ((size_t)(q_ok ? slot : 0) * kSegCount + (size_t)pair) * kSegCap;
+        const size_t seg_id = (size_t)(q_ok ? slot : 0) * kSegCount + (size_t)(pair * (kTS_EpiWarps / 4) + chalf);
         uint32_t my_cnt = 0;
         int i = 0;
         for (int t = pair; t < a.n_tiles; t += n_pairs, ++i) {
             mbar_wait(&tfull_bar, (uint32_t)i & 1u);
             tc_fence_after();
-            uint32_t v[kTS_N / 32][32];
+            uint32_t v[kTS_EpiCols / 32][32];
 #pragma unroll
-            for (int j = 0; j < kTS_N / 32; ++j) tmem_ld_32x32(taddr + 32u * j, v[j]);
+            for (int j = 0; j < kTS_EpiCols / 32; ++j) tmem_ld_32x32(taddr + 32u * j, v[j]);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(tempty_leader);           // D of this CTA is free again
-            const long long row0 = a.tile_row0 + (long long)t * kTS_N;
+            if (lane == 0) mbar_arrive_cluster(tempty_leader);           // this warp's part of this CTA's D is free again
+            const long long row0 = a.tile_row0 + (long long)t * kTS_N + chalf * kTS_EpiCols;
             if (a.mode >= 2) dense_ts_add_scratch(a, v, slot, row0);
             if (a.mode == 1 || a.mode == 2) dense_ts_store_scratch(a, v, slot, row0);
-            else if (use_seg) dense_ts_filter_append_seg(a, v, row0, tau_q, a.seg_score + seg0, a.seg_row + seg0, my_cnt);
+            else if (use_seg) dense_ts_filter_append_seg(a, v, row0, tau_q, a.seg_score + seg_id * kSegCap, a.seg_row + seg_id * kSegCap, my_cnt);
             else dense_ts_filter_append(a, v, slot, row0, tau_q);
         }
-        if (use_seg) a.seg_cnt[(size_t)slot * kSegCount + pair] = my_cnt;
+        if (use_seg) a.seg_cnt[seg_id] = my_cnt;
     }
     tc_fence_before();
     cluster_sync_all();                          // no CTA of the pair exits (or frees TMEM) while the other may still signal it
@@ -1000,6 +1002,7 @@ int launch_dense_pass(const dhr_index* h, const __half* blocked, const __half* r
             cfg.gridDim = dim3((unsigned)(per_q * 2));
         }
     }
+    if (per_q * (kTS_EpiWarps / 4) > kSegCount) { a.seg_score = nullptr; a.seg_row = nullptr; a.seg_cnt = nullptr; }   // more writers than list segments: atomics
     // with multicast / the CTA-pair form the corpus map delivers half a stage (64 passages) per load
     const int box_rows = a.cluster ? kTS_N / 2 : kTS_N;
     if (blocked)

@@ -34,8 +34,8 @@ struct TopkState {
     int32_t*  seg_row = nullptr;
     uint32_t* seg_cnt = nullptr;         // [slots][kSegCount] appended per segment (may exceed kSegCap -> overflow); zeroed before a scan launch
 };
-constexpr int kSegCount = 160;           // >= CTAs that can work on one query group in one launch (SMs of the device)
-constexpr int kSegCap = 512;             // per (slot, CTA) and chunk: the first chunk hands a CTA <= 2 tiles of 128 rows, later chunks ~100 rows
+constexpr int kSegCount = 320;           // >= 2 x CTAs that can work on one query group in one launch (two epilogue warps per TMEM lane quadrant, each its own writer); multiple of 32
+constexpr int kSegCap = 256;             // per (slot, CTA) and chunk: the first chunk hands a CTA <= 2 tiles of 128 rows, later chunks ~100 rows
 
 struct EventPool {
     std::vector<cudaEvent_t> ev;
