@@ -26,7 +26,7 @@ namespace dhr {
 // Timeline hooks of the micro-benchmark harness (tools/k2_micro.cu defines DHR_K2_TRACE); compiled out of the library.
 #ifdef DHR_K2_TRACE
 __device__ long long g_k2_trace[8][64];
-__device__ int g_k2_dbg;       // experiment bits (TS kernel): 4 = no epilogue stores, 8 = free-running MMA (no corpus loads, no stage barriers)
+__device__ int g_k2_dbg;       // experiment bits (TS kernel): 4 = no epilogue stores, 8 = free-running MMA (no corpus loads, no stage barriers), 16 = no MMAs (corpus stream + barriers only)
 #define K2_TRACE(role, idx) do { if (blockIdx.x == 0 && (idx) < 64) g_k2_trace[role][idx] = clock64(); } while (0)
 #define K2_DBG() g_k2_dbg
 #else
@@ -359,6 +359,8 @@ struct DenseTsArgs {
     long long scratch_slots;
     float* tau; uint32_t* cnt; float* cand_score; int32_t* cand_row; int cap;
     float* seg_score; int32_t* seg_row; uint32_t* seg_cnt;   // segmented candidate lists (filter modes) or nullptr: append with atomics
+    const void* blocked_ptr;           // the K-blocked copy (experiments: plain bulk copies instead of tensor-map loads)
+    int prefetch;                      // TMA L2 prefetch of the tile kTS_Prefetch iterations ahead (option dense_prefetch)
 };
 
 // ---- epilogue bodies shared by the cta_group::1 and cta_group::2 kernels: thread = one query, v = the scores of its kTS_EpiCols passages starting at row0 ----
@@ -502,6 +504,7 @@ dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
     __shared__ __align__(8) uint64_t q_bar;
     __shared__ uint32_t tmem_base_smem;
 
+    const int k2dbg = K2_DBG();                                        // experiment bits, read once (0 in the library build)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) K2_TRACE(0, 0);
     const int qg = blockIdx.x % a.n_qgroups;
@@ -571,15 +574,15 @@ dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
             if (lane == 0) K2_TRACE(1, i);
             const int row0 = (int)(a.tile_row0 + (long long)t * kTS_N);
             const int blk0 = row0 / kTS_N * a.n_kblocks * kTS_N;                  // first row of the tile's k-block 0 in the blocked copy
-            const bool do_pf = qg == 0 && t + pf_tiles < a.n_tiles;
+            const bool do_pf = a.prefetch && qg == 0 && t + pf_tiles < a.n_tiles;
             for (int kb = 0; kb < a.n_kblocks; ++kb) {
-                if (K2_DBG() & 8) continue;
+                if (k2dbg & 8) continue;
                 mbar_wait_u32(empty_s + 8u * s, ph ^ 1u);
                 if (elect_one()) {
                     // the ring holds exactly one corpus tile, so the demand load is issued only one tile-time ahead of its use:
                     // pull the same k-block of the tile `kTS_Prefetch` iterations further on into L2 now (HBM latency off the
                     // critical path); the two query groups share tiles, group 0 prefetches
-                    if (do_pf) {
+                    if (do_pf && !(k2dbg & 64)) {
                         if (a.blocked) tma_prefetch_l2_2d(&tmap_c, 0, blk0 + (pf_tiles * a.n_kblocks + kb) * kTS_N);
                         else tma_prefetch_l2_2d(&tmap_c, kb * kDT_KB, row0 + pf_tiles * kTS_N);
                     }
@@ -587,7 +590,18 @@ dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
                     const uint32_t dst = ring_s + (uint32_t)s * kTS_BBytes + half_off;
                     mbar_arrive_expect_tx_u32(bar, kTS_BBytes);                   // both halves (own + peer's multicast)
                     const int c0 = a.blocked ? 0 : kb * kDT_KB;
-                    const int c1 = (a.blocked ? blk0 + kb * kTS_N : row0) + half_rows;
+                    int c1 = (a.blocked ? blk0 + kb * kTS_N : row0) + half_rows;
+                    if (k2dbg & 256) {          // stream-rate experiment: every CTA reads its own contiguous range of tiles
+                        const int per = a.n_tiles / ctas_per_q;
+                        c1 = (int)(((long long)(cta_in_q * per + (i % (per > 0 ? per : 1))) * a.n_kblocks + kb) % ((long long)a.n_tiles * a.n_kblocks)) * kTS_N + half_rows;
+                    }
+                    if (k2dbg & 128)            // stream-rate experiment: blocks read at one instant by all CTAs are adjacent in memory
+                        c1 = (int)(((long long)(i * a.n_kblocks + kb) * ctas_per_q + cta_in_q) % ((long long)a.n_tiles * a.n_kblocks)) * kTS_N + half_rows;
+                    if ((k2dbg & 32) && !a.cluster) {
+                        const char* src = (const char*)a.blocked_ptr + (size_t)(blk0 + kb * kTS_N) * 128u;
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(dst), "l"(src), "r"((uint32_t)kTS_BBytes), "r"(bar) : "memory");
+                    } else
                     if (a.cluster) tma_load_2d_multicast_u32(dst, &tmap_c, bar, c0, c1, 3);
                     else tma_load_2d_u32(dst, &tmap_c, bar, c0, c1);
                 }
@@ -613,15 +627,19 @@ dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
             tc_fence_after();
             if (lane == 0) K2_TRACE(3, i);
             for (int kb = 0; kb < a.n_kblocks; ++kb) {
-                if (!(K2_DBG() & 8)) mbar_wait_u32(full_s + 8u * s, ph);
+                if (!(k2dbg & 8)) mbar_wait_u32(full_s + 8u * s, ph);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t bd = desc0 + (uint64_t)((uint32_t)s * (kTS_BBytes >> 4));
                     const uint32_t at = tmem_u + (uint32_t)kb * 32u;
+                    if (!(k2dbg & 16)) {
 #pragma unroll
-                    for (int k = 0; k < kDT_KB / 16; ++k)
-                        umma_f16_ts(d_tmem, at + (uint32_t)k * 8u, bd + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-                    if (!(K2_DBG() & 8)) {                                // frees the corpus stage once these MMAs have read it
+                        for (int k = 0; k < kDT_KB / 16; ++k)
+                            umma_f16_ts(d_tmem, at + (uint32_t)k * 8u, bd + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    if (!(k2dbg & 8)) {                                // frees the corpus stage once these MMAs have read it
+                        if ((k2dbg & 1024) && !a.cluster) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_s + 8u * s) : "memory");
+                        else
                         if (a.cluster) umma_commit_multicast_u32(empty_s + 8u * s, 3);
                         else umma_commit_u32(empty_s + 8u * s);
                     }
@@ -657,9 +675,21 @@ dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[0]);                  // D is free again: the next tile's MMAs may start
             if (threadIdx.x == 64) K2_TRACE(6, i);
+            if ((k2dbg & 512) && a.blocked) {
+                const int tp = t + ((k2dbg >> 12) & 7) * ctas_per_q;
+                if (tp < a.n_tiles) {
+                    const char* pbase = (const char*)a.blocked_ptr + (size_t)(a.tile_row0 / kTS_N + tp) * a.n_kblocks * kTS_BBytes;
+                    const int nshare = a.cluster ? 2 : 1;
+                    const int n256 = a.n_kblocks * kTS_BBytes / 256;
+                    for (int u = ((int)threadIdx.x - 64) * nshare + (int)crank; u < n256; u += 32 * kTS_EpiWarps * nshare) {
+                        uint32_t dummy;
+                        asm volatile("ld.global.nc.L1::no_allocate.L2::256B.u32 %0, [%1];" : "=r"(dummy) : "l"(pbase + (size_t)u * 256));
+                    }
+                }
+            }
             const long long row0 = a.tile_row0 + (long long)t * kTS_N + chalf * kTS_EpiCols;
             if (a.mode >= 2) dense_ts_add_scratch(a, v, slot, row0);
-            if (K2_DBG() & 4) {
+            if (k2dbg & 4) {
             } else if (a.mode == 1 || a.mode == 2) dense_ts_store_scratch(a, v, slot, row0);
             else if (use_seg) dense_ts_filter_append_seg(a, v, row0, tau_q, a.seg_score + seg_id * kSegCap, a.seg_row + seg_id * kSegCap, my_cnt);
             else dense_ts_filter_append(a, v, slot, row0, tau_q);
@@ -731,6 +761,7 @@ dense_tile_ts2_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_c
     __shared__ __align__(8) uint64_t q_bar;
     __shared__ uint32_t tmem_base_smem;
 
+    const int k2dbg = K2_DBG();                                        // experiment bits, read once (0 in the library build)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t crank = cluster_ctarank();
     const bool leader = crank == 0;
@@ -791,11 +822,12 @@ dense_tile_ts2_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_c
         for (int t = pair; t < a.n_tiles; t += n_pairs) {
             const int row0 = (int)(a.tile_row0 + (long long)t * kTS_N);
             const int blk0 = row0 / kTS_N * a.n_kblocks * kTS_N;
-            const bool do_pf = leader && t + pf_tiles < a.n_tiles;
+            const bool do_pf = a.prefetch && leader && t + pf_tiles < a.n_tiles;
             for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                if (k2dbg & 8) continue;
                 mbar_wait_u32(empty_s + 8u * s, ph ^ 1u);
                 if (elect_one()) {
-                    if (do_pf) {
+                    if (do_pf && !(k2dbg & 64)) {
                         if (a.blocked) tma_prefetch_l2_2d(&tmap_c, 0, blk0 + (pf_tiles * a.n_kblocks + kb) * kTS_N);
                         else tma_prefetch_l2_2d(&tmap_c, kb * kDT_KB, row0 + pf_tiles * kTS_N);
                     }
@@ -825,14 +857,17 @@ dense_tile_ts2_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_c
                 mbar_wait_u32(tempty_s, ((uint32_t)i & 1u) ^ 1u);
                 tc_fence_after();
                 for (int kb = 0; kb < a.n_kblocks; ++kb) {
-                    mbar_wait_u32(full_s + 8u * s, ph);
+                    if (!(k2dbg & 8)) mbar_wait_u32(full_s + 8u * s, ph);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t bd = desc0 + (uint64_t)((uint32_t)s * (kTS2_StageBytes >> 4));
                         const uint32_t at = tmem_u + (uint32_t)kb * 32u;
+                        if (!(k2dbg & 16)) {
 #pragma unroll
-                        for (int k = 0; k < kDT_KB / 16; ++k)
-                            umma_f16_ts_2sm(d_tmem, at + (uint32_t)k * 8u, bd + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < kDT_KB / 16; ++k)
+                                umma_f16_ts_2sm(d_tmem, at + (uint32_t)k * 8u, bd + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        if (!(k2dbg & 8))
                         asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                                      ::"r"(empty_s + 8u * s), "h"((uint16_t)3) : "memory");     // both CTAs may refill the stage
                     }
@@ -870,6 +905,8 @@ dense_tile_ts2_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_c
             if (lane == 0) mbar_arrive_cluster(tempty_leader);           // this warp's part of this CTA's D is free again
             const long long row0 = a.tile_row0 + (long long)t * kTS_N + chalf * kTS_EpiCols;
             if (a.mode >= 2) dense_ts_add_scratch(a, v, slot, row0);
+            if (k2dbg & 4) {
+            } else
             if (a.mode == 1 || a.mode == 2) dense_ts_store_scratch(a, v, slot, row0);
             else if (use_seg) dense_ts_filter_append_seg(a, v, row0, tau_q, a.seg_score + seg_id * kSegCap, a.seg_row + seg_id * kSegCap, my_cnt);
             else dense_ts_filter_append(a, v, slot, row0, tau_q);
@@ -958,6 +995,8 @@ int launch_dense_pass(const dhr_index* h, const __half* blocked, const __half* r
     a.scratch = scratch; a.scratch_slots = scratch_slots;
     a.tau = t.tau; a.cnt = t.cnt; a.cand_score = t.cand_score; a.cand_row = t.cand_row; a.cap = cap;
     a.seg_score = t.seg_score; a.seg_row = t.seg_row; a.seg_cnt = t.seg_cnt;
+    a.blocked_ptr = blocked;
+    a.prefetch = h->opt_dense_prefetch;
     const size_t smem = (size_t)a.n_stages * kTS_BBytes + 1024;
     DHR_CUDA(cudaFuncSetAttribute(dense_tile_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DHR_CUDA(cudaFuncSetAttribute(dense_tile_ts2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTS2_MaxStages * kTS2_StageBytes + 1024));

@@ -675,6 +675,7 @@ int dhr_index_set_option(dhr_index* h, const char* name, int64_t value) {
     }
     if (!strcmp(name, "query_groups")) { if (value < 1 || value > kMaxScanInflight) return DHR_ERR_INVALID; h->opt_query_groups = (int)value; return DHR_OK; }
     if (!strcmp(name, "tile_mode")) { h->opt_tile_mode = value != 0; return DHR_OK; }
+    if (!strcmp(name, "dense_prefetch")) { if (value < 0 || value > 1) return DHR_ERR_INVALID; h->opt_dense_prefetch = (int)value; return DHR_OK; }
     if (!strcmp(name, "dense_multicast")) { if (value < 0 || value > 2) return DHR_ERR_INVALID; h->opt_dense_multicast = (int)value; return DHR_OK; }
     if (!strcmp(name, "lanes")) { if (value < 1 || value > 2) return DHR_ERR_INVALID; h->opt_lanes = (int)value; return DHR_OK; }
     if (!strcmp(name, "overlap")) { h->opt_overlap = value != 0; return DHR_OK; }

@@ -109,6 +109,7 @@ struct dhr_index {
     int opt_profile = 0;
     int opt_tile_mode = 1;               // use the tensor-core tile kernels when the shape allows
     int opt_overlap = 1;                 // hybrid tile path: run K2 on a second stream, one sub-chunk ahead of K1t
+    int opt_dense_prefetch = 0;          // K2: TMA L2 prefetch two tiles ahead of the demand loads (measured slower on B200 once the ring holds a whole tile: 0)
     int opt_dense_multicast = 1;         // K2 (TS): the two query groups of a batch share corpus tiles as a cluster of two CTAs (0 off, 1 dense-only searches, 2 always)
     int opt_dense_variant = 3;           // K2: 0 = both operands in shared memory (SS), 1 = queries in TMEM (TS), 2 = TS as a CTA pair (cta_group::2, M = 256), 3 = auto (2 for filter-mode launches, 1 for scratch-mode ones)
     int num_sms = 148;

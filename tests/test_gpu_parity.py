@@ -414,6 +414,7 @@ def test_tile_path_options_agree():
                 ix.set_option('dense_variant', dv)
                 ix.set_option('overlap', ov)
                 ix.set_option('dense_multicast', 2 if ov else 0)       # cluster-of-two multicast also in scratch mode
+                ix.set_option('dense_prefetch', ov)                    # TMA L2 prefetch ahead of the demand loads
                 outs.append(ix.search(case['q_vals'], case['q_idx'], k))
                 assert ix.stats()['scan_variant'] == 3, 'tile path not taken'
     sub = dict(case)

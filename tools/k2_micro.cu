@@ -19,6 +19,36 @@ __global__ void fill_random_halves(__half* p, size_t n, unsigned seed, float sca
     }
 }
 
+__global__ void read_stream_kernel(const uint4* p, size_t n, unsigned* out) {
+    unsigned acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint4 v; asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p + i));
+        acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+    if (acc == 0x12345678u) *out = acc;
+}
+
+// the K2 access pattern with plain loads: block c reads tiles c, c + grid, ... of 192 KiB each (or, `range`, its own contiguous run)
+__global__ void __launch_bounds__(1024) pattern_read_kernel(const uint4* p, int n_tiles, int tile_u4, int range, unsigned* out) {
+    unsigned acc = 0;
+    const int per = n_tiles / gridDim.x;
+    for (int i = 0; i < per; ++i) {
+        const int t = range ? blockIdx.x * per + i : i * gridDim.x + blockIdx.x;
+        const uint4* q = p + (size_t)t * tile_u4;
+        for (int u = threadIdx.x; u < tile_u4; u += 4096) {
+            uint4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (u + j * 1024 < tile_u4)
+                    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[j].x), "=r"(v[j].y), "=r"(v[j].z), "=r"(v[j].w) : "l"(q + u + j * 1024));
+                else v[j] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc ^= v[j].x ^ v[j].y ^ v[j].z ^ v[j].w;
+        }
+    }
+    if (acc == 0x12345678u) *out = acc;
+}
+
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e_)); return 1; } } while (0)
 
 int main(int argc, char** argv) {
@@ -48,10 +78,41 @@ int main(int argc, char** argv) {
     const float tau_arg = argc > 7 ? (float)atof(argv[7]) : 0.f;            // finite admission threshold for the dense-only (mode 0) runs
     CK(cudaMalloc(&t.cand_score, (size_t)256 * 16384 * 4)); CK(cudaMalloc(&t.cand_row, (size_t)256 * 16384 * 4));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    const int dbgs[] = {0, 0, 0, 4, 12, 0};
-    const int mcast[] = {1, 0, 1, 1, 1, 1};
-    for (int vi = 0; vi < 6; ++vi) {
-        const int variant = vi == 0 ? 0 : (vi == 5 ? 2 : 1);
+    if (h.dnst) {     // calibration: the K2 tile order with plain loads
+        const int n_tiles = (int)(sub / 128), tile_u4 = ((h.g.C_pad + 63) / 64) * 16384 / 16;
+        for (int mode = 0; mode < 4; ++mode) {
+            const int blocks = (mode & 2) ? 296 : 148, range = mode & 1;
+            std::vector<float> ms;
+            for (int i = 0; i < 20; ++i) {
+                cudaEventRecord(e0);
+                pattern_read_kernel<<<blocks, 1024>>>((const uint4*)((const char*)h.dnst + (size_t)i * n_tiles * tile_u4 * 16), n_tiles, tile_u4, range, (unsigned*)t.cnt);
+                cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+                float m; cudaEventElapsedTime(&m, e0, e1); ms.push_back(m);
+            }
+            std::sort(ms.begin(), ms.end());
+            printf("read stream, K2 tile order (%d blocks x 1024 threads, %s): median %.1f us -> %.0f GB/s\n", blocks, range ? "contiguous run per block" : "tiles interleaved over blocks",
+                   ms[10] * 1e3, (double)(n_tiles / blocks * blocks) * tile_u4 * 16 / (ms[10] * 1e-3) / 1e9);
+        }
+    }
+    if (h.dnst) {     // calibration: plain vector-load read stream over the same buffer
+        const size_t nb = (size_t)sub * h.g.C_pad * 2;
+        for (int blocks : {148 * 4, 148 * 8, 148 * 16}) {
+            std::vector<float> ms;
+            for (int i = 0; i < 20; ++i) {
+                cudaEventRecord(e0);
+                read_stream_kernel<<<blocks, 512>>>((const uint4*)((const char*)h.dnst + (size_t)i * nb), nb / 16, (unsigned*)t.cnt);
+                cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+                float m; cudaEventElapsedTime(&m, e0, e1); ms.push_back(m);
+            }
+            std::sort(ms.begin(), ms.end());
+            printf("read stream (ld.global.nc.v4, %d x 512 threads): median %.1f us -> %.0f GB/s\n", blocks, ms[10] * 1e3, nb / (ms[10] * 1e-3) / 1e9);
+        }
+    }
+    const int dbgs[] =  {0, 64, 0, 64, 4, 12, 20, 84, 0, 64, 4, 68, 12, 20, 84};
+    const int mcast[] = {0, 0,  1, 1,  1, 1,  1,  1,  1, 1,  1, 1,  1,  1,  1};
+    const int vars[] =  {1, 1,  1, 1,  1, 1,  1,  1,  2, 2,  2, 2,  2,  2,  2};
+    for (int vi = 0; vi < 15; ++vi) {
+        const int variant = vars[vi];
         const int dbg = dbgs[vi];
         CK(cudaMemcpyToSymbol(dhr::g_k2_dbg, &dbg, sizeof(int)));
         h.opt_dense_variant = variant;
@@ -68,7 +129,7 @@ int main(int argc, char** argv) {
         }
         std::sort(ms.begin(), ms.end());
         const double flops = 2.0 * sub * nq * C;
-        printf("dbg %2d multicast %d variant %d (%s): median %.1f us  min %.1f us  -> %.0f TFLOP/s, corpus read %.0f GB/s\n", dbg, mcast[vi], variant, variant == 2 ? "TS 2-CTA" : (variant ? "TS" : "SS"),
+        printf("dbg %5d multicast %d variant %d (%s): median %.1f us  min %.1f us  -> %.0f TFLOP/s, corpus read %.0f GB/s\n", dbg, mcast[vi], variant, variant == 2 ? "TS 2-CTA" : (variant ? "TS" : "SS"),
                ms[20] * 1e3, ms[0] * 1e3, flops / (ms[20] * 1e-3) / 1e12, sub * h.g.C_pad * 2.0 / (ms[20] * 1e-3) / 1e9);
     }
     // dense-only mode (filter + append, nothing passes tau): one launch over all rows, both variants
