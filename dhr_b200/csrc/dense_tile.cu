@@ -673,7 +673,8 @@ dense_tile_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[0]);                  // D is free again: the next tile's MMAs may start
+            if (lane == 0)                                               // D is free again: the next tile's MMAs may start (relaxed: see mbar_arrive_cluster_relaxed)
+                asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty_bar[0])) : "memory");
             if (threadIdx.x == 64) K2_TRACE(6, i);
             if ((k2dbg & 512) && a.blocked) {
                 const int tp = t + ((k2dbg >> 12) & 7) * ctas_per_q;
@@ -728,6 +729,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta_rank
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// The accumulator-drained signal orders no memory: the TMEM reads are complete (tcgen05.wait::ld) and fenced
+// (tcgen05.fence::before_thread_sync).  A release arrive would also wait for the thread's earlier global stores (the previous
+// tile's candidate / scratch writes) -- measured: the dominant part of the per-tile bubble.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA 2-D load into THIS CTA's shared memory whose completion is counted on a barrier of the CTA pair's leader
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* tmap, uint32_t bar_cluster_addr, int c0, int c1) {
@@ -854,7 +861,7 @@ dense_tile_ts2_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_c
             int s = 0; uint32_t ph = 0;
             int i = 0;
             for (int t = pair; t < a.n_tiles; t += n_pairs, ++i) {
-                mbar_wait_u32(tempty_s, ((uint32_t)i & 1u) ^ 1u);
+                if (!(k2dbg & 2048)) mbar_wait_u32(tempty_s, ((uint32_t)i & 1u) ^ 1u);
                 tc_fence_after();
                 for (int kb = 0; kb < a.n_kblocks; ++kb) {
                     if (!(k2dbg & 8)) mbar_wait_u32(full_s + 8u * s, ph);
@@ -867,6 +874,10 @@ dense_tile_ts2_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_c
                             for (int k = 0; k < kDT_KB / 16; ++k)
                                 umma_f16_ts_2sm(d_tmem, at + (uint32_t)k * 8u, bd + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
                         }
+                        if (k2dbg & 1024) {                                // experiment: software arrives instead of the commit
+                            mbar_arrive_cluster(mapa_shared(empty_s + 8u * s, 0u));
+                            mbar_arrive_cluster(mapa_shared(empty_s + 8u * s, 1u));
+                        } else
                         if (!(k2dbg & 8))
                         asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                                      ::"r"(empty_s + 8u * s), "h"((uint16_t)3) : "memory");     // both CTAs may refill the stage
@@ -874,7 +885,7 @@ dense_tile_ts2_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_c
                     __syncwarp();
                     if (++s == a.n_stages) { s = 0; ph ^= 1u; }
                 }
-                if (elect_one())                                           // accumulator tile complete in both CTAs
+                if (!(k2dbg & 2048) && elect_one())                        // accumulator tile complete in both CTAs
                     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                                  ::"r"(tfull_s), "h"((uint16_t)3) : "memory");
                 __syncwarp();
@@ -894,6 +905,7 @@ dense_tile_ts2_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_c
         uint32_t my_cnt = 0;
         int i = 0;
         for (int t = pair; t < a.n_tiles; t += n_pairs, ++i) {
+            if (k2dbg & 2048) break;
             mbar_wait(&tfull_bar, (uint32_t)i & 1u);
             tc_fence_after();
             uint32_t v[kTS_EpiCols / 32][32];
@@ -902,7 +914,7 @@ dense_tile_ts2_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_c
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(tempty_leader);           // this warp's part of this CTA's D is free again
+            if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader);   // this warp's part of this CTA's D is free again
             const long long row0 = a.tile_row0 + (long long)t * kTS_N + chalf * kTS_EpiCols;
             if (a.mode >= 2) dense_ts_add_scratch(a, v, slot, row0);
             if (k2dbg & 4) {

@@ -108,10 +108,10 @@ int main(int argc, char** argv) {
             printf("read stream (ld.global.nc.v4, %d x 512 threads): median %.1f us -> %.0f GB/s\n", blocks, ms[10] * 1e3, nb / (ms[10] * 1e-3) / 1e9);
         }
     }
-    const int dbgs[] =  {0, 64, 0, 64, 4, 12, 20, 84, 0, 64, 4, 68, 12, 20, 84};
-    const int mcast[] = {0, 0,  1, 1,  1, 1,  1,  1,  1, 1,  1, 1,  1,  1,  1};
-    const int vars[] =  {1, 1,  1, 1,  1, 1,  1,  1,  2, 2,  2, 2,  2,  2,  2};
-    for (int vi = 0; vi < 15; ++vi) {
+    const int dbgs[] =  {0, 4, 12, 84, 84 + 2048, 64 + 2048, 0, 0, 4, 84, 0, 0};
+    const int mcast[] = {1, 1, 1,  1,  1,  1,  0, 1, 1, 1, 1, 1};
+    const int vars[] =  {2, 2, 2,  2,  2,  2,  1, 1, 1, 1, 2, 2};
+    for (int vi = 0; vi < 10; ++vi) {
         const int variant = vars[vi];
         const int dbg = dbgs[vi];
         CK(cudaMemcpyToSymbol(dhr::g_k2_dbg, &dbg, sizeof(int)));
