@@ -119,7 +119,9 @@ int dhr_index_device_bytes(const dhr_index* h, int64_t* bytes); /* HBM bytes the
 
 /* options: "scan_variant" (0|1), "query_block" (1|2|4|8), "query_groups" (1..64), "profile" (0|1), "tile_mode" (0|1),
  * "rowmajor" (0 = free the row-major arrays now and keep only the tiled copies; they are rebuilt on the first call that
- * needs them -- fp32 / lamda-scaled queries, --IP, rerank, overflow fallback; 1 = make them resident now) */
+ * needs them -- fp32 / lamda-scaled queries, --IP, rerank, overflow fallback; 1 = make them resident now);
+ * tuning of the tile path (defaults are the measured best): "overlap" (0|1), "lanes" (1|2), "dense_variant" (0..3),
+ * "dense_multicast" (0..2), "dense_prefetch" (0|1: TMA L2 prefetch ahead of the dense tile loads, default 0) */
 int dhr_index_set_option(dhr_index* h, const char* name, int64_t value);
 int dhr_index_get_stats(const dhr_index* h, dhr_stats* out);
 
