@@ -361,6 +361,7 @@ struct DenseTsArgs {
     float* seg_score; int32_t* seg_row; uint32_t* seg_cnt;   // segmented candidate lists (filter modes) or nullptr: append with atomics
     const void* blocked_ptr;           // the K-blocked copy (experiments: plain bulk copies instead of tensor-map loads)
     int prefetch;                      // TMA L2 prefetch of the tile kTS_Prefetch iterations ahead (option dense_prefetch)
+    const void* q16; int q_pitch, q_cols;   // lite kernel: the prepared fp16 queries (row pitch in elements, valid columns)
 };
 
 // ---- epilogue bodies shared by the cta_group::1 and cta_group::2 kernels: thread = one query, v = the scores of its kTS_EpiCols passages starting at row0 ----
@@ -930,6 +931,151 @@ dense_tile_ts2_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_c
     if (warp == 1) tmem_dealloc_2sm(tmem_base, 512);
 }
 
+// ---- lite variant: K2 small enough to share an SM with a K1t CTA --------------------------------------------------------
+// In the hybrid path K2 (scratch mode) and K1t both wanted > 190 KB of shared memory, so they alternated on the SMs and K2's
+// 20 us per sub-chunk were lost to K1t.  K1t is bound by instruction issue and shared-memory wavefronts and uses no tensor
+// core, no TMEM and 43 K of the 64 K registers: this variant fits beside it -- 64-passage tiles through a 2-4 stage ring of
+// 8 KiB stages (the layout of the cta_group::2 kernel's half stages), the query operand read straight from global memory
+// into TMEM (no staging ring), two 64-column accumulators (no drain bubble), 192 threads under a 112-register cap, epilogue
+// = plain scratch stores (modes 1 and 2 only).  Slower than the big kernel when alone, free when it runs in K1t's shadow.
+constexpr int kTL_N = 64;
+// waits of the lite kernel back off: its six warps share the SM's issue slots with K1t's seventeen, and K1t is issue-bound
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_u32(bar, parity)) {
+        __nanosleep(128);
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+constexpr int kTL_StageBytes = kTL_N * kDT_KB * 2;   // 8 KiB
+constexpr int kTL_MaxStages = 8;
+constexpr int kTL_Threads = 192;                     // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue
+static_assert(kTL_N == kTS_EpiCols, "the shared epilogue bodies take 64 columns per thread");
+
+__global__ void __launch_bounds__(kTL_Threads, 3)
+dense_tile_lite_kernel(const __grid_constant__ CUtensorMap tmap_c, const DenseTsArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[kTL_MaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kTL_MaxStages];
+    __shared__ __align__(8) uint64_t tfull_bar[2];
+    __shared__ __align__(8) uint64_t tempty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qg = blockIdx.x % a.n_qgroups;
+    const int cta_in_q = blockIdx.x / a.n_qgroups;
+    const int ctas_per_q = gridDim.x / a.n_qgroups;
+    const uint32_t a_cols = (uint32_t)a.n_kblocks * 32u;
+    uint8_t* ring = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===== TMA producer: 64-passage x 64-column pieces of the K-blocked copy (8 KiB contiguous in HBM) =====
+        int s = 0; uint32_t ph = 0;
+        const uint32_t ring_s = smem_u32(ring), full_s = smem_u32(full_bar), empty_s = smem_u32(empty_bar);
+        for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q) {
+            const int row0 = (int)(a.tile_row0 + (long long)t * kTL_N);
+            const int blk0 = row0 / kTS_N * a.n_kblocks * kTS_N + (row0 % kTS_N);   // row of the half tile in k-block 0 of its 128-row block
+            for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                mbar_wait_sleep(empty_s + 8u * s, ph ^ 1u);
+                if (elect_one()) {
+                    const uint32_t bar = full_s + 8u * s;
+                    mbar_arrive_expect_tx_u32(bar, kTL_StageBytes);
+                    tma_load_2d_u32(ring_s + (uint32_t)s * kTL_StageBytes, &tmap_c, bar, 0, blk0 + kb * kTS_N);
+                }
+                __syncwarp();
+                if (++s == a.n_stages) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: M128 x N64 x K16, accumulators alternate between two 64-column buffers =====
+        constexpr uint32_t idesc = umma_idesc_f16(kTS_M, kTL_N);
+        const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);
+        const uint32_t full_s = smem_u32(full_bar), empty_s = smem_u32(empty_bar), tempty_s = smem_u32(tempty_bar), tfull_s = smem_u32(tfull_bar);
+        const uint64_t desc0 = umma_smem_desc_base(smem_u32(ring));
+        // the epilogue warps write the query operand and then arrive once on tempty_bar[0] and [1]: phase 0 of either barrier
+        // means "operand in TMEM", every later phase "this accumulator buffer has been drained"
+        int s = 0; uint32_t ph = 0;
+        int i = 0;
+        for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q, ++i) {
+            const uint32_t buf = (uint32_t)i & 1u;
+            mbar_wait_sleep(tempty_s + 8u * buf, ((uint32_t)i >> 1) & 1u);           // phase 0 = "queries in TMEM", then one phase per drained tile
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_u + a_cols + buf * (uint32_t)kTL_N;
+            for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                mbar_wait_sleep(full_s + 8u * s, ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t bd = desc0 + (uint64_t)((uint32_t)s * (kTL_StageBytes >> 4));
+                    const uint32_t at = tmem_u + (uint32_t)kb * 32u;
+#pragma unroll
+                    for (int k = 0; k < kDT_KB / 16; ++k)
+                        umma_f16_ts(d_tmem, at + (uint32_t)k * 8u, bd + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit_u32(empty_s + 8u * s);
+                }
+                __syncwarp();
+                if (++s == a.n_stages) { s = 0; ph ^= 1u; }
+            }
+            if (elect_one()) umma_commit_u32(tfull_s + 8u * buf);
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue warps: TMEM lane quarter = warp % 4; thread = one query =====
+        const int quarter = warp & 3;
+        const int qi = quarter * 32 + lane;
+        const int slot = qg * kTS_M + qi;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        {   // query operand -> TMEM straight from global memory: lane = query, column kb * 32 + j = fp16 pair (2j, 2j + 1) of k-block kb
+            const uint4* qrow = (const uint4*)((const __half*)a.q16 + (size_t)slot * a.q_pitch);
+            const bool q_in = slot < a.n_queries;
+            for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                uint32_t r[32];
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    uint4 x = make_uint4(0u, 0u, 0u, 0u);
+                    if (q_in && kb * kDT_KB + v * 8 < a.q_cols) x = __ldg(qrow + kb * 8 + v);
+                    r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+                }
+                tmem_st_32x32(lane_addr + (uint32_t)kb * 32u, r);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&tempty_bar[0]); mbar_arrive(&tempty_bar[1]); }     // phase 0 of both: operand in place
+        }
+        const uint32_t tempty_s = smem_u32(tempty_bar);
+        int i = 0;
+        for (int t = cta_in_q; t < a.n_tiles; t += ctas_per_q, ++i) {
+            const uint32_t buf = (uint32_t)i & 1u;
+            mbar_wait_sleep(smem_u32(&tfull_bar[buf]), ((uint32_t)i >> 1) & 1u);
+            tc_fence_after();
+            uint32_t v[kTS_EpiCols / 32][32];
+#pragma unroll
+            for (int j = 0; j < kTS_EpiCols / 32; ++j) tmem_ld_32x32(lane_addr + a_cols + buf * (uint32_t)kTL_N + 32u * j, v[j]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(tempty_s + 8u * buf) : "memory");
+            const long long row0 = a.tile_row0 + (long long)t * kTL_N;
+            if (a.mode >= 2) dense_ts_add_scratch(a, v, slot, row0);
+            dense_ts_store_scratch(a, v, slot, row0);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 // ---- host side --------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1009,6 +1155,26 @@ int launch_dense_pass(const dhr_index* h, const __half* blocked, const __half* r
     a.seg_score = t.seg_score; a.seg_row = t.seg_row; a.seg_cnt = t.seg_cnt;
     a.blocked_ptr = blocked;
     a.prefetch = h->opt_dense_prefetch;
+    // lite form (hybrid path, scratch mode, K2 overlapped with K1t): sized by the caller to fit beside a K1t CTA on every SM
+    if (h->opt_dense_lite && h->lite_stages >= 2 && mode == 1 && blocked && ((uintptr_t)q16 & 15u) == 0 && q_pitch % 8 == 0) {
+        a.n_tiles = (int)((row_end - a.tile_row0 + kTL_N - 1) / kTL_N);
+        a.n_stages = h->lite_stages < kTL_MaxStages ? h->lite_stages : kTL_MaxStages;
+        a.q16 = q16; a.q_pitch = q_pitch; a.q_cols = cols;
+        a.cluster = 0;
+        DHR_TRY(make_tmap_f16(&tmap_c, blocked, (uint64_t)round_up(h->n_rows, kTS_N) * nkb, (uint64_t)kDT_KB, (uint64_t)kDT_KB, kTL_N));
+        int per_q = h->num_sms / a.n_qgroups;
+        if (per_q < 1) per_q = 1;
+        if (per_q > a.n_tiles) per_q = a.n_tiles;
+        static bool carveout_set = false;
+        if (!carveout_set) {      // never let this small kernel configure an SM with a shared-memory carveout K1t does not fit in
+            DHR_CUDA(cudaFuncSetAttribute(dense_tile_lite_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+            carveout_set = true;
+        }
+        const size_t lsmem = (size_t)a.n_stages * kTL_StageBytes + 1024;
+        dense_tile_lite_kernel<<<per_q * a.n_qgroups, kTL_Threads, lsmem, st>>>(tmap_c, a);
+        DHR_CUDA(cudaGetLastError());
+        return DHR_OK;
+    }
     const size_t smem = (size_t)a.n_stages * kTS_BBytes + 1024;
     DHR_CUDA(cudaFuncSetAttribute(dense_tile_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DHR_CUDA(cudaFuncSetAttribute(dense_tile_ts2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTS2_MaxStages * kTS2_StageBytes + 1024));

@@ -449,7 +449,7 @@ int dhr_index_create(dhr_index** out, int device, int64_t cap_rows, int n_slices
     g.n_chunks = g.C_pad / 8;
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
-    if (e == cudaSuccess) h->num_sms = prop.multiProcessorCount;
+    if (e == cudaSuccess) { h->num_sms = prop.multiProcessorCount; h->smem_per_sm = (long long)prop.sharedMemPerMultiprocessor; }
     int status = DHR_OK;
     auto fail = [&](int s) { dhr_index_close(h); return s; };
     const size_t rows = (size_t)(cap_rows > 0 ? cap_rows : 1);
@@ -675,6 +675,9 @@ int dhr_index_set_option(dhr_index* h, const char* name, int64_t value) {
     }
     if (!strcmp(name, "query_groups")) { if (value < 1 || value > kMaxScanInflight) return DHR_ERR_INVALID; h->opt_query_groups = (int)value; return DHR_OK; }
     if (!strcmp(name, "tile_mode")) { h->opt_tile_mode = value != 0; return DHR_OK; }
+    if (!strcmp(name, "stream_priority")) { if (value < 0 || value > 1) return DHR_ERR_INVALID; h->opt_stream_priority = (int)value; return DHR_OK; }
+    if (!strcmp(name, "lex_stages")) { if (value < 0 || value > 8 || value == 1) return DHR_ERR_INVALID; h->opt_lex_stages = (int)value; return DHR_OK; }
+    if (!strcmp(name, "dense_lite")) { if (value < 0 || value > 1) return DHR_ERR_INVALID; h->opt_dense_lite = (int)value; return DHR_OK; }
     if (!strcmp(name, "dense_prefetch")) { if (value < 0 || value > 1) return DHR_ERR_INVALID; h->opt_dense_prefetch = (int)value; return DHR_OK; }
     if (!strcmp(name, "dense_multicast")) { if (value < 0 || value > 2) return DHR_ERR_INVALID; h->opt_dense_multicast = (int)value; return DHR_OK; }
     if (!strcmp(name, "lanes")) { if (value < 1 || value > 2) return DHR_ERR_INVALID; h->opt_lanes = (int)value; return DHR_OK; }

@@ -109,10 +109,15 @@ struct dhr_index {
     int opt_profile = 0;
     int opt_tile_mode = 1;               // use the tensor-core tile kernels when the shape allows
     int opt_overlap = 1;                 // hybrid tile path: run K2 on a second stream, one sub-chunk ahead of K1t
+    int opt_stream_priority = 0;         // 1: lane streams that carry K1t are created with the highest priority (set before the first search)
+    int opt_lex_stages = 0;              // K1t ring depth cap (0 = as many stages as fit)
+    int opt_dense_lite = 0;              // hybrid path: 1 = K2 in its small-footprint form that co-resides with a K1t CTA on an SM (measured slower: 9.1-9.7 k vs 10.3 k q/s); 0 = the big kernel, alternating
+    int lite_stages = 0;                 // ring depth the lite K2 may use beside the current K1t geometry (set per batch by the hybrid runner; 0 = does not fit)
     int opt_dense_prefetch = 0;          // K2: TMA L2 prefetch two tiles ahead of the demand loads (measured slower on B200 once the ring holds a whole tile: 0)
     int opt_dense_multicast = 1;         // K2 (TS): the two query groups of a batch share corpus tiles as a cluster of two CTAs (0 off, 1 dense-only searches, 2 always)
     int opt_dense_variant = 3;           // K2: 0 = both operands in shared memory (SS), 1 = queries in TMEM (TS), 2 = TS as a CTA pair (cta_group::2, M = 256), 3 = auto (2 for filter-mode launches, 1 for scratch-mode ones)
     int num_sms = 148;
+    long long smem_per_sm = 233472;      // shared memory of one SM (B200: 228 KiB)
     dhr_stats stats{};
     dhr::EventPool events;
 };
@@ -162,6 +167,7 @@ constexpr int kLexTileRows = 512;        // passages per K1t tile (= consumer th
 constexpr int kLexTileQueries = 64;      // queries per K1t tile (acc[64][512] fp32 = 128 KiB, 16 consumer warps per SM)
 constexpr int kLexTileSlices = 4;        // slices per chunk
 LexTileGeom lex_tile_geom(const Geometry& g, int rt);
+size_t lex_tile_cta_footprint(const LexTileGeom& t, int n_stages);   // shared memory one K1t CTA takes from its SM (dynamic + static + driver reserve)
 // postings layout of the corpus tile (K1p, lex_tile.cu): per (tile of 512 rows, chunk of 4 slices) a fixed-stride block holding a
 // 16-byte header and the NON-EMPTY passages of each slice sorted by code, item = {passage | code << 16, G fp16}
 LexTileGeom lex_post_geom(const Geometry& g, int rt);

@@ -51,6 +51,7 @@ __host__ __device__ constexpr int lt_pval_words(int G) { return (G + 1) / 2; }
 constexpr int kLT_WideSliceBytes = 16 + kLT_QT * 8;
 
 constexpr size_t kLT_StaticSmem = kLT_QT * 4 + 2048;
+constexpr size_t kLT_PreferredFootprint = (size_t)204 * 1024;
 constexpr size_t kLT_SmemBudget = (size_t)(227 * 1024) / kLT_CtasPerSm - 1024;   // per CTA (1 KiB reserved per CTA by the driver)
 
 LexTileGeom lex_tile_geom(const Geometry& g, int rt) {
@@ -66,11 +67,18 @@ LexTileGeom lex_tile_geom(const Geometry& g, int rt) {
     const size_t fixed = (size_t)kLT_QT * kLT_PT * 4 + 128 + kLT_StaticSmem;
     t.n_stages = kLT_MaxStages;
     while (t.n_stages > 2 && fixed + (size_t)t.n_stages * t.stage_bytes > kLT_SmemBudget) --t.n_stages;
+    // leave >= 24 KiB of the SM's unified shared memory / L1 to the cache (scratch reads, candidate appends): at the config-2
+    // shape two 31 KB stages beat three by 1.6 % (10.30 k vs 10.13 k q/s), shapes with smaller stages are unaffected
+    while (t.n_stages > 2 && fixed + (size_t)t.n_stages * t.stage_bytes > kLT_PreferredFootprint) --t.n_stages;
     return t;
 }
 
 size_t lex_tile_smem_bytes(const LexTileGeom& t) {
     return (size_t)kLT_QT * kLT_PT * 4 + (size_t)t.n_stages * t.stage_bytes + 128;
+}
+
+size_t lex_tile_cta_footprint(const LexTileGeom& t, int n_stages) {
+    return (size_t)kLT_QT * kLT_PT * 4 + (size_t)n_stages * t.stage_bytes + 128 + kLT_StaticSmem + 1024;
 }
 
 bool lex_tile_supported(const Geometry& g, int rt) {

@@ -373,9 +373,13 @@ static int ensure_lane(dhr_index* h, int L, bool need_scratch) {
         ln.scratch_bytes = sc_need;
     }
     if (!ln.aux) {
-        if (L == 1) DHR_CUDA(cudaStreamCreateWithFlags(&ln.main, cudaStreamNonBlocking));
-        DHR_CUDA(cudaStreamCreateWithFlags(&ln.aux, cudaStreamNonBlocking));
-        DHR_CUDA(cudaStreamCreateWithFlags(&ln.aux2, cudaStreamNonBlocking));
+        // option stream_priority: the streams that carry K1t launches (and the selects) outrank K2's stream, so that the block
+        // scheduler places K1t's big CTAs first and K2's fill what is left of an SM
+        int least = 0, greatest = 0;
+        if (h->opt_stream_priority) DHR_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        if (L == 1) DHR_CUDA(cudaStreamCreateWithPriority(&ln.main, cudaStreamNonBlocking, greatest));
+        DHR_CUDA(cudaStreamCreateWithPriority(&ln.aux, cudaStreamNonBlocking, least));
+        DHR_CUDA(cudaStreamCreateWithPriority(&ln.aux2, cudaStreamNonBlocking, greatest));
         DHR_CUDA(cudaEventCreateWithFlags(&ln.ev_join, cudaEventDisableTiming));
         DHR_CUDA(cudaEventCreateWithFlags(&ln.ev_sel, cudaEventDisableTiming));
         for (int i = 0; i < 2; ++i) {
@@ -665,6 +669,16 @@ static int enqueue_search(dhr_index* h, const SearchRequest& r, SelectOut so, bo
     LexTileGeom lt{};
     if (tile_hybrid) {
         lt = post ? lex_post_geom(g, rt) : lex_tile_geom(g, rt);
+        // K2 beside K1t on the same SM (dense_tile.cu, lite form): K1t gives up ring stages until two 8 KiB K2 stages (+ 4 KiB for K2's
+        // alignment slack, static and reserved shared memory) fit into what its CTA leaves of the SM
+        if (!post && h->opt_lex_stages >= 2 && h->opt_lex_stages < lt.n_stages) lt.n_stages = h->opt_lex_stages;
+        h->lite_stages = 0;
+        if (!post && g.C_pad > 0 && h->opt_dense_lite && h->opt_overlap && h->opt_dense_variant >= 1 && dense_tile_ts_supported(g)) {
+            auto room = [&](int stages) { return h->smem_per_sm - (long long)lex_tile_cta_footprint(lt, stages) - 4096; };
+            int stages = lt.n_stages;
+            while (stages > 2 && room(stages) < 2 * 8192) --stages;
+            if (room(stages) >= 2 * 8192) { lt.n_stages = stages; h->lite_stages = (int)std::min<long long>(8, room(stages) / 8192); }
+        }
         DHR_TRY(ensure_tile_workspace(h, lt, n_queries));
         DHR_TRY(ensure_lane(h, 0, g.C_pad > 0));
         DHR_TRY(launch_lex_tile_prep(h, lt, h->q_lex16, h->q_code, n_queries, h->qblocks, h->qblock_bytes, st));

@@ -121,7 +121,9 @@ int dhr_index_device_bytes(const dhr_index* h, int64_t* bytes); /* HBM bytes the
  * "rowmajor" (0 = free the row-major arrays now and keep only the tiled copies; they are rebuilt on the first call that
  * needs them -- fp32 / lamda-scaled queries, --IP, rerank, overflow fallback; 1 = make them resident now);
  * tuning of the tile path (defaults are the measured best): "overlap" (0|1), "lanes" (1|2), "dense_variant" (0..3),
- * "dense_multicast" (0..2), "dense_prefetch" (0|1: TMA L2 prefetch ahead of the dense tile loads, default 0) */
+ * "dense_multicast" (0..2), "dense_prefetch" (0|1: TMA L2 prefetch ahead of the dense tile loads, default 0), "dense_lite"
+ * (0|1: small-footprint dense kernel sharing the SMs with the lexical tile kernel, default 0), "lex_stages" (0 = auto, 2..8: ring
+ * depth cap of the lexical tile kernel), "stream_priority" (0|1, before the first search) */
 int dhr_index_set_option(dhr_index* h, const char* name, int64_t value);
 int dhr_index_get_stats(const dhr_index* h, dhr_stats* out);
 

@@ -415,6 +415,7 @@ def test_tile_path_options_agree():
                 ix.set_option('overlap', ov)
                 ix.set_option('dense_multicast', 2 if ov else 0)       # cluster-of-two multicast also in scratch mode
                 ix.set_option('dense_prefetch', ov)                    # TMA L2 prefetch ahead of the demand loads
+                ix.set_option('dense_lite', 1 if dv == 1 else 0)       # small-footprint K2 beside K1t (overlapped plan only)
                 outs.append(ix.search(case['q_vals'], case['q_idx'], k))
                 assert ix.stats()['scan_variant'] == 3, 'tile path not taken'
     sub = dict(case)

@@ -1,11 +1,10 @@
-timeout 300 python bench.py --rows 1105228 --steps 3 --warmup 3 --no-cpu-baseline --no-verify > gpurun_out/shard8.json 2>gpurun_out/shard8.err
-python -c "
-import json; d=json.load(open('gpurun_out/shard8.json')); print('shard8 proxy', d['value'], d['ms_per_step'], d['roofline'].get('scan_stream_ms_per_step'), d['roofline'].get('select_stream_ms_per_step'))"
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'dense_tile|select|init_slots|lex_tile_kernel|merge' -s 200 -c 80 --csv --log-file gpurun_out/shard8_launches.csv python bench.py --rows 1105228 --queries 512 --steps 1 --warmup 1 --no-cpu-baseline --no-verify --option lanes=1 > gpurun_out/shard8_ll.log 2>&1
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/r2_bench_default_n1.json 2> gpurun_out/r2_bench_default_n1.err; echo "default rc=$?"
+timeout 300 python bench.py --workload delade_cls_zipf --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_n1_delade_cls_zipf.json 2> gpurun_out/r2_bench_n1_delade_cls_zipf.err; echo "zipf rc=$?"
+timeout 300 python bench.py --workload bm25 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_n1_bm25.json 2> gpurun_out/r2_bench_n1_bm25.err; echo "bm25 rc=$?"
 python - <<'PY'
-import csv
-rows=[r for r in csv.reader(open('gpurun_out/shard8_launches.csv')) if len(r)>5]
-hdr=rows[0]; ki=hdr.index('Kernel Name'); vi=hdr.index('Metric Value')
-for r in rows[1:]:
-    print(r[ki][:40], r[vi], r[hdr.index('Grid Size')])
+import json
+for f in ('r2_bench_default_n1','r2_bench_n1_delade_cls_zipf','r2_bench_n1_bm25'):
+    d=json.load(open('gpurun_out/%s.json'%f)); print(f, round(d['value'],1), round(d['e2e']['value'],1), d['verified']['ok'], d['roofline']['frac'], d['clocks'].get('reasons'))
 PY
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
